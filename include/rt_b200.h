@@ -1,0 +1,319 @@
+/*
+ * rt_b200.h — C ABI of the B200-native path-tracing core for rustracer.
+ *
+ * This is the drop-in boundary.  The reference (KaminariOS/rustracer) has no
+ * FFI of its own: its `gltf_viewer` + `asset_loader` crates call the in-tree `vulkan` crate for
+ * everything that touches the GPU.  Each entry point below replaces one group of those calls and
+ * cites it.  All structs are the reference's own `#[repr(C)]` / std430 layouts, byte for byte, so a
+ * Rust host can pass its existing vectors unchanged.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure; rt_last_error() returns a
+ * thread-local message.  Inputs are copied (caller keeps ownership).  A context and the scenes
+ * created from it are not thread-safe (the reference drives Vulkan from one thread).
+ * There is no CPU fallback: if no CUDA device is usable rt_context_create fails.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Binary layouts
+ * ---------------------------------------------------------------------------------------- */
+
+/* crates/libs/asset_loader/src/geometry.rs:10-22  ==  shaders/lib/RayTracingCommons.glsl:54-63 */
+typedef struct rt_vertex {
+    float    position[4];   /* xyz, w = 0 */
+    float    normal[4];     /* xyz, w = 0 */
+    float    tangent[4];    /* xyz + handedness */
+    float    color[4];
+    float    weights[4];
+    uint32_t joints[4];
+    float    uv0[2];
+    float    uv1[2];
+    int32_t  skin_index;    /* -1 = not skinned */
+    uint32_t _pad[3];
+} rt_vertex;                /* 128 B */
+
+/* geometry.rs:65-73 == RayTracingCommons.glsl:47-52 */
+typedef struct rt_prim_info {
+    uint32_t v_offset;
+    uint32_t i_offset;
+    uint32_t material_id;
+    uint32_t _pad;
+} rt_prim_info;             /* 16 B */
+
+/* material.rs:11-17 == Material.glsl:2-5.  index -1 = none; real indices are glTF index + 1 */
+typedef struct rt_texture_info {
+    int32_t index;
+    int32_t coord;
+} rt_texture_info;
+
+/* material.rs:130-160 == Material.glsl:51-73 */
+typedef struct rt_material {
+    uint32_t        alpha_mode;          /*   0: 1 OPAQUE, 2 MASK, 3 BLEND (RayTracing.rahit:39-41) */
+    float           alpha_cutoff;        /*   4 */
+    uint32_t        double_sided;        /*   8 (never read by a shader) */
+    uint32_t        workflow;            /*  12: 0 metallic-roughness, 1 specular-glossiness */
+    float           _pad0[2];            /*  16 */
+    rt_texture_info base_color_texture;  /*  24 */
+    float           base_color[4];       /*  32 */
+    float           metallic_factor;     /*  48 */
+    float           roughness_factor;    /*  52 */
+    rt_texture_info metallic_roughness_texture; /* 56 */
+    rt_texture_info normal_texture;      /*  64 */
+    rt_texture_info emissive_texture;    /*  72 */
+    float           emissive_factor[4];  /*  80 */
+    rt_texture_info occlusion_texture;   /*  96 (unused) */
+    float           ior;                 /* 104 */
+    uint32_t        unlit;               /* 108 */
+    rt_texture_info transmission_texture;/* 112 */
+    float           transmission_factor; /* 120 */
+    uint32_t        transmission_exist;  /* 124 */
+    float           attenuation_color[3];/* 128 */
+    float           thickness_factor;    /* 140 */
+    rt_texture_info thickness_texture;   /* 144 */
+    float           attenuation_distance;/* 152 */
+    uint32_t        volume_exists;       /* 156 */
+    rt_texture_info specular_texture;    /* 160 */
+    rt_texture_info specular_color_texture; /* 168 */
+    float           specular_color_factor[4]; /* 176 */
+    float           specular_factor;     /* 192 */
+    uint32_t        specular_exist;      /* 196 */
+    float           _pad1[2];            /* 200 */
+    float           sg_diffuse_factor[4];/* 208 */
+    float           sg_specular_glossiness_factor[4]; /* 224: rgb specular, a glossiness */
+    rt_texture_info sg_diffuse_texture;  /* 240 */
+    rt_texture_info sg_specular_glossiness_texture; /* 248 */
+} rt_material;              /* 256 B */
+
+/* light.rs:62-71 == PunctualLight.glsl:8-15 */
+typedef struct rt_light {
+    float    color[4];
+    float    transform[4];  /* position (point) or direction (directional) */
+    uint32_t kind;          /* 0 directional, 1 point */
+    float    range;
+    float    intensity;
+    uint32_t _pad;
+} rt_light;                 /* 48 B */
+
+/* gltf_viewer/src/ubo.rs:3-31 == UniformBufferObject.glsl:3-30.  Matrices are column-major. */
+typedef struct rt_ubo {
+    float    model_view[16];
+    float    projection[16];
+    float    model_view_inverse[16];
+    float    projection_inverse[16];
+    float    aperture;
+    float    focus_distance;
+    float    fov_angle;
+    float    orthographic_fov_dis;
+    float    heatmap_scale;
+    uint32_t total_number_of_samples;
+    uint32_t number_of_samples;
+    uint32_t number_of_bounces;
+    uint32_t random_seed;   /* deviation D1: seeds the clockARB() surrogate */
+    uint32_t has_sky;
+    uint32_t antialiasing;
+    uint32_t mapping;
+    uint32_t frame_count;
+    uint32_t debug;
+    uint32_t fully_opaque;
+    float    exposure;
+    uint32_t tone_mapping_mode;
+} rt_ubo;                   /* 324 B */
+
+/* mapping values: RayTracingCommons.glsl:139-150 */
+enum {
+    RT_MAP_RENDER = 0, RT_MAP_HEAT = 1, RT_MAP_INSTANCE = 2, RT_MAP_TRIANGLE = 3, RT_MAP_DISTANCE = 4,
+    RT_MAP_ALBEDO = 5, RT_MAP_METALLIC = 6, RT_MAP_ROUGHNESS = 7, RT_MAP_NORMAL = 8, RT_MAP_TANGENT = 9,
+    RT_MAP_TRANSMISSION = 10, RT_MAP_GEO_ID = 11
+};
+
+#define RT_MAX_JOINTS 256   /* skinning.rs:9 ; one skin = 256 column-major mat4 = 16384 B */
+
+/* geometry.rs:38-43 (GeoBuilder.len / .opaque): one entry per glTF primitive == one BLAS */
+typedef struct rt_geometry {
+    uint32_t v_len;
+    uint32_t i_len;
+    uint32_t opaque;        /* VkGeometryFlags OPAQUE iff material alphaMode == OPAQUE */
+    uint32_t _pad;
+} rt_geometry;
+
+/* VkAccelerationStructureInstanceKHR as filled by acceleration_structures.rs:144-171 */
+typedef struct rt_instance {
+    float    transform[12]; /* object->world, 3x4 row-major */
+    uint32_t geo_id;        /* instanceCustomIndex == BLAS index */
+    uint32_t mask;          /* 0xFF */
+    uint32_t flags;
+    uint32_t _pad;
+} rt_instance;              /* 64 B */
+
+typedef struct rt_image_desc {      /* asset_loader/src/image.rs:14-23 */
+    const uint8_t* rgba8;           /* width*height*4, row 0 first */
+    uint32_t width, height;
+    uint32_t srgb;                  /* TexGamma::Srgb => 1 */
+    uint32_t _pad;
+} rt_image_desc;
+
+enum { RT_FILTER_NEAREST = 0, RT_FILTER_LINEAR = 1 };
+enum { RT_WRAP_CLAMP = 0, RT_WRAP_MIRROR = 1, RT_WRAP_REPEAT = 2 };
+
+typedef struct rt_sampler_desc {    /* asset_loader/src/texture.rs:23-29, globals.rs:362-382 */
+    uint32_t mag_filter, min_filter;
+    uint32_t wrap_s, wrap_t;
+} rt_sampler_desc;
+
+typedef struct rt_texture_desc {    /* globals.rs:336-340: [index, image_index, sampler_index] */
+    uint32_t image_index;
+    uint32_t sampler_index;
+} rt_texture_desc;
+
+typedef struct rt_scene_desc {
+    const rt_vertex*       vertices;     uint32_t n_vertices;
+    const uint32_t*        indices;      uint32_t n_indices;
+    const rt_prim_info*    prim_infos;   /* n_geometries */
+    const rt_geometry*     geometries;   uint32_t n_geometries;
+    const rt_material*     materials;    uint32_t n_materials;
+    const rt_instance*     instances;    uint32_t n_instances;
+    const rt_image_desc*   images;       uint32_t n_images;
+    const rt_sampler_desc* samplers;     uint32_t n_samplers;
+    const rt_texture_desc* textures;     uint32_t n_textures;
+    const rt_light*        dlights;      uint32_t n_dlights;
+    const rt_light*        plights;      uint32_t n_plights;
+    const float*           skins;        uint32_t n_skins;     /* n_skins * 256 * 16 floats */
+    const uint8_t*         skybox_faces[6];                    /* +x,-x,+y,-y,+z,-z ; may be NULL */
+    uint32_t               skybox_width, skybox_height, skybox_srgb;
+    uint32_t               _pad;
+} rt_scene_desc;
+
+/* ------------------------------------------------------------------------------------------
+ * Parity-test records (new; SURVEY.md §8b last rows)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rt_ray {
+    float origin[3]; float tmin;
+    float direction[3]; float tmax;
+} rt_ray;                   /* 32 B */
+
+typedef struct rt_hit {
+    float    t;             /* < 0 on miss */
+    float    u, v;          /* barycentric weights of vertex 1 and vertex 2 (gl HitAttributes) */
+    uint32_t instance_id;   /* gl_InstanceID ; 0xFFFFFFFF on miss */
+    uint32_t primitive_id;  /* gl_PrimitiveID */
+    uint32_t geo_id;        /* gl_InstanceCustomIndexEXT */
+} rt_hit;                   /* 24 B */
+
+enum {
+    RT_TRACE_OPAQUE = 1     /* gl_RayFlagsOpaqueEXT: never run the alpha test */
+};
+
+typedef struct rt_stats {
+    float    ms_total, ms_raygen, ms_extend, ms_shade, ms_shadow, ms_accum;
+    uint32_t n_extend_launches, n_kernel_launches;
+    uint64_t rays_extend;   /* path segments traced (every primary traceRayEXT equivalent) */
+    uint64_t rays_shadow;   /* shadow rays traced */
+    uint64_t shaded_hits;
+    uint64_t pixel_samples;
+    /* traversal counters, only filled when RT_RENDER_COUNTERS was requested */
+    uint64_t nodes, tris, insts, anyhits, tex_taps, light_cands;
+} rt_stats;
+
+enum {
+    RT_RENDER_COUNTERS   = 1,   /* count nodes/tris/instances visited (slower; for the bytes/ray figure) */
+    RT_RENDER_NO_TONEMAP = 2    /* skip the RGBA8 pass (used by sample-pass sharding before the reduce) */
+};
+
+typedef struct rt_render_opts {
+    uint32_t flags;
+    /* tile partition: rows are cut into strips of strip_rows; this context renders
+       strips with (strip % n_parts) == part.  n_parts = 0 or 1 => whole frame. */
+    uint32_t strip_rows, n_parts, part;
+} rt_render_opts;
+
+typedef struct rt_context rt_context;
+typedef struct rt_scene   rt_scene;
+
+/* ------------------------------------------------------------------------------------------
+ * Entry points
+ * ---------------------------------------------------------------------------------------- */
+const char* rt_last_error(void);
+const char* rt_version(void);
+
+/* replaces ContextBuilder::build (vulkan/src/context.rs:88-179) + BaseApp::new image creation
+   (app/src/lib.rs:305-325).  device = CUDA ordinal. */
+int rt_context_create(int device, uint32_t width, uint32_t height, rt_context** out);
+void rt_context_destroy(rt_context* ctx);
+/* replaces BaseApp::recreate_swapchain (app/src/lib.rs:355-385): drops the accumulation */
+int rt_frame_resize(rt_context* ctx, uint32_t width, uint32_t height);
+
+/* replaces create_global + Buffers::new (asset_loader/src/globals.rs:309,43), create_as
+   (acceleration_structures.rs:79-129), create_pipeline + SBT (gltf_viewer/src/pipeline_res.rs:21),
+   create_descriptor_sets (desc_sets.rs:21) and the initial ComputeUnit::dispatch (main.rs:85-91) */
+int rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out);
+void rt_scene_destroy(rt_scene* scene);
+
+/* replaces create_top_as + update_tlas (acceleration_structures.rs:136 ; main.rs:397-409,424-436) */
+int rt_scene_update_instances(rt_scene* scene, const rt_instance* instances, uint32_t n);
+/* replaces skin.copy_data_to_buffer + ComputeUnit::dispatch + create_as (main.rs:384-395,
+   compute_unit.rs:30-68): skinning kernel, BLAS refit (rebuild != 0: full rebuild), TLAS rebuild */
+int rt_scene_update_skins(rt_scene* scene, const float* skin_mats, uint32_t n_skins, int rebuild);
+/* replaces dlights_buffer / plights_buffer.copy_data_to_buffer (main.rs:353-374) */
+int rt_scene_update_lights(rt_scene* scene, const rt_light* dlights, uint32_t n_dlights,
+                           const rt_light* plights, uint32_t n_plights);
+/* replaces SkyboxResource::new + update_desc (globals.rs:175-199 ; main.rs:346-350) */
+int rt_scene_set_skybox(rt_scene* scene, const uint8_t* const faces[6], uint32_t width,
+                        uint32_t height, uint32_t srgb);
+
+/* replaces ubo_buffer.copy_data_to_buffer + bind_* + trace_rays (main.rs:239,254-267): one frame of
+   ubo->number_of_samples spp at ubo->number_of_bounces depth, accumulated per RayTracing.rgen:132-166.
+   opts may be NULL.  stream is a cudaStream_t or NULL (context's own stream).  Asynchronous. */
+int rt_render(rt_context* ctx, rt_scene* scene, const rt_ubo* ubo, const rt_render_opts* opts,
+              void* stream);
+/* accumulate+tonemap only (RayTracing.rgen:132-166 tail) over the current accumulation image;
+   used after a cross-GPU reduce of the accumulation buffer. */
+int rt_tonemap(rt_context* ctx, const rt_ubo* ubo, void* stream);
+int rt_synchronize(rt_context* ctx);
+
+/* replaces the storage-image -> swapchain copy (app/src/lib.rs:563-611).  Either may be NULL.
+   Synchronises the context first. */
+int rt_readback(rt_context* ctx, float* acc_rgba32f, uint8_t* out_rgba8);
+int rt_upload_accumulation(rt_context* ctx, const float* acc_rgba32f);     /* resume */
+/* zero-copy interop: device pointers of the RGBA32F accumulation and RGBA8 output images */
+int rt_device_ptrs(rt_context* ctx, void** acc, void** out);
+/* replaces the GPU timestamp queries (app/src/lib.rs:549-555,652-656).  Synchronises. */
+int rt_last_frame_stats(rt_context* ctx, rt_stats* stats);
+
+/* parity-test entry points (no reference equivalent: traversal lives in the Vulkan driver).
+   rng4: optional n x uvec4 payload RNG state used by the BLEND alpha test (NULL = zeros). */
+int rt_trace_closest(rt_scene* scene, const rt_ray* rays, uint32_t n, uint32_t flags,
+                     const uint32_t* rng4, rt_hit* hits);
+int rt_trace_any(rt_scene* scene, const rt_ray* rays, uint32_t n, uint32_t flags,
+                 const uint32_t* rng4, uint8_t* occluded);
+/* read back the (skinned) vertex buffer the BLASes were built from (AnimationCompute.comp output) */
+int rt_scene_read_vertices(rt_scene* scene, rt_vertex* out, uint32_t n);
+/* BVH statistics for DESIGN/bench: nodes, max depth, bytes */
+typedef struct rt_bvh_info {
+    uint64_t blas_nodes, blas_tris, tlas_nodes, bytes;
+    uint32_t max_depth_blas, max_depth_tlas;
+    float    build_ms, refit_ms, skin_ms, tlas_ms;
+} rt_bvh_info;
+int rt_scene_bvh_info(rt_scene* scene, rt_bvh_info* info);
+
+/* multi-GPU (new): cross-process peer access to the accumulation image.
+   rt_ipc_export writes a 64-byte cudaIpcMemHandle; rt_ipc_open maps a peer's handle and returns
+   the device pointer in this process; rt_reduce_peers sums peers' accumulation images into this
+   context's rows [row0,row1) and tonemaps them (fused reduce + tonemap over NVLink peer loads). */
+int rt_ipc_export(rt_context* ctx, void* handle64);
+int rt_ipc_open(rt_context* ctx, const void* handle64, void** peer_acc);
+int rt_ipc_close(rt_context* ctx, void* peer_acc);
+int rt_reduce_peers(rt_context* ctx, void* const* peer_acc, uint32_t n_peers, const rt_ubo* ubo,
+                    uint32_t row0, uint32_t row1, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */
