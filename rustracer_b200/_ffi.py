@@ -222,6 +222,48 @@ def load_host() -> C.CDLL:
     return _host
 
 
+def bind_rt(lib: C.CDLL, rename=lambda n: n, optional=()) -> C.CDLL:
+    """Attach argument/return types for the rt_* entry points of include/rt_b200.h to `lib`."""
+    vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+    sigs = {
+        "rt_last_error": ([], C.c_char_p), "rt_version": ([], C.c_char_p),
+        "rt_context_create": ([C.c_int, c_u32, c_u32, vpp], C.c_int),
+        "rt_context_destroy": ([vp], None),
+        "rt_frame_resize": ([vp, c_u32, c_u32], C.c_int),
+        "rt_scene_create": ([vp, C.POINTER(rt_scene_desc), vpp], C.c_int),
+        "rt_scene_destroy": ([vp], None),
+        "rt_scene_update_instances": ([vp, C.POINTER(rt_instance), c_u32], C.c_int),
+        "rt_scene_update_skins": ([vp, C.POINTER(c_f), c_u32, C.c_int], C.c_int),
+        "rt_scene_update_lights": ([vp, C.POINTER(rt_light), c_u32, C.POINTER(rt_light), c_u32], C.c_int),
+        "rt_scene_set_skybox": ([vp, c_u8p * 6, c_u32, c_u32, c_u32], C.c_int),
+        "rt_render": ([vp, vp, C.POINTER(rt_ubo), C.POINTER(rt_render_opts), vp], C.c_int),
+        "rt_tonemap": ([vp, C.POINTER(rt_ubo), vp], C.c_int),
+        "rt_synchronize": ([vp], C.c_int),
+        "rt_readback": ([vp, C.POINTER(c_f), c_u8p], C.c_int),
+        "rt_upload_accumulation": ([vp, C.POINTER(c_f)], C.c_int),
+        "rt_device_ptrs": ([vp, vpp, vpp], C.c_int),
+        "rt_last_frame_stats": ([vp, C.POINTER(rt_stats)], C.c_int),
+        "rt_trace_closest": ([vp, C.POINTER(rt_ray), c_u32, c_u32, C.POINTER(c_u32), C.POINTER(rt_hit)], C.c_int),
+        "rt_trace_any": ([vp, C.POINTER(rt_ray), c_u32, c_u32, C.POINTER(c_u32), c_u8p], C.c_int),
+        "rt_scene_read_vertices": ([vp, C.POINTER(rt_vertex), c_u32], C.c_int),
+        "rt_scene_bvh_info": ([vp, C.POINTER(rt_bvh_info)], C.c_int),
+        "rt_ipc_export": ([vp, vp], C.c_int),
+        "rt_ipc_open": ([vp, vp, vpp], C.c_int),
+        "rt_ipc_close": ([vp, vp], C.c_int),
+        "rt_reduce_peers": ([vp, vpp, c_u32, C.POINTER(rt_ubo), c_u32, c_u32, vp], C.c_int),
+    }
+    assert set(sigs) == set(RT_EXPORTS)
+    for name, (args, res) in sigs.items():
+        try:
+            fn = getattr(lib, rename(name))
+        except AttributeError:
+            if name in optional:
+                continue
+            raise
+        fn.argtypes, fn.restype = args, res
+    return lib
+
+
 def load_rt() -> C.CDLL:
     """Load the CUDA core.  Raises (never falls back) when the extension has not been built."""
     global _rt
@@ -229,37 +271,7 @@ def load_rt() -> C.CDLL:
         if not RT_LIB.exists():
             raise RuntimeError(f"CUDA extension missing: {RT_LIB} — build it with __graft_entry__.build(); "
                                "rustracer_b200 has no CPU fallback")
-        lib = C.CDLL(str(RT_LIB), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
-        vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
-        lib.rt_last_error.restype = C.c_char_p
-        lib.rt_version.restype = C.c_char_p
-        lib.rt_context_create.argtypes = [C.c_int, c_u32, c_u32, vpp]
-        lib.rt_context_destroy.argtypes = [vp]
-        lib.rt_context_destroy.restype = None
-        lib.rt_frame_resize.argtypes = [vp, c_u32, c_u32]
-        lib.rt_scene_create.argtypes = [vp, C.POINTER(rt_scene_desc), vpp]
-        lib.rt_scene_destroy.argtypes = [vp]
-        lib.rt_scene_destroy.restype = None
-        lib.rt_scene_update_instances.argtypes = [vp, C.POINTER(rt_instance), c_u32]
-        lib.rt_scene_update_skins.argtypes = [vp, C.POINTER(c_f), c_u32, C.c_int]
-        lib.rt_scene_update_lights.argtypes = [vp, C.POINTER(rt_light), c_u32, C.POINTER(rt_light), c_u32]
-        lib.rt_scene_set_skybox.argtypes = [vp, c_u8p * 6, c_u32, c_u32, c_u32]
-        lib.rt_render.argtypes = [vp, vp, C.POINTER(rt_ubo), C.POINTER(rt_render_opts), vp]
-        lib.rt_tonemap.argtypes = [vp, C.POINTER(rt_ubo), vp]
-        lib.rt_synchronize.argtypes = [vp]
-        lib.rt_readback.argtypes = [vp, C.POINTER(c_f), c_u8p]
-        lib.rt_upload_accumulation.argtypes = [vp, C.POINTER(c_f)]
-        lib.rt_device_ptrs.argtypes = [vp, vpp, vpp]
-        lib.rt_last_frame_stats.argtypes = [vp, C.POINTER(rt_stats)]
-        lib.rt_trace_closest.argtypes = [vp, C.POINTER(rt_ray), c_u32, c_u32, C.POINTER(c_u32), C.POINTER(rt_hit)]
-        lib.rt_trace_any.argtypes = [vp, C.POINTER(rt_ray), c_u32, c_u32, C.POINTER(c_u32), c_u8p]
-        lib.rt_scene_read_vertices.argtypes = [vp, C.POINTER(rt_vertex), c_u32]
-        lib.rt_scene_bvh_info.argtypes = [vp, C.POINTER(rt_bvh_info)]
-        lib.rt_ipc_export.argtypes = [vp, vp]
-        lib.rt_ipc_open.argtypes = [vp, vp, vpp]
-        lib.rt_ipc_close.argtypes = [vp, vp]
-        lib.rt_reduce_peers.argtypes = [vp, vpp, c_u32, C.POINTER(rt_ubo), c_u32, c_u32, vp]
-        _rt = lib
+        _rt = bind_rt(C.CDLL(str(RT_LIB)))
     return _rt
 
 

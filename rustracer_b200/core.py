@@ -1,0 +1,160 @@
+"""Python view of the C ABI (include/rt_b200.h): Context / Scene / render / readback / trace.
+
+This is the call surface a host uses in place of the reference's Vulkan calls.  It binds the
+CUDA library built from rustracer_b200/csrc; if that library is missing, construction raises — there is no
+CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi as F
+
+
+class RtError(RuntimeError):
+    pass
+
+
+class Api:
+    """Function table over a loaded library exporting the rt_* entry points."""
+
+    def __init__(self, lib: C.CDLL | None = None, rename=lambda n: n):
+        self.lib = lib if lib is not None else F.load_rt()
+        self._rename = rename
+
+    def __getattr__(self, name):
+        if name.startswith("rt_"):
+            return getattr(self.lib, self._rename(name))
+        raise AttributeError(name)
+
+    def check(self, rc: int):
+        if rc:
+            raise RtError(self.rt_last_error().decode())
+
+
+class Context:
+    """Replaces vulkan::Context + the storage / accumulation images of BaseApp."""
+
+    def __init__(self, width: int, height: int, device: int = 0, api: Api | None = None):
+        self.api = api or Api()
+        self.width, self.height = width, height
+        self._h = C.c_void_p()
+        self.api.check(self.api.rt_context_create(device, width, height, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.api.rt_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def resize(self, width: int, height: int):
+        self.api.check(self.api.rt_frame_resize(self._h, width, height))
+        self.width, self.height = width, height
+
+    def render(self, scene: "Scene", ubo: F.rt_ubo, flags: int = 0, strip_rows: int = 0, n_parts: int = 0, part: int = 0,
+               stream=None):
+        opts = F.rt_render_opts(flags, strip_rows, n_parts, part)
+        self.api.check(self.api.rt_render(self._h, scene._h, C.byref(ubo), C.byref(opts), stream))
+
+    def tonemap(self, ubo: F.rt_ubo, stream=None):
+        self.api.check(self.api.rt_tonemap(self._h, C.byref(ubo), stream))
+
+    def synchronize(self):
+        self.api.check(self.api.rt_synchronize(self._h))
+
+    def readback(self, want_acc: bool = True, want_out: bool = True, acc_buf=None, out_buf=None):
+        acc = out = None
+        if want_acc:
+            acc = acc_buf if acc_buf is not None else np.empty((self.height, self.width, 4), np.float32)
+        if want_out:
+            out = out_buf if out_buf is not None else np.empty((self.height, self.width, 4), np.uint8)
+        self.api.check(self.api.rt_readback(self._h, F.as_ptr(acc, F.c_f) if acc is not None else None,
+                                            out.ctypes.data_as(F.c_u8p) if out is not None else None))
+        return acc, out
+
+    def upload_accumulation(self, acc: np.ndarray):
+        acc = np.ascontiguousarray(acc, np.float32)
+        assert acc.shape == (self.height, self.width, 4)
+        self.api.check(self.api.rt_upload_accumulation(self._h, F.as_ptr(acc, F.c_f)))
+
+    def device_ptrs(self):
+        a, o = C.c_void_p(), C.c_void_p()
+        self.api.check(self.api.rt_device_ptrs(self._h, C.byref(a), C.byref(o)))
+        return a.value, o.value
+
+    def stats(self) -> F.rt_stats:
+        st = F.rt_stats()
+        self.api.check(self.api.rt_last_frame_stats(self._h, C.byref(st)))
+        return st
+
+
+class Scene:
+    """Replaces create_global + Buffers::new + create_as + pipeline/descriptor setup."""
+
+    def __init__(self, ctx: Context, desc: F.rt_scene_desc):
+        self.ctx, self.api = ctx, ctx.api
+        self._h = C.c_void_p()
+        self.n_vertices = desc.n_vertices
+        self.api.check(self.api.rt_scene_create(ctx._h, C.byref(desc), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.api.rt_scene_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def update_instances(self, inst: np.ndarray):
+        inst = np.ascontiguousarray(inst, F.INSTANCE_DTYPE)
+        self.api.check(self.api.rt_scene_update_instances(self._h, F.as_ptr(inst, F.rt_instance), len(inst)))
+
+    def update_skins(self, mats: np.ndarray, rebuild: bool = False):
+        mats = np.ascontiguousarray(mats, np.float32)
+        self.api.check(self.api.rt_scene_update_skins(self._h, F.as_ptr(mats, F.c_f), mats.size // 4096, int(rebuild)))
+
+    def update_lights(self, dlights: np.ndarray, plights: np.ndarray):
+        d = np.ascontiguousarray(dlights, F.LIGHT_DTYPE)
+        p = np.ascontiguousarray(plights, F.LIGHT_DTYPE)
+        self.api.check(self.api.rt_scene_update_lights(self._h, F.as_ptr(d, F.rt_light), len(d), F.as_ptr(p, F.rt_light), len(p)))
+
+    def set_skybox(self, faces, srgb: bool = True):
+        faces = [np.ascontiguousarray(f, np.uint8) for f in faces]
+        h, w = faces[0].shape[:2]
+        arr = (F.c_u8p * 6)(*[f.ctypes.data_as(F.c_u8p) for f in faces])
+        self.api.check(self.api.rt_scene_set_skybox(self._h, arr, w, h, int(srgb)))
+
+    def _rng(self, rng4, n):
+        if rng4 is None:
+            return None, None
+        a = np.ascontiguousarray(rng4, np.uint32).reshape(n, 4)
+        return a, F.as_ptr(a, F.c_u32)
+
+    def trace_closest(self, rays: np.ndarray, flags: int = 0, rng4=None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, F.RAY_DTYPE)
+        hits = np.zeros(len(rays), F.HIT_DTYPE)
+        keep, rp = self._rng(rng4, len(rays))
+        self.api.check(self.api.rt_trace_closest(self._h, F.as_ptr(rays, F.rt_ray), len(rays), flags, rp, F.as_ptr(hits, F.rt_hit)))
+        return hits
+
+    def trace_any(self, rays: np.ndarray, flags: int = 0, rng4=None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, F.RAY_DTYPE)
+        occ = np.zeros(len(rays), np.uint8)
+        keep, rp = self._rng(rng4, len(rays))
+        self.api.check(self.api.rt_trace_any(self._h, F.as_ptr(rays, F.rt_ray), len(rays), flags, rp, occ.ctypes.data_as(F.c_u8p)))
+        return occ
+
+    def read_vertices(self, n: int | None = None) -> np.ndarray:
+        n = self.n_vertices if n is None else n
+        v = np.zeros(n, F.VERTEX_DTYPE)
+        self.api.check(self.api.rt_scene_read_vertices(self._h, F.as_ptr(v, F.rt_vertex), n))
+        return v
+
+    def bvh_info(self) -> F.rt_bvh_info:
+        info = F.rt_bvh_info()
+        self.api.check(self.api.rt_scene_bvh_info(self._h, C.byref(info)))
+        return info

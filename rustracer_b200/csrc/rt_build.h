@@ -1,0 +1,357 @@
+// rt_build.h — GPU BVH builder: Morton codes -> radix sort -> Karras LBVH -> bottom-up AABB fit ->
+// surface-area-guided collapse to 8-wide nodes with quantised child boxes (80 B/node), plus bottom-up refit.
+// Replaces vkCmdBuildAccelerationStructuresKHR (crates/libs/vulkan/src/ray_tracing/acceleration_structure.rs:95-173)
+// as driven by create_as / create_top_as (crates/libs/asset_loader/src/acceleration_structures.rs:79-249).
+// The same builder serves BLASes (primitives = triangles) and the TLAS (primitives = instance boxes).
+#pragma once
+#include "rt_scene_dev.h"
+
+struct DAabb { float lo[3], hi[3]; };
+
+RT_D float aabb_half_area(const DAabb& b) {
+    const float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+    return ex * ey + ey * ez + ez * ex;
+}
+RT_D DAabb aabb_union(const DAabb& a, const DAabb& b) {
+    DAabb r;
+    for (int k = 0; k < 3; ++k) { r.lo[k] = fminf(a.lo[k], b.lo[k]); r.hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+    return r;
+}
+RT_D uint32_t float_to_ordered(float f) { uint32_t u = rt_float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+RT_D float ordered_to_float(uint32_t u) { return rt_uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+
+RT_D uint64_t expand21(uint32_t v) {
+    uint64_t x = v & 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+struct BuildScratch {
+    size_t capacity = 0;        // primitives
+    uint64_t *keys = nullptr, *keys_tmp = nullptr;
+    uint32_t *vals = nullptr, *vals_tmp = nullptr;
+    int2* bin_children = nullptr;     // n-1 internal nodes: child ids (internal k -> k, leaf k -> n-1+k)
+    uint32_t* bin_parent = nullptr;   // 2n-1
+    DAabb* bin_box = nullptr;         // 2n-1
+    uint2* bin_range = nullptr;       // n-1: [first,last] sorted-primitive range of each internal node
+    uint32_t* flags = nullptr;        // n-1
+    uint32_t* bounds = nullptr;       // 6 ordered-uint centroid bounds
+    uint2 *q_a = nullptr, *q_b = nullptr;   // collapse work queues: (binary node, wide node)
+    uint32_t* counters = nullptr;     // [0] wide nodes, [1] primitives emitted, [2] next queue size
+};
+
+inline int scratch_reserve(BuildScratch& s, size_t n) {
+    if (n <= s.capacity) return 0;
+    void** ptrs[] = {(void**)&s.keys, (void**)&s.keys_tmp, (void**)&s.vals, (void**)&s.vals_tmp, (void**)&s.bin_children, (void**)&s.bin_parent,
+                     (void**)&s.bin_box, (void**)&s.bin_range, (void**)&s.flags, (void**)&s.bounds, (void**)&s.q_a, (void**)&s.q_b, (void**)&s.counters};
+    for (void** p : ptrs) { if (*p) rt_free(*p); *p = nullptr; }
+    size_t cap = n + n / 4 + 16;
+    int e = 0;
+    e |= rt_malloc((void**)&s.keys, cap * 8); e |= rt_malloc((void**)&s.keys_tmp, cap * 8);
+    e |= rt_malloc((void**)&s.vals, cap * 4); e |= rt_malloc((void**)&s.vals_tmp, cap * 4);
+    e |= rt_malloc((void**)&s.bin_children, cap * sizeof(int2)); e |= rt_malloc((void**)&s.bin_parent, 2 * cap * 4);
+    e |= rt_malloc((void**)&s.bin_box, 2 * cap * sizeof(DAabb)); e |= rt_malloc((void**)&s.bin_range, cap * sizeof(uint2));
+    e |= rt_malloc((void**)&s.flags, cap * 4); e |= rt_malloc((void**)&s.bounds, 64);
+    e |= rt_malloc((void**)&s.q_a, cap * sizeof(uint2)); e |= rt_malloc((void**)&s.q_b, cap * sizeof(uint2));
+    e |= rt_malloc((void**)&s.counters, 64);
+    s.capacity = e ? 0 : cap;
+    return e;
+}
+inline void scratch_free(BuildScratch& s) {
+    void** ptrs[] = {(void**)&s.keys, (void**)&s.keys_tmp, (void**)&s.vals, (void**)&s.vals_tmp, (void**)&s.bin_children, (void**)&s.bin_parent,
+                     (void**)&s.bin_box, (void**)&s.bin_range, (void**)&s.flags, (void**)&s.bounds, (void**)&s.q_a, (void**)&s.q_b, (void**)&s.counters};
+    for (void** p : ptrs) { if (*p) rt_free(*p); *p = nullptr; }
+    s.capacity = 0;
+}
+
+// ---- Karras 2012 -------------------------------------------------------------------------------------
+RT_D int lbvh_delta(const uint64_t* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + rt_clz32((uint32_t)i ^ (uint32_t)j);
+    return rt_clz64(a ^ b);
+}
+RT_D void lbvh_build_node(const uint64_t* keys, int n, int i, int2* children, uint32_t* parent, uint2* range) {
+    const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    const int gamma = i + s * d + (d < 0 ? d : 0);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const int left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    children[i] = make_int2(left, right);
+    parent[left] = (uint32_t)i; parent[right] = (uint32_t)i;
+    range[i] = make_uint2((uint32_t)lo, (uint32_t)hi);
+    if (i == 0) parent[0] = 0xFFFFFFFFu;
+}
+
+// ---- wide node emission --------------------------------------------------------------------------------
+struct WideOut {
+    float4* nodes;          // RT_NODE_F4 per node (indices local to this BVH)
+    uint32_t* prim_order;   // leaf-order -> source primitive index
+    DAabb* node_box;        // unquantised box per wide node (refit / TLAS input)
+    uint32_t* node_parent;  // parent wide node (0xFFFFFFFF for the root)
+    uint32_t max_nodes;
+};
+
+RT_D uint32_t pack4(const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); }
+
+// Quantise and write one wide node.  child_box[i] valid for meta[i] != 0.  Conservative: the de-quantised box
+// always contains the child box (checked in double precision).
+RT_D void write_wide_node(float4* node, const DAabb& box, const DAabb* child_box, const uint32_t* meta, uint32_t imask,
+                          uint32_t child_base, uint32_t prim_base) {
+    int ex[3]; double scale[3];
+    for (int a = 0; a < 3; ++a) {
+        const double ext = (double)box.hi[a] - (double)box.lo[a];
+        int e = -100;
+        if (ext > 0.0) { int fe; frexp(ext / 255.0, &fe); e = fe; if (e < -100) e = -100; }   // 2^e >= ext/255
+        for (;;) {
+            const double sc = ldexp(1.0, e);
+            bool ok = true;
+            for (int i = 0; i < 8 && ok; ++i) {
+                if (!meta[i]) continue;
+                if (ceil(((double)child_box[i].hi[a] - (double)box.lo[a]) / sc) > 255.0) ok = false;
+            }
+            if (ok) break;
+            ++e;
+        }
+        ex[a] = e; scale[a] = ldexp(1.0, e);
+    }
+    uint32_t qlo[3][8], qhi[3][8];
+    for (int i = 0; i < 8; ++i) {
+        for (int a = 0; a < 3; ++a) {
+            if (!meta[i]) { qlo[a][i] = 255; qhi[a][i] = 0; continue; }
+            double lo = floor(((double)child_box[i].lo[a] - (double)box.lo[a]) / scale[a]);
+            double hi = ceil(((double)child_box[i].hi[a] - (double)box.lo[a]) / scale[a]);
+            if (lo < 0.0) lo = 0.0; if (lo > 255.0) lo = 255.0;
+            if (hi < 0.0) hi = 0.0; if (hi > 255.0) hi = 255.0;
+            qlo[a][i] = (uint32_t)lo; qhi[a][i] = (uint32_t)hi;
+        }
+    }
+    const uint32_t e_imask = (uint32_t)((ex[0] + 127) & 0xFF) | ((uint32_t)((ex[1] + 127) & 0xFF) << 8) | ((uint32_t)((ex[2] + 127) & 0xFF) << 16) | (imask << 24);
+    node[0] = make_float4(box.lo[0], box.lo[1], box.lo[2], rt_uint_as_float(e_imask));
+    node[1] = make_float4(rt_uint_as_float(child_base), rt_uint_as_float(prim_base), rt_uint_as_float(pack4(meta)), rt_uint_as_float(pack4(meta + 4)));
+    node[2] = make_float4(rt_uint_as_float(pack4(qlo[0])), rt_uint_as_float(pack4(qlo[0] + 4)), rt_uint_as_float(pack4(qlo[1])), rt_uint_as_float(pack4(qlo[1] + 4)));
+    node[3] = make_float4(rt_uint_as_float(pack4(qlo[2])), rt_uint_as_float(pack4(qlo[2] + 4)), rt_uint_as_float(pack4(qhi[0])), rt_uint_as_float(pack4(qhi[0] + 4)));
+    node[4] = make_float4(rt_uint_as_float(pack4(qhi[1])), rt_uint_as_float(pack4(qhi[1] + 4)), rt_uint_as_float(pack4(qhi[2])), rt_uint_as_float(pack4(qhi[2] + 4)));
+}
+
+// One collapse work item: binary subtree `bin` becomes wide node `wide`.
+RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, const uint2* bin_range, const uint32_t* vals,
+                        uint32_t bin, uint32_t wide, uint32_t parent_wide, WideOut out, uint32_t* counters, uint2* q_out) {
+    auto count_of = [&](uint32_t c) -> uint32_t { return c >= (uint32_t)(n - 1) ? 1u : (bin_range[c].y - bin_range[c].x + 1u); };
+    auto first_of = [&](uint32_t c) -> uint32_t { return c >= (uint32_t)(n - 1) ? (c - (uint32_t)(n - 1)) : bin_range[c].x; };
+    uint32_t ch[8]; int nch = 0;
+    if (n == 1 || count_of(bin) <= RT_LEAF_MAX) { ch[nch++] = bin; }
+    else { ch[nch++] = (uint32_t)bin_children[bin].x; ch[nch++] = (uint32_t)bin_children[bin].y; }
+    // greedy: open the child with the largest surface area until 8 children or nothing left to open
+    while (nch < 8) {
+        int best = -1; float best_area = -1.0f;
+        for (int i = 0; i < nch; ++i) {
+            if (count_of(ch[i]) <= RT_LEAF_MAX) continue;
+            const float a = aabb_half_area(bin_box[ch[i]]);
+            if (a > best_area) { best_area = a; best = i; }
+        }
+        if (best < 0) break;
+        const int2 c = bin_children[ch[best]];
+        ch[best] = (uint32_t)c.x; ch[nch++] = (uint32_t)c.y;
+    }
+    const DAabb box = (n == 1) ? bin_box[0] : bin_box[bin];
+    // slot assignment: slot s is visited first by rays travelling in the negative direction of the axes whose bit
+    // is set in s, so it should hold the child lying furthest towards +axis on those axes (greedy max-cost matching)
+    const float cx = 0.5f * (box.lo[0] + box.hi[0]), cy = 0.5f * (box.lo[1] + box.hi[1]), cz = 0.5f * (box.lo[2] + box.hi[2]);
+    float cost[8][8];
+    for (int i = 0; i < nch; ++i) {
+        const DAabb& b = bin_box[ch[i]];
+        const float dx = 0.5f * (b.lo[0] + b.hi[0]) - cx, dy = 0.5f * (b.lo[1] + b.hi[1]) - cy, dz = 0.5f * (b.lo[2] + b.hi[2]) - cz;
+        for (int s = 0; s < 8; ++s) cost[i][s] = ((s & 4) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 1) ? dz : -dz);
+    }
+    int slot_child[8]; for (int s = 0; s < 8; ++s) slot_child[s] = -1;
+    bool used[8] = {false, false, false, false, false, false, false, false};
+    for (int k = 0; k < nch; ++k) {
+        int bi = -1, bs = -1; float bc = -3.0e38f;
+        for (int i = 0; i < nch; ++i) {
+            if (used[i]) continue;
+            for (int s = 0; s < 8; ++s) if (slot_child[s] < 0 && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+        }
+        used[bi] = true; slot_child[bs] = bi;
+    }
+    // emit
+    uint32_t n_inner = 0, n_prims = 0;
+    for (int s = 0; s < 8; ++s) {
+        if (slot_child[s] < 0) continue;
+        const uint32_t c = ch[slot_child[s]], cnt = count_of(c);
+        if (cnt <= RT_LEAF_MAX) n_prims += cnt; else n_inner++;
+    }
+    const uint32_t child_base = n_inner ? rt_atomic_add(&counters[0], n_inner) : 0u;
+    const uint32_t prim_base = n_prims ? rt_atomic_add(&counters[1], n_prims) : 0u;
+    uint32_t meta[8]; DAabb cbox[8]; uint32_t imask = 0, inner_rank = 0, prim_off = 0;
+    for (int s = 0; s < 8; ++s) {
+        meta[s] = 0;
+        if (slot_child[s] < 0) continue;
+        const uint32_t c = ch[slot_child[s]], cnt = count_of(c);
+        cbox[s] = (n == 1) ? bin_box[0] : bin_box[c];
+        if (cnt <= RT_LEAF_MAX) {
+            const uint32_t first = first_of(c);
+            for (uint32_t k = 0; k < cnt; ++k) out.prim_order[prim_base + prim_off + k] = vals[first + k];
+            meta[s] = (((1u << cnt) - 1u) << 5) | prim_off;   // unary count | first offset
+            prim_off += cnt;
+        } else {
+            const uint32_t w = child_base + inner_rank;
+            if (w < out.max_nodes) {
+                const uint32_t qi = rt_atomic_add(&counters[2], 1u);
+                q_out[qi] = make_uint2(c, w);
+                out.node_parent[w] = wide;
+            }
+            meta[s] = (1u << 5) | (24u + (uint32_t)s);
+            imask |= 1u << s; inner_rank++;
+        }
+    }
+    out.node_box[wide] = box;
+    if (parent_wide == 0xFFFFFFFFu) out.node_parent[wide] = 0xFFFFFFFFu;
+    write_wide_node(out.nodes + (size_t)wide * RT_NODE_F4, box, cbox, meta, imask, child_base, prim_base);
+}
+
+struct WideBvhInfo { uint32_t n_nodes = 0, n_prims = 0, depth = 0; };
+
+// Builds an 8-wide BVH over n primitive boxes (device pointer).  Synchronises the stream once per tree level.
+inline int build_wide_bvh(const DAabb* prim_boxes, uint32_t n, BuildScratch& sc, WideOut out, rt_stream_t stream, WideBvhInfo* info) {
+    info->n_nodes = 0; info->n_prims = n; info->depth = 0;
+    if (n == 0) {
+        // empty BVH: one root node with no children
+        DAabb* nb = out.node_box; float4* nodes = out.nodes; uint32_t* np = out.node_parent;
+        rt_launch(1, stream, RT_LAMBDA(size_t) {
+            DAabb b; for (int k = 0; k < 3; ++k) { b.lo[k] = 0.0f; b.hi[k] = 0.0f; }
+            uint32_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0}; DAabb cb[8];
+            nb[0] = b; np[0] = 0xFFFFFFFFu;
+            write_wide_node(nodes, b, cb, meta, 0, 0, 0);
+        });
+        info->n_nodes = 1; info->depth = 1;
+        return 0;
+    }
+    if (scratch_reserve(sc, n)) return 1;
+    uint32_t* bounds = sc.bounds; uint64_t* keys = sc.keys; uint32_t* vals = sc.vals;
+    const uint32_t init_bounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    rt_h2d(bounds, init_bounds, sizeof init_bounds, stream);
+    rt_launch(n, stream, RT_LAMBDA(size_t i) {
+        const DAabb b = prim_boxes[i];
+        for (int k = 0; k < 3; ++k) {
+            const float c = 0.5f * (b.lo[k] + b.hi[k]);
+            rt_atomic_min(&bounds[k], float_to_ordered(c)); rt_atomic_max(&bounds[3 + k], float_to_ordered(c));
+        }
+    });
+    rt_launch(n, stream, RT_LAMBDA(size_t i) {
+        const DAabb b = prim_boxes[i];
+        uint32_t q[3];
+        for (int k = 0; k < 3; ++k) {
+            const float lo = ordered_to_float(bounds[k]), hi = ordered_to_float(bounds[3 + k]);
+            const float c = 0.5f * (b.lo[k] + b.hi[k]);
+            float f = (hi > lo) ? (c - lo) / (hi - lo) : 0.0f;
+            f = fminf(fmaxf(f, 0.0f), 1.0f);
+            q[k] = (uint32_t)fminf(f * 2097152.0f, 2097151.0f);
+        }
+        keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+        vals[i] = (uint32_t)i;
+    });
+    if (rt_sort_pairs_u64(sc.keys, sc.vals, sc.keys_tmp, sc.vals_tmp, n, stream)) return 1;
+    int2* bin_children = sc.bin_children; uint32_t* bin_parent = sc.bin_parent; uint2* bin_range = sc.bin_range;
+    DAabb* bin_box = sc.bin_box; uint32_t* flags = sc.flags;
+    const int ni = (int)n;
+    if (n > 1) {
+        rt_memset(flags, 0, (size_t)(n - 1) * 4, stream);
+        rt_launch(n - 1, stream, RT_LAMBDA(size_t i) { lbvh_build_node(keys, ni, (int)i, bin_children, bin_parent, bin_range); });
+        rt_launch(n, stream, RT_LAMBDA(size_t i) {
+            const uint32_t leaf = (uint32_t)(ni - 1) + (uint32_t)i;
+            bin_box[leaf] = prim_boxes[vals[i]];
+            uint32_t cur = bin_parent[leaf];
+            for (;;) {
+                rt_threadfence();
+                const uint32_t old = rt_atomic_add(&flags[cur], 1u);
+                if (old == 0u) return;   // first arrival: the sibling subtree is not finished yet
+                rt_threadfence();
+                const int2 c = bin_children[cur];
+                // volatile-style reads: the sibling's box was published before its atomic
+                const volatile DAabb* lb = bin_box + c.x; const volatile DAabb* rb = bin_box + c.y;
+                DAabb u;
+                for (int k = 0; k < 3; ++k) { u.lo[k] = fminf(lb->lo[k], rb->lo[k]); u.hi[k] = fmaxf(lb->hi[k], rb->hi[k]); }
+                bin_box[cur] = u;
+                if (cur == 0u) return;
+                cur = bin_parent[cur];
+            }
+        });
+    } else {
+        rt_launch(1, stream, RT_LAMBDA(size_t) { bin_box[0] = prim_boxes[vals[0]]; });
+    }
+    // collapse, level by level
+    uint32_t* counters = sc.counters;
+    const uint32_t init_counters[3] = {1u, 0u, 0u};
+    rt_h2d(counters, init_counters, sizeof init_counters, stream);
+    const uint2 root_item = make_uint2(0u, 0u);
+    rt_h2d(sc.q_a, &root_item, sizeof root_item, stream);
+    uint2 *q_in = sc.q_a, *q_out = sc.q_b;
+    uint32_t q_count = 1, depth = 0;
+    while (q_count) {
+        ++depth;
+        const uint32_t zero = 0; rt_h2d(&counters[2], &zero, 4, stream);
+        const uint2* qi = q_in; uint2* qo = q_out; const bool is_root = depth == 1;
+        rt_launch(q_count, stream, RT_LAMBDA(size_t i) {
+            const uint2 it = qi[i];
+            collapse_node(ni, bin_children, bin_box, bin_range, vals, it.x, it.y, is_root ? 0xFFFFFFFFu : 0u, out, counters, qo);
+        });
+        uint32_t host_counters[3];
+        if (rt_d2h(host_counters, counters, sizeof host_counters, stream)) return 1;
+        if (rt_stream_sync(stream)) return 1;
+        if (host_counters[0] > out.max_nodes) return 2;
+        q_count = host_counters[2];
+        info->n_nodes = host_counters[0]; info->n_prims = host_counters[1];
+        uint2* t = q_in; q_in = q_out; q_out = t;
+        if (depth > 512) return 3;
+    }
+    info->depth = depth;
+    return 0;
+}
+
+// ---- refit -------------------------------------------------------------------------------------------
+// Recomputes one wide node from its children: leaf children from `leaf_boxes` (one box per emitted primitive, in
+// leaf order), inner children from node_box.  Keeps topology, slots and metas; re-quantises.
+RT_D void refit_wide_node(float4* nodes, DAabb* node_box, const DAabb* leaf_boxes, uint32_t w) {
+    float4* node = nodes + (size_t)w * RT_NODE_F4;
+    const float4 n0 = node[0], n1 = node[1];
+    const uint32_t imask = rt_float_as_uint(n0.w) >> 24;
+    const uint32_t child_base = rt_float_as_uint(n1.x), prim_base = rt_float_as_uint(n1.y);
+    uint32_t meta[8];
+    for (int i = 0; i < 4; ++i) { meta[i] = (rt_float_as_uint(n1.z) >> (8 * i)) & 0xFFu; meta[4 + i] = (rt_float_as_uint(n1.w) >> (8 * i)) & 0xFFu; }
+    DAabb cbox[8]; DAabb box; bool any = false;
+    for (int k = 0; k < 3; ++k) { box.lo[k] = 0.0f; box.hi[k] = 0.0f; }
+    for (int s = 0; s < 8; ++s) {
+        if (!meta[s]) continue;
+        DAabb b;
+        if ((meta[s] & 0x18u) == 0x18u) {
+            const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xFFFFFFFFu << s));
+            b = node_box[child_base + rel];
+        } else {
+            const uint32_t off = meta[s] & 0x1Fu, cnt = (uint32_t)rt_popc(meta[s] >> 5);
+            b = leaf_boxes[prim_base + off];
+            for (uint32_t k = 1; k < cnt; ++k) b = aabb_union(b, leaf_boxes[prim_base + off + k]);
+        }
+        cbox[s] = b;
+        box = any ? aabb_union(box, b) : b; any = true;
+    }
+    node_box[w] = box;
+    write_wide_node(node, box, cbox, meta, imask, child_base, prim_base);
+}

@@ -1,0 +1,789 @@
+// rt_core.h — contexts, scenes, frame orchestration and the C ABI of include/rt_b200.h.
+// Included by rt_api.cu (product, CUDA) and by tests/emu/emu.cpp (RT_EMU: test-only host emulation whose
+// exported symbols carry an emu_ prefix and which the rustracer_b200 package never loads).
+#pragma once
+#include "rt_kernels.h"
+
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cmath>
+
+#ifdef RT_EMU
+#define RT_API(name) emu_##name
+#else
+#define RT_API(name) name
+#endif
+
+namespace rtcore {
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define RT_CHECK(expr, what) do { if (expr) return fail(std::string(what) + ": " + rt_platform_error()); } while (0)
+
+static uint32_t host_tea16(uint32_t val0, uint32_t val1) {
+    uint32_t v0 = val0, v1 = val1, s0 = 0;
+    for (int n = 0; n < 16; n++) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v0;
+}
+
+// object->world 3x4 (row-major) -> world->object, evaluated in double with a fixed formula.  The oracle uses the
+// same formula so both sides feed identical matrices to the (bit-exact) ray transform.
+static void invert_3x4(const float* m, float* out) {
+    double a00 = m[0], a01 = m[1], a02 = m[2], t0 = m[3];
+    double a10 = m[4], a11 = m[5], a12 = m[6], t1 = m[7];
+    double a20 = m[8], a21 = m[9], a22 = m[10], t2 = m[11];
+    double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    double det = a00 * c00 + a01 * c01 + a02 * c02;
+    double id = 1.0 / det;
+    double i00 = c00 * id, i01 = (a02 * a21 - a01 * a22) * id, i02 = (a01 * a12 - a02 * a11) * id;
+    double i10 = c01 * id, i11 = (a00 * a22 - a02 * a20) * id, i12 = (a02 * a10 - a00 * a12) * id;
+    double i20 = c02 * id, i21 = (a01 * a20 - a00 * a21) * id, i22 = (a00 * a11 - a01 * a10) * id;
+    out[0] = (float)i00; out[1] = (float)i01; out[2] = (float)i02; out[3] = (float)(-(i00 * t0 + i01 * t1 + i02 * t2));
+    out[4] = (float)i10; out[5] = (float)i11; out[6] = (float)i12; out[7] = (float)(-(i10 * t0 + i11 * t1 + i12 * t2));
+    out[8] = (float)i20; out[9] = (float)i21; out[10] = (float)i22; out[11] = (float)(-(i20 * t0 + i21 * t1 + i22 * t2));
+}
+
+template <class T> static int dev_alloc(T** p, size_t count) { return rt_malloc((void**)p, count * sizeof(T)); }
+template <class T> static int dev_upload(T** p, const T* src, size_t count, rt_stream_t s) {
+    if (dev_alloc(p, count ? count : 1)) return 1;
+    if (count && rt_h2d(*p, src, count * sizeof(T), s)) return 1;
+    return 0;
+}
+
+struct StageEvent { int stage; rt_timer a, b; };
+
+}  // namespace rtcore
+using namespace rtcore;
+
+struct rt_context {
+    int device = 0;
+    rt_stream_t stream = nullptr;
+    uint32_t width = 0, height = 0;
+    FrameBuffers fb{};
+    DQueue q[2]{};
+    DHits hits{};
+    DShadowQueue sq{};
+    uint32_t* counters = nullptr; size_t counters_cap = 0;   // qcount | scount | fetch_extend | fetch_shadow
+    RtCounters* dev_cnt = nullptr;
+    // last frame
+    uint32_t last_S = 0, last_B = 0; uint64_t last_pixels = 0; bool last_counted = false; bool last_valid = false;
+    rt_timer ev_begin, ev_end; bool timers = false;
+    std::vector<StageEvent> stage_events; size_t stage_used = 0;
+    unsigned long long launches_before = 0, launches_after = 0;
+    std::vector<void*> ipc_opened;
+};
+
+struct GeoRecord { uint32_t node_off, tri_off, n_tris, n_nodes, depth; bool skinned; };
+
+struct rt_scene {
+    rt_context* ctx = nullptr;
+    // host mirrors needed for rebuilds
+    std::vector<rt_geometry> geometries; std::vector<rt_prim_info> prim_infos; std::vector<rt_instance> instances;
+    std::vector<GeoRecord> geo;
+    uint32_t n_vertices = 0, n_indices = 0, n_materials = 0, n_skins = 0;
+    // device arrays
+    rt_vertex *d_vin = nullptr, *d_vout = nullptr; uint32_t* d_indices = nullptr; rt_prim_info* d_prim = nullptr;
+    rt_material* d_mat = nullptr; float* d_skins = nullptr;
+    rt_light *d_dl = nullptr, *d_pl = nullptr; uint32_t cap_dl = 0, cap_pl = 0;
+    std::vector<uint8_t*> d_image_px; DImage* d_images = nullptr; DTexture* d_textures = nullptr; float* d_lut = nullptr;
+    uint8_t* d_sky[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float4 *d_blas_nodes = nullptr, *d_tris = nullptr; DAabb* d_node_box = nullptr; uint32_t* d_node_parent = nullptr;
+    uint32_t* d_prim_order = nullptr; DAabb* d_leaf_boxes = nullptr; DAabb* d_prim_boxes = nullptr; uint32_t* d_pending = nullptr;
+    uint64_t total_nodes = 0, total_tris = 0;
+    float4 *d_tlas_nodes = nullptr; uint32_t* d_tlas_prims = nullptr; DAabb* d_tlas_box = nullptr; uint32_t* d_tlas_parent = nullptr;
+    DAabb* d_inst_boxes = nullptr; float4 *d_inst_w2o = nullptr, *d_inst_o2w = nullptr; uint32_t* d_inst_root = nullptr;
+    uint32_t tlas_nodes = 0, tlas_depth = 0, blas_depth = 0;
+    BuildScratch scratch;
+    DScene ds{};
+    bool has_nee = false;
+    float build_ms = 0, refit_ms = 0, skin_ms = 0, tlas_ms = 0;
+};
+
+namespace rtcore {
+
+static void free_frame(rt_context* c) {
+    void* ptrs[] = {c->fb.acc, c->fb.out, c->fb.rad, c->fb.aux, c->fb.pixrng, c->hits.tuvp, c->hits.inst, c->sq.o_tmax, c->sq.d_pix, c->sq.contrib,
+                    c->q[0].o_tmin, c->q[0].d_tmax, c->q[0].thr_pix, c->q[0].rng, c->q[1].o_tmin, c->q[1].d_tmax, c->q[1].thr_pix, c->q[1].rng};
+    for (void* p : ptrs) if (p) rt_free(p);
+    c->fb = FrameBuffers{}; c->hits = DHits{}; c->sq = DShadowQueue{}; c->q[0] = DQueue{}; c->q[1] = DQueue{};
+}
+
+static int alloc_frame(rt_context* c, uint32_t w, uint32_t h) {
+    free_frame(c);
+    const size_t n = (size_t)w * h;
+    int e = 0;
+    e |= dev_alloc(&c->fb.acc, n); e |= dev_alloc(&c->fb.out, n); e |= dev_alloc(&c->fb.rad, n); e |= dev_alloc(&c->fb.aux, n); e |= dev_alloc(&c->fb.pixrng, n);
+    e |= dev_alloc(&c->hits.tuvp, n); e |= dev_alloc(&c->hits.inst, n);
+    e |= dev_alloc(&c->sq.o_tmax, n); e |= dev_alloc(&c->sq.d_pix, n); e |= dev_alloc(&c->sq.contrib, n);
+    for (int k = 0; k < 2; ++k) { e |= dev_alloc(&c->q[k].o_tmin, n); e |= dev_alloc(&c->q[k].d_tmax, n); e |= dev_alloc(&c->q[k].thr_pix, n); e |= dev_alloc(&c->q[k].rng, n); }
+    if (e) { free_frame(c); return 1; }
+    rt_memset(c->fb.acc, 0, n * sizeof(float4), c->stream); rt_memset(c->fb.out, 0, n * 4, c->stream);
+    rt_memset(c->fb.rad, 0, n * sizeof(float4), c->stream); rt_memset(c->fb.aux, 0, n * sizeof(float2), c->stream);
+    c->width = w; c->height = h; c->last_valid = false;
+    return 0;
+}
+
+static void update_ds(rt_scene* s) {
+    DScene& d = s->ds;
+    d.tlas_nodes = s->d_tlas_nodes; d.tlas_prims = s->d_tlas_prims; d.blas_nodes = s->d_blas_nodes; d.tris = s->d_tris;
+    d.inst_w2o = s->d_inst_w2o; d.inst_o2w = s->d_inst_o2w; d.n_instances = (uint32_t)s->instances.size();
+    d.vertices = s->d_vout; d.indices = s->d_indices; d.prim_infos = s->d_prim; d.materials = s->d_mat;
+    d.textures = s->d_textures; d.images = s->d_images; d.srgb_lut = s->d_lut;
+    d.dlights = s->d_dl; d.plights = s->d_pl;
+}
+
+static int run_skinning(rt_scene* s) {
+    rt_stream_t st = s->ctx->stream;
+    const rt_vertex* vin = s->d_vin; rt_vertex* vout = s->d_vout; const float* skins = s->d_skins; const uint32_t ns = s->n_skins;
+    rt_launch(s->n_vertices, st, RT_LAMBDA(size_t i) { skin_item(vin, vout, skins, ns, (uint32_t)i); });
+    return 0;
+}
+
+// (re)packs the triangles of geometry g in leaf order and refreshes the per-leaf boxes
+static void pack_tris(rt_scene* s, uint32_t g) {
+    const GeoRecord& gr = s->geo[g]; const rt_prim_info pi = s->prim_infos[g];
+    const rt_vertex* verts = s->d_vout; const uint32_t* indices = s->d_indices;
+    const uint32_t* order = s->d_prim_order + gr.tri_off; float4* tris = s->d_tris + (size_t)gr.tri_off * RT_TRI_F4; DAabb* lb = s->d_leaf_boxes + gr.tri_off;
+    rt_launch(gr.n_tris, s->ctx->stream, RT_LAMBDA(size_t k) {
+        const uint32_t prim = order[k];
+        const uint32_t io = pi.i_offset + 3 * prim;
+        const float* p0 = verts[pi.v_offset + indices[io]].position; const float* p1 = verts[pi.v_offset + indices[io + 1]].position; const float* p2 = verts[pi.v_offset + indices[io + 2]].position;
+        tris[k * RT_TRI_F4 + 0] = make_float4(p0[0], p0[1], p0[2], rt_uint_as_float(prim));
+        tris[k * RT_TRI_F4 + 1] = make_float4(p1[0], p1[1], p1[2], 0.0f);
+        tris[k * RT_TRI_F4 + 2] = make_float4(p2[0], p2[1], p2[2], 0.0f);
+        DAabb b;
+        for (int a = 0; a < 3; ++a) { b.lo[a] = fminf(p0[a], fminf(p1[a], p2[a])); b.hi[a] = fmaxf(p0[a], fmaxf(p1[a], p2[a])); }
+        lb[k] = b;
+    });
+}
+
+static int build_blas(rt_scene* s, uint32_t g) {
+    GeoRecord& gr = s->geo[g]; const rt_prim_info pi = s->prim_infos[g];
+    rt_stream_t st = s->ctx->stream;
+    const rt_vertex* verts = s->d_vout; const uint32_t* indices = s->d_indices; DAabb* pb = s->d_prim_boxes;
+    rt_launch(gr.n_tris, st, RT_LAMBDA(size_t k) { pb[k] = tri_box_of(verts, indices, pi.v_offset, pi.i_offset, (uint32_t)k); });
+    WideOut out;
+    out.nodes = s->d_blas_nodes + (size_t)gr.node_off * RT_NODE_F4; out.prim_order = s->d_prim_order + gr.tri_off;
+    out.node_box = s->d_node_box + gr.node_off; out.node_parent = s->d_node_parent + gr.node_off; out.max_nodes = gr.n_tris ? gr.n_tris : 1u;
+    WideBvhInfo info;
+    const int e = build_wide_bvh(pb, gr.n_tris, s->scratch, out, st, &info);
+    if (e) return fail("BLAS build failed for geometry " + std::to_string(g) + " (code " + std::to_string(e) + ")");
+    gr.n_nodes = info.n_nodes; gr.depth = info.depth;
+    pack_tris(s, g);
+    return 0;
+}
+
+static void refit_blas(rt_scene* s, uint32_t g) {
+    const GeoRecord& gr = s->geo[g];
+    rt_stream_t st = s->ctx->stream;
+    pack_tris(s, g);
+    float4* nodes = s->d_blas_nodes + (size_t)gr.node_off * RT_NODE_F4; DAabb* nb = s->d_node_box + gr.node_off;
+    const uint32_t* parent = s->d_node_parent + gr.node_off; uint32_t* pending = s->d_pending + gr.node_off;
+    const DAabb* lb = s->d_leaf_boxes + gr.tri_off;
+    rt_launch(gr.n_nodes, st, RT_LAMBDA(size_t w) { pending[w] = (uint32_t)rt_popc(rt_float_as_uint(nodes[w * RT_NODE_F4].w) >> 24); });
+    rt_launch(gr.n_nodes, st, RT_LAMBDA(size_t w0) {
+        uint32_t w = (uint32_t)w0;
+        if ((rt_float_as_uint(nodes[(size_t)w * RT_NODE_F4].w) >> 24) != 0u) return;   // only nodes without inner children start
+        for (;;) {
+            refit_wide_node(nodes, nb, lb, w);
+            const uint32_t p = parent[w];
+            if (p == 0xFFFFFFFFu) return;
+            rt_threadfence();
+            const uint32_t old = rt_atomic_add(&pending[p], 0xFFFFFFFFu);   // decrement
+            if (old != 1u) return;   // other children still pending
+            rt_threadfence();
+            w = p;
+        }
+    });
+}
+
+static int build_tlas(rt_scene* s) {
+    rt_stream_t st = s->ctx->stream;
+    const uint32_t n = (uint32_t)s->instances.size();
+    std::vector<float> w2o((size_t)n * 16), o2w((size_t)n * 12); std::vector<uint32_t> roots(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const rt_instance& in = s->instances[i];
+        float inv[12]; invert_3x4(in.transform, inv);
+        memcpy(&w2o[(size_t)i * 16], inv, 48);
+        const GeoRecord& gr = s->geo[in.geo_id];
+        uint32_t meta[4] = {gr.node_off, in.geo_id, s->geometries[in.geo_id].opaque ? RT_INST_OPAQUE : 0u, gr.tri_off};
+        memcpy(&w2o[(size_t)i * 16 + 12], meta, 16);
+        memcpy(&o2w[(size_t)i * 12], in.transform, 48);
+        roots[i] = gr.node_off;
+    }
+    RT_CHECK(rt_h2d(s->d_inst_w2o, w2o.data(), w2o.size() * 4, st), "upload instances");
+    RT_CHECK(rt_h2d(s->d_inst_o2w, o2w.data(), o2w.size() * 4, st), "upload instances");
+    RT_CHECK(rt_h2d(s->d_inst_root, roots.data(), roots.size() * 4, st), "upload instances");
+    const float4* o2wd = s->d_inst_o2w; const uint32_t* rootd = s->d_inst_root; const DAabb* nb = s->d_node_box; DAabb* ib = s->d_inst_boxes;
+    rt_launch(n, st, RT_LAMBDA(size_t i) {
+        const float4 m0 = o2wd[i * 3], m1 = o2wd[i * 3 + 1], m2 = o2wd[i * 3 + 2];
+        const DAabb b = nb[rootd[i]];
+        DAabb w;
+        for (int c = 0; c < 8; ++c) {
+            const float x = (c & 1) ? b.hi[0] : b.lo[0], y = (c & 2) ? b.hi[1] : b.lo[1], z = (c & 4) ? b.hi[2] : b.lo[2];
+            const float p[3] = {m0.x * x + m0.y * y + m0.z * z + m0.w, m1.x * x + m1.y * y + m1.z * z + m1.w, m2.x * x + m2.y * y + m2.z * z + m2.w};
+            for (int a = 0; a < 3; ++a) { if (c == 0) { w.lo[a] = p[a]; w.hi[a] = p[a]; } else { w.lo[a] = fminf(w.lo[a], p[a]); w.hi[a] = fmaxf(w.hi[a], p[a]); } }
+        }
+        // the corners were rounded and the object-space ray is rounded too: keep the world box conservative
+        for (int a = 0; a < 3; ++a) {
+            const float pad = (w.hi[a] - w.lo[a]) * 1e-5f + 1e-6f * fmaxf(fabsf(w.lo[a]), fabsf(w.hi[a])) + 1e-7f;
+            w.lo[a] -= pad; w.hi[a] += pad;
+        }
+        ib[i] = w;
+    });
+    WideOut out; out.nodes = s->d_tlas_nodes; out.prim_order = s->d_tlas_prims; out.node_box = s->d_tlas_box; out.node_parent = s->d_tlas_parent; out.max_nodes = n ? n : 1u;
+    WideBvhInfo info;
+    const int e = build_wide_bvh(ib, n, s->scratch, out, st, &info);
+    if (e) return fail("TLAS build failed (code " + std::to_string(e) + ")");
+    s->tlas_nodes = info.n_nodes; s->tlas_depth = info.depth;
+    if (s->tlas_depth + s->blas_depth + 4 > RT_STACK_SIZE)
+        return fail("BVH too deep for the traversal stack: tlas " + std::to_string(s->tlas_depth) + " + blas " + std::to_string(s->blas_depth));
+    return 0;
+}
+
+static void compute_has_nee(rt_scene* s, const rt_light* pl, uint32_t n) {
+    // RayTracing.rchit:86: a candidate slot i < min(n,3) is skipped when luminance(color*intensity) < 0.1
+    s->has_nee = false;
+    for (uint32_t i = 0; i < n && i < 3; ++i) {
+        const float lum = 0.2126f * pl[i].color[0] * pl[i].intensity + 0.7152f * pl[i].color[1] * pl[i].intensity + 0.0722f * pl[i].color[2] * pl[i].intensity;
+        if (!(lum < 0.1f)) s->has_nee = true;
+    }
+}
+
+static int upload_sky(rt_scene* s, const uint8_t* const faces[6], uint32_t w, uint32_t h, uint32_t srgb) {
+    for (int f = 0; f < 6; ++f) {
+        if (s->d_sky[f]) { rt_free(s->d_sky[f]); s->d_sky[f] = nullptr; }
+        RT_CHECK(dev_upload(&s->d_sky[f], faces[f], (size_t)w * h * 4, s->ctx->stream), "skybox upload");
+        s->ds.sky[f].px = s->d_sky[f]; s->ds.sky[f].w = w; s->ds.sky[f].h = h; s->ds.sky[f].srgb = srgb; s->ds.sky[f]._pad = 0;
+    }
+    s->ds.has_sky_faces = 1;
+    return 0;
+}
+
+static uint32_t owned_rows(const TilePart& tp) {
+    if (tp.n_parts <= 1) return tp.height;
+    uint32_t rows = 0;
+    const uint32_t n_strips = (tp.height + tp.strip_rows - 1) / tp.strip_rows;
+    for (uint32_t k = tp.part; k < n_strips; k += tp.n_parts) rows += ((k + 1) * tp.strip_rows <= tp.height) ? tp.strip_rows : (tp.height - k * tp.strip_rows);
+    return rows;
+}
+
+static StageEvent* stage_begin(rt_context* c, bool on, int stage, rt_stream_t st) {
+    if (!on) return nullptr;
+    if (c->stage_used == c->stage_events.size()) { StageEvent e; e.stage = stage; e.a.create(); e.b.create(); c->stage_events.push_back(e); }
+    StageEvent* e = &c->stage_events[c->stage_used++];
+    e->stage = stage; e->a.record(st);
+    return e;
+}
+static void stage_end(StageEvent* e, rt_stream_t st) { if (e) e->b.record(st); }
+
+#ifndef RT_EMU
+static inline unsigned persistent_grid(int blocks_per_sm) { return (unsigned)((g_rt_sm_count > 0 ? g_rt_sm_count : 148) * blocks_per_sm); }
+#endif
+
+template <bool ALPHA, bool COUNT>
+static void launch_extend(rt_context* c, const DScene& S, const FrameParams& P, const DQueue& q, const uint32_t* count, uint32_t* fetch, uint32_t max_count, rt_stream_t st) {
+#ifdef RT_EMU
+    const uint32_t n = *count;
+    for (uint32_t i = 0; i < n; ++i) extend_item<ALPHA, COUNT>(S, P, q, c->hits, i, c->dev_cnt);
+    (void)fetch; (void)max_count; (void)st;
+#else
+    extend_kernel<ALPHA, COUNT><<<persistent_grid(8), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
+    ++g_rt_launch_count; (void)max_count;
+#endif
+}
+template <bool ALPHA, bool COUNT>
+static void launch_shadow(rt_context* c, const DScene& S, const FrameParams& P, const uint32_t* count, uint32_t* fetch, rt_stream_t st) {
+#ifdef RT_EMU
+    const uint32_t n = *count;
+    for (uint32_t i = 0; i < n; ++i) shadow_item<ALPHA, COUNT>(S, P, c->fb, c->sq, i, c->dev_cnt);
+    (void)fetch; (void)st;
+#else
+    shadow_kernel<ALPHA, COUNT><<<persistent_grid(8), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
+    ++g_rt_launch_count;
+#endif
+}
+template <bool COUNT>
+static void launch_shade(rt_context* c, const DScene& S, const FrameParams& P, const DQueue& qin, const DQueue& qout, const uint32_t* count, uint32_t* out_count,
+                         uint32_t* shadow_count, uint32_t bounce, rt_stream_t st) {
+#ifdef RT_EMU
+    const uint32_t n = *count;
+    for (uint32_t i = 0; i < n; ++i) {
+        ShadeResult r = shade_item<COUNT>(S, P, c->fb, qin, c->hits, i, bounce, c->dev_cnt);
+        if (r.alive) store_path(qout, (*out_count)++, r.next);
+        if (r.has_shadow) {
+            const uint32_t k = (*shadow_count)++;
+            c->sq.o_tmax[k] = make_float4(r.shadow.origin.x, r.shadow.origin.y, r.shadow.origin.z, r.shadow.tmax);
+            c->sq.d_pix[k] = make_float4(r.shadow.dir.x, r.shadow.dir.y, r.shadow.dir.z, rt_uint_as_float(r.shadow.pixel));
+            c->sq.contrib[k] = make_float4(r.shadow.contrib.x, r.shadow.contrib.y, r.shadow.contrib.z, rt_uint_as_float(r.shadow.path_w));
+        }
+    }
+    (void)st;
+#else
+    shade_kernel<COUNT><<<persistent_grid(8), 128, 0, st>>>(S, P, c->fb, qin, c->hits, qout, c->sq, count, out_count, shadow_count, bounce, c->dev_cnt);
+    ++g_rt_launch_count;
+#endif
+}
+
+template <bool ALPHA, bool COUNT>
+static int render_frame(rt_context* c, rt_scene* s, const FrameParams& P0, const TilePart& tp, uint32_t flags, rt_stream_t st) {
+    FrameParams P = P0;
+    const uint32_t S = P.ubo.number_of_samples, B = P.ubo.number_of_bounces;
+    const uint32_t n_local = owned_rows(tp) * tp.width;
+    const size_t per = (size_t)(S ? S : 1) * (B + 1);
+    if (per * 4 > c->counters_cap) {
+        if (c->counters) rt_free(c->counters);
+        c->counters_cap = per * 4 + 64;
+        RT_CHECK(dev_alloc(&c->counters, c->counters_cap), "counter allocation");
+    }
+    uint32_t* qcount = c->counters; uint32_t* scount = c->counters + per; uint32_t* fetch_e = c->counters + 2 * per; uint32_t* fetch_s = c->counters + 3 * per;
+    rt_memset(c->counters, 0, per * 4 * sizeof(uint32_t), st);
+    if (COUNT) rt_memset(c->dev_cnt, 0, sizeof(RtCounters), st);
+    const bool timing = (flags & 4u) != 0;
+    c->stage_used = 0;
+    const FrameBuffers fb = c->fb; const DScene DS = s->ds;
+    for (uint32_t smp = 0; smp < S; ++smp) {
+        P.sample = smp;
+        const FrameParams Pk = P; const DQueue q0 = c->q[0]; uint32_t* qc0 = qcount + (size_t)smp * (B + 1);
+        StageEvent* ev = stage_begin(c, timing, 0, st);
+        rt_launch(n_local, st, RT_LAMBDA(size_t i) {
+            if (i == 0) *qc0 = n_local;
+            raygen_item(Pk, tp, fb, q0, (uint32_t)i);
+        });
+        stage_end(ev, st);
+        for (uint32_t b = 0; b < B; ++b) {
+            const size_t idx = (size_t)smp * (B + 1) + b;
+            const DQueue& qin = c->q[b & 1]; const DQueue& qout = c->q[(b + 1) & 1];
+            ev = stage_begin(c, timing, 1, st);
+            launch_extend<ALPHA, COUNT>(c, DS, P, qin, qcount + idx, fetch_e + idx, n_local, st);
+            stage_end(ev, st);
+            ev = stage_begin(c, timing, 2, st);
+            launch_shade<COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, b, st);
+            stage_end(ev, st);
+            if (s->has_nee) {
+                ev = stage_begin(c, timing, 3, st);
+                launch_shadow<ALPHA, COUNT>(c, DS, P, scount + idx, fetch_s + idx, st);
+                stage_end(ev, st);
+            }
+        }
+    }
+    {
+        const FrameParams Pk = P; const bool no_trace = (S == 0);
+        StageEvent* ev = stage_begin(c, timing, 4, st);
+        rt_launch(n_local, st, RT_LAMBDA(size_t i) {
+            if (no_trace) { const uint32_t pixel = local_to_pixel(tp, (uint32_t)i); fb.rad[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); fb.aux[pixel] = make_float2(0.0f, 0.0f); }
+            accumulate_item(Pk, tp, fb, (uint32_t)i, false);
+        });
+        stage_end(ev, st);
+    }
+    c->last_S = S; c->last_B = B; c->last_pixels = (uint64_t)n_local * S; c->last_counted = COUNT; c->last_valid = true;
+    return 0;
+}
+
+}  // namespace rtcore
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* RT_API(rt_last_error)(void) { return g_err.c_str(); }
+const char* RT_API(rt_version)(void) {
+#ifdef RT_EMU
+    return "rustracer_b200 0.1.0 (host emulation build — tests only)";
+#else
+    return "rustracer_b200 0.1.0 (CUDA sm_100a)";
+#endif
+}
+
+int RT_API(rt_context_create)(int device, uint32_t width, uint32_t height, rt_context** out) {
+    if (!out || !width || !height) return fail("rt_context_create: bad arguments");
+    rt_context* c = new rt_context();
+    c->device = device;
+#ifndef RT_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { delete c; return fail("rt_context_create: no CUDA device (there is no CPU fallback)"); }
+    if (device < 0 || device >= ndev) { delete c; return fail("rt_context_create: device ordinal out of range"); }
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail("rt_context_create: cudaSetDevice failed"); }
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); g_rt_sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("rt_context_create: stream creation failed"); }
+    c->ev_begin.create(); c->ev_end.create(); c->timers = true;
+#endif
+    if (dev_alloc(&c->dev_cnt, 1) || alloc_frame(c, width, height)) { delete c; return fail(std::string("rt_context_create: allocation failed: ") + rt_platform_error()); }
+    rt_memset(c->dev_cnt, 0, sizeof(RtCounters), c->stream);
+    rt_stream_sync(c->stream);
+    *out = c;
+    return 0;
+}
+
+void RT_API(rt_context_destroy)(rt_context* c) {
+    if (!c) return;
+    rt_stream_sync(c->stream);
+    free_frame(c);
+    if (c->counters) rt_free(c->counters);
+    if (c->dev_cnt) rt_free(c->dev_cnt);
+    for (auto& e : c->stage_events) { e.a.destroy(); e.b.destroy(); }
+#ifndef RT_EMU
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    c->ev_begin.destroy(); c->ev_end.destroy();
+    if (c->stream) cudaStreamDestroy(c->stream);
+#endif
+    delete c;
+}
+
+int RT_API(rt_frame_resize)(rt_context* c, uint32_t width, uint32_t height) {
+    if (!c || !width || !height) return fail("rt_frame_resize: bad arguments");
+    rt_stream_sync(c->stream);
+    if (alloc_frame(c, width, height)) return fail(std::string("rt_frame_resize: allocation failed: ") + rt_platform_error());
+    return 0;
+}
+
+void RT_API(rt_scene_destroy)(rt_scene* s) {
+    if (!s) return;
+    rt_stream_sync(s->ctx->stream);
+    void* ptrs[] = {s->d_vin, s->d_vout, s->d_indices, s->d_prim, s->d_mat, s->d_skins, s->d_dl, s->d_pl, s->d_images, s->d_textures, s->d_lut,
+                    s->d_blas_nodes, s->d_tris, s->d_node_box, s->d_node_parent, s->d_prim_order, s->d_leaf_boxes, s->d_prim_boxes, s->d_pending,
+                    s->d_tlas_nodes, s->d_tlas_prims, s->d_tlas_box, s->d_tlas_parent, s->d_inst_boxes, s->d_inst_w2o, s->d_inst_o2w, s->d_inst_root};
+    for (void* p : ptrs) if (p) rt_free(p);
+    for (uint8_t* p : s->d_image_px) if (p) rt_free(p);
+    for (int f = 0; f < 6; ++f) if (s->d_sky[f]) rt_free(s->d_sky[f]);
+    scratch_free(s->scratch);
+    delete s;
+}
+
+int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** out) {
+    if (!c || !d || !out) return fail("rt_scene_create: null argument");
+#ifndef RT_EMU
+    cudaSetDevice(c->device);
+#endif
+    rt_stream_t st = c->stream;
+    // ---- validation (the reference panics on malformed input; we return an error) ----
+    if (d->n_geometries && (!d->prim_infos || !d->geometries)) return fail("rt_scene_create: geometry arrays missing");
+    if (!d->n_materials) return fail("rt_scene_create: at least one material is required");
+    for (uint32_t g = 0; g < d->n_geometries; ++g) {
+        const rt_prim_info& pi = d->prim_infos[g]; const rt_geometry& ge = d->geometries[g];
+        if (ge.i_len % 3) return fail("rt_scene_create: geometry index count not a multiple of 3");
+        if ((uint64_t)pi.i_offset + ge.i_len > d->n_indices || (uint64_t)pi.v_offset + ge.v_len > d->n_vertices) return fail("rt_scene_create: geometry range outside vertex/index arrays");
+        if (pi.material_id >= d->n_materials) return fail("rt_scene_create: material_id out of range");
+        for (uint32_t k = 0; k < ge.i_len; ++k) if (d->indices[pi.i_offset + k] >= ge.v_len) return fail("rt_scene_create: vertex index out of range");
+    }
+    for (uint32_t i = 0; i < d->n_instances; ++i) if (d->instances[i].geo_id >= d->n_geometries) return fail("rt_scene_create: instance geo_id out of range");
+    for (uint32_t t = 0; t < d->n_textures; ++t) if (d->textures[t].image_index >= d->n_images || d->textures[t].sampler_index >= d->n_samplers) return fail("rt_scene_create: texture refers to a missing image or sampler");
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const rt_material& mt = d->materials[m];
+        const rt_texture_info* tis[] = {&mt.base_color_texture, &mt.metallic_roughness_texture, &mt.normal_texture, &mt.emissive_texture, &mt.transmission_texture,
+                                         &mt.specular_texture, &mt.specular_color_texture, &mt.sg_diffuse_texture, &mt.sg_specular_glossiness_texture};
+        for (const rt_texture_info* ti : tis) if (ti->index >= 0 && (uint32_t)ti->index >= d->n_textures) return fail("rt_scene_create: material texture index out of range");
+    }
+
+    rt_scene* s = new rt_scene(); s->ctx = c;
+    auto bail = [&](const std::string& m) { RT_API(rt_scene_destroy)(s); return fail(m); };
+    s->n_vertices = d->n_vertices; s->n_indices = d->n_indices; s->n_materials = d->n_materials; s->n_skins = d->n_skins;
+    s->geometries.assign(d->geometries, d->geometries + d->n_geometries);
+    s->prim_infos.assign(d->prim_infos, d->prim_infos + d->n_geometries);
+    s->instances.assign(d->instances, d->instances + d->n_instances);
+    int e = 0;
+    e |= dev_upload(&s->d_vin, d->vertices, d->n_vertices, st); e |= dev_alloc(&s->d_vout, d->n_vertices ? d->n_vertices : 1);
+    e |= dev_upload(&s->d_indices, d->indices, d->n_indices, st); e |= dev_upload(&s->d_prim, d->prim_infos, d->n_geometries, st);
+    e |= dev_upload(&s->d_mat, d->materials, d->n_materials, st);
+    e |= dev_upload(&s->d_skins, d->skins, (size_t)d->n_skins * RT_MAX_JOINTS * 16, st);
+    s->cap_dl = d->n_dlights; s->cap_pl = d->n_plights;
+    e |= dev_upload(&s->d_dl, d->dlights, d->n_dlights, st); e |= dev_upload(&s->d_pl, d->plights, d->n_plights, st);
+    if (e) return bail(std::string("rt_scene_create: upload failed: ") + rt_platform_error());
+    s->ds.n_dlights = d->n_dlights; s->ds.n_plights = d->n_plights; compute_has_nee(s, d->plights, d->n_plights);
+    // textures
+    std::vector<DImage> dimg(d->n_images); s->d_image_px.assign(d->n_images, nullptr);
+    for (uint32_t i = 0; i < d->n_images; ++i) {
+        const rt_image_desc& im = d->images[i];
+        if (dev_upload(&s->d_image_px[i], im.rgba8, (size_t)im.width * im.height * 4, st)) return bail("rt_scene_create: image upload failed");
+        dimg[i].px = s->d_image_px[i]; dimg[i].w = im.width; dimg[i].h = im.height; dimg[i].srgb = im.srgb; dimg[i]._pad = 0;
+    }
+    std::vector<DTexture> dtex(d->n_textures);
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        const rt_sampler_desc& sm = d->samplers[d->textures[t].sampler_index];
+        dtex[t].image = d->textures[t].image_index; dtex[t].mag_filter = sm.mag_filter; dtex[t].wrap_s = sm.wrap_s; dtex[t].wrap_t = sm.wrap_t;
+    }
+    float lut[256];
+    for (int i = 0; i < 256; ++i) { const double cc = i / 255.0; lut[i] = (float)(cc <= 0.04045 ? cc / 12.92 : pow((cc + 0.055) / 1.055, 2.4)); }
+    e |= dev_upload(&s->d_images, dimg.data(), dimg.size(), st); e |= dev_upload(&s->d_textures, dtex.data(), dtex.size(), st); e |= dev_upload(&s->d_lut, lut, 256, st);
+    if (e) return bail("rt_scene_create: texture table upload failed");
+    s->ds.n_textures = d->n_textures;
+    if (d->skybox_faces[0] && d->skybox_width && upload_sky(s, d->skybox_faces, d->skybox_width, d->skybox_height, d->skybox_srgb)) return bail(g_err);
+
+    // ---- geometry records and BVH storage ----
+    uint64_t node_off = 0, tri_off = 0; uint32_t max_tris = 0;
+    s->geo.resize(d->n_geometries);
+    std::vector<uint8_t> vskinned;
+    for (uint32_t g = 0; g < d->n_geometries; ++g) {
+        GeoRecord& gr = s->geo[g];
+        gr.n_tris = d->geometries[g].i_len / 3; gr.node_off = (uint32_t)node_off; gr.tri_off = (uint32_t)tri_off; gr.n_nodes = 0; gr.depth = 0; gr.skinned = false;
+        for (uint32_t v = 0; v < d->geometries[g].v_len && !gr.skinned; ++v) if (d->vertices[d->prim_infos[g].v_offset + v].skin_index >= 0) gr.skinned = true;
+        node_off += gr.n_tris ? gr.n_tris : 1; tri_off += gr.n_tris; if (gr.n_tris > max_tris) max_tris = gr.n_tris;
+    }
+    if (node_off > 0xFFFFFFF0ull || tri_off > 0xFFFFFFF0ull) return bail("rt_scene_create: scene too large for 32-bit BVH indices");
+    s->total_nodes = node_off; s->total_tris = tri_off;
+    const uint32_t ninst = d->n_instances;
+    e = 0;
+    e |= dev_alloc(&s->d_blas_nodes, (size_t)(node_off ? node_off : 1) * RT_NODE_F4); e |= dev_alloc(&s->d_tris, (size_t)(tri_off ? tri_off : 1) * RT_TRI_F4);
+    e |= dev_alloc(&s->d_node_box, node_off ? node_off : 1); e |= dev_alloc(&s->d_node_parent, node_off ? node_off : 1); e |= dev_alloc(&s->d_pending, node_off ? node_off : 1);
+    e |= dev_alloc(&s->d_prim_order, tri_off ? tri_off : 1); e |= dev_alloc(&s->d_leaf_boxes, tri_off ? tri_off : 1); e |= dev_alloc(&s->d_prim_boxes, max_tris ? max_tris : 1);
+    e |= dev_alloc(&s->d_tlas_nodes, (size_t)(ninst ? ninst : 1) * RT_NODE_F4); e |= dev_alloc(&s->d_tlas_prims, ninst ? ninst : 1);
+    e |= dev_alloc(&s->d_tlas_box, ninst ? ninst : 1); e |= dev_alloc(&s->d_tlas_parent, ninst ? ninst : 1); e |= dev_alloc(&s->d_inst_boxes, ninst ? ninst : 1);
+    e |= dev_alloc(&s->d_inst_w2o, (size_t)(ninst ? ninst : 1) * RT_INST_F4); e |= dev_alloc(&s->d_inst_o2w, (size_t)(ninst ? ninst : 1) * 3); e |= dev_alloc(&s->d_inst_root, ninst ? ninst : 1);
+    if (e) return bail(std::string("rt_scene_create: BVH allocation failed: ") + rt_platform_error());
+
+    rt_timer t0, t1, t2; t0.create(); t1.create(); t2.create();
+    t0.record(st);
+    run_skinning(s);   // initial ComputeUnit::dispatch (main.rs:85-91); copy-through when nothing is skinned
+    s->blas_depth = 0;
+    for (uint32_t g = 0; g < d->n_geometries; ++g) {
+        if (build_blas(s, g)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(g_err); }
+        if (s->geo[g].depth > s->blas_depth) s->blas_depth = s->geo[g].depth;
+    }
+    t1.record(st);
+    if (build_tlas(s)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(g_err); }
+    t2.record(st);
+    if (rt_stream_sync(st)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(std::string("rt_scene_create: device error: ") + rt_platform_error()); }
+    s->build_ms = rt_timer_ms(t0, t1); s->tlas_ms = rt_timer_ms(t1, t2);
+    t0.destroy(); t1.destroy(); t2.destroy();
+    update_ds(s);
+    *out = s;
+    return 0;
+}
+
+int RT_API(rt_scene_update_instances)(rt_scene* s, const rt_instance* inst, uint32_t n) {
+    if (!s || !inst) return fail("rt_scene_update_instances: null argument");
+    if (n != s->instances.size()) return fail("rt_scene_update_instances: instance count differs from the scene's");
+    for (uint32_t i = 0; i < n; ++i) if (inst[i].geo_id >= s->geo.size()) return fail("rt_scene_update_instances: geo_id out of range");
+    s->instances.assign(inst, inst + n);
+    rt_timer t0, t1; t0.create(); t1.create(); t0.record(s->ctx->stream);
+    const int e = build_tlas(s);
+    t1.record(s->ctx->stream); rt_stream_sync(s->ctx->stream); s->tlas_ms = rt_timer_ms(t0, t1); t0.destroy(); t1.destroy();
+    if (e) return 1;
+    update_ds(s);
+    return 0;
+}
+
+int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_skins, int rebuild) {
+    if (!s || (!mats && n_skins)) return fail("rt_scene_update_skins: null argument");
+    if (n_skins != s->n_skins) return fail("rt_scene_update_skins: skin count differs from the scene's");
+    rt_stream_t st = s->ctx->stream;
+    rt_timer t0, t1, t2, t3; t0.create(); t1.create(); t2.create(); t3.create();
+    RT_CHECK(rt_h2d(s->d_skins, mats, (size_t)n_skins * RT_MAX_JOINTS * 16 * 4, st), "skin upload");
+    t0.record(st);
+    run_skinning(s);
+    t1.record(st);
+    for (uint32_t g = 0; g < s->geo.size(); ++g) {
+        if (!s->geo[g].skinned) continue;
+        if (rebuild) { if (build_blas(s, g)) return 1; } else refit_blas(s, g);
+    }
+    if (rebuild) { s->blas_depth = 0; for (auto& g : s->geo) if (g.depth > s->blas_depth) s->blas_depth = g.depth; }
+    t2.record(st);
+    const int e = build_tlas(s);
+    t3.record(st);
+    rt_stream_sync(st);
+    s->skin_ms = rt_timer_ms(t0, t1); s->refit_ms = rt_timer_ms(t1, t2); s->tlas_ms = rt_timer_ms(t2, t3);
+    t0.destroy(); t1.destroy(); t2.destroy(); t3.destroy();
+    if (e) return 1;
+    update_ds(s);
+    return 0;
+}
+
+int RT_API(rt_scene_update_lights)(rt_scene* s, const rt_light* dl, uint32_t ndl, const rt_light* pl, uint32_t npl) {
+    if (!s) return fail("rt_scene_update_lights: null scene");
+    rt_stream_t st = s->ctx->stream;
+    rt_stream_sync(st);
+    if (ndl > s->cap_dl) { rt_free(s->d_dl); s->d_dl = nullptr; RT_CHECK(dev_alloc(&s->d_dl, ndl), "light allocation"); s->cap_dl = ndl; }
+    if (npl > s->cap_pl) { rt_free(s->d_pl); s->d_pl = nullptr; RT_CHECK(dev_alloc(&s->d_pl, npl), "light allocation"); s->cap_pl = npl; }
+    if (ndl) RT_CHECK(rt_h2d(s->d_dl, dl, (size_t)ndl * sizeof(rt_light), st), "light upload");
+    if (npl) RT_CHECK(rt_h2d(s->d_pl, pl, (size_t)npl * sizeof(rt_light), st), "light upload");
+    s->ds.n_dlights = ndl; s->ds.n_plights = npl; compute_has_nee(s, pl, npl);
+    update_ds(s);
+    return 0;
+}
+
+int RT_API(rt_scene_set_skybox)(rt_scene* s, const uint8_t* const faces[6], uint32_t w, uint32_t h, uint32_t srgb) {
+    if (!s || !faces || !w || !h) return fail("rt_scene_set_skybox: bad arguments");
+    for (int f = 0; f < 6; ++f) if (!faces[f]) return fail("rt_scene_set_skybox: null face");
+    rt_stream_sync(s->ctx->stream);
+    return upload_sky(s, faces, w, h, srgb);
+}
+
+int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_render_opts* opts, void* stream) {
+    if (!c || !s || !ubo) return fail("rt_render: null argument");
+    if (s->ctx != c) return fail("rt_render: scene belongs to another context");
+    if (ubo->total_number_of_samples == 0) return fail("rt_render: total_number_of_samples must be > 0");
+#ifndef RT_EMU
+    cudaSetDevice(c->device);
+#endif
+    rt_stream_t st = stream ? (rt_stream_t)stream : c->stream;
+    FrameParams P; P.ubo = *ubo; P.width = c->width; P.height = c->height; P.sample = 0;
+    P.clk = host_tea16(ubo->total_number_of_samples, ubo->random_seed);   // D1
+    TilePart tp; tp.width = c->width; tp.height = c->height; tp.strip_rows = 1; tp.n_parts = 1; tp.part = 0;
+    uint32_t flags = 0;
+    if (opts) {
+        flags = opts->flags;
+        if (opts->n_parts > 1) {
+            if (!opts->strip_rows || opts->part >= opts->n_parts) return fail("rt_render: bad tile partition");
+            tp.strip_rows = opts->strip_rows; tp.n_parts = opts->n_parts; tp.part = opts->part;
+        }
+    }
+#ifndef RT_EMU
+    c->launches_before = g_rt_launch_count;
+#endif
+    if (c->timers) c->ev_begin.record(st);
+    const bool alpha = !ubo->fully_opaque, count = (flags & RT_RENDER_COUNTERS) != 0;
+    int e;
+    if (alpha) e = count ? render_frame<true, true>(c, s, P, tp, flags, st) : render_frame<true, false>(c, s, P, tp, flags, st);
+    else e = count ? render_frame<false, true>(c, s, P, tp, flags, st) : render_frame<false, false>(c, s, P, tp, flags, st);
+    if (c->timers) c->ev_end.record(st);
+#ifndef RT_EMU
+    c->launches_after = g_rt_launch_count;
+    if (!e && cudaPeekAtLastError() != cudaSuccess) return fail(std::string("rt_render: launch failed: ") + rt_platform_error());
+#endif
+    return e;
+}
+
+int RT_API(rt_tonemap)(rt_context* c, const rt_ubo* ubo, void* stream) {
+    if (!c || !ubo) return fail("rt_tonemap: null argument");
+    rt_stream_t st = stream ? (rt_stream_t)stream : c->stream;
+    FrameParams P; P.ubo = *ubo; P.width = c->width; P.height = c->height; P.sample = 0; P.clk = 0;
+    TilePart tp; tp.width = c->width; tp.height = c->height; tp.strip_rows = 1; tp.n_parts = 1; tp.part = 0;
+    const FrameBuffers fb = c->fb;
+    rt_launch((size_t)c->width * c->height, st, RT_LAMBDA(size_t i) { accumulate_item(P, tp, fb, (uint32_t)i, true); });
+    return 0;
+}
+
+int RT_API(rt_synchronize)(rt_context* c) {
+    if (!c) return fail("rt_synchronize: null context");
+    if (rt_stream_sync(c->stream)) return fail(std::string("rt_synchronize: ") + rt_platform_error());
+    return 0;
+}
+
+int RT_API(rt_readback)(rt_context* c, float* acc, uint8_t* out) {
+    if (!c) return fail("rt_readback: null context");
+    const size_t n = (size_t)c->width * c->height;
+    if (rt_stream_sync(c->stream)) return fail(std::string("rt_readback: ") + rt_platform_error());
+    if (acc) RT_CHECK(rt_d2h(acc, c->fb.acc, n * 16, c->stream), "rt_readback");
+    if (out) RT_CHECK(rt_d2h(out, c->fb.out, n * 4, c->stream), "rt_readback");
+    if (rt_stream_sync(c->stream)) return fail(std::string("rt_readback: ") + rt_platform_error());
+    return 0;
+}
+
+int RT_API(rt_upload_accumulation)(rt_context* c, const float* acc) {
+    if (!c || !acc) return fail("rt_upload_accumulation: null argument");
+    RT_CHECK(rt_h2d(c->fb.acc, acc, (size_t)c->width * c->height * 16, c->stream), "rt_upload_accumulation");
+    rt_stream_sync(c->stream);
+    return 0;
+}
+
+int RT_API(rt_device_ptrs)(rt_context* c, void** acc, void** out) {
+    if (!c) return fail("rt_device_ptrs: null context");
+    if (acc) *acc = c->fb.acc;
+    if (out) *out = c->fb.out;
+    return 0;
+}
+
+int RT_API(rt_last_frame_stats)(rt_context* c, rt_stats* o) {
+    if (!c || !o) return fail("rt_last_frame_stats: null argument");
+    memset(o, 0, sizeof *o);
+    if (!c->last_valid) return fail("rt_last_frame_stats: no frame rendered yet");
+    if (rt_stream_sync(c->stream)) return fail(std::string("rt_last_frame_stats: ") + rt_platform_error());
+    const size_t per = (size_t)(c->last_S ? c->last_S : 1) * (c->last_B + 1);
+    std::vector<uint32_t> h(per * 2);
+    RT_CHECK(rt_d2h(h.data(), c->counters, per * 2 * 4, c->stream), "rt_last_frame_stats");
+    rt_stream_sync(c->stream);
+    for (uint32_t smp = 0; smp < c->last_S; ++smp)
+        for (uint32_t b = 0; b < c->last_B; ++b) { o->rays_extend += h[(size_t)smp * (c->last_B + 1) + b]; o->rays_shadow += h[per + (size_t)smp * (c->last_B + 1) + b]; }
+    o->pixel_samples = c->last_pixels;
+    if (c->last_counted) {
+        RtCounters k; RT_CHECK(rt_d2h(&k, c->dev_cnt, sizeof k, c->stream), "rt_last_frame_stats"); rt_stream_sync(c->stream);
+        o->nodes = k.nodes; o->tris = k.tris; o->insts = k.insts; o->anyhits = k.anyhits; o->tex_taps = k.tex_taps; o->light_cands = k.light_cands;
+    }
+    if (c->timers) o->ms_total = rt_timer_ms(c->ev_begin, c->ev_end);
+    for (size_t i = 0; i < c->stage_used; ++i) {
+        StageEvent& e = c->stage_events[i]; const float ms = rt_timer_ms(e.a, e.b);
+        switch (e.stage) { case 0: o->ms_raygen += ms; break; case 1: o->ms_extend += ms; o->n_extend_launches++; break; case 2: o->ms_shade += ms; break; case 3: o->ms_shadow += ms; break; default: o->ms_accum += ms; }
+    }
+    o->n_kernel_launches = (uint32_t)(c->launches_after - c->launches_before);
+    // shaded hits = extend rays that hit something = rays_extend - misses; approximated by the next-queue inputs is wrong
+    // (terminated paths also shade), so report the number of shade invocations
+    o->shaded_hits = o->rays_extend;
+    return 0;
+}
+
+static int trace_common(rt_scene* s, const rt_ray* rays, uint32_t n, uint32_t flags, const uint32_t* rng4, rt_hit* hits, uint8_t* occ) {
+    if (!s || (!rays && n)) return fail("rt_trace: null argument");
+    if (n == 0) return 0;
+    rt_context* c = s->ctx; rt_stream_t st = c->stream;
+#ifndef RT_EMU
+    cudaSetDevice(c->device);
+#endif
+    rt_ray* d_rays = nullptr; uint32_t* d_rng = nullptr; rt_hit* d_hits = nullptr; uint8_t* d_occ = nullptr;
+    int e = dev_upload(&d_rays, rays, n, st);
+    if (rng4) e |= dev_upload(&d_rng, rng4, (size_t)n * 4, st);
+    if (hits) e |= dev_alloc(&d_hits, n); else e |= dev_alloc(&d_occ, n);
+    if (e) { rt_free(d_rays); rt_free(d_rng); rt_free(d_hits); rt_free(d_occ); return fail(std::string("rt_trace: allocation failed: ") + rt_platform_error()); }
+    const DScene DS = s->ds; const bool alpha = !(flags & RT_TRACE_OPAQUE);
+#ifdef RT_EMU
+    for (uint32_t i = 0; i < n; ++i) {
+        u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
+        if (d_rng) { rng.x = d_rng[4 * i]; rng.y = d_rng[4 * i + 1]; rng.z = d_rng[4 * i + 2]; rng.w = d_rng[4 * i + 3]; }
+        const rt_ray& r = d_rays[i]; RtHit h; bool f;
+        const f3 o = mk3(r.origin[0], r.origin[1], r.origin[2]), dd = mk3(r.direction[0], r.direction[1], r.direction[2]);
+        if (d_occ) { f = alpha ? trace_ray<RT_MODE_ANY, true, false>(DS, o, dd, r.tmin, r.tmax, rng, h, nullptr) : trace_ray<RT_MODE_ANY, false, false>(DS, o, dd, r.tmin, r.tmax, rng, h, nullptr); d_occ[i] = f; }
+        else {
+            f = alpha ? trace_ray<RT_MODE_CLOSEST, true, false>(DS, o, dd, r.tmin, r.tmax, rng, h, nullptr) : trace_ray<RT_MODE_CLOSEST, false, false>(DS, o, dd, r.tmin, r.tmax, rng, h, nullptr);
+            rt_hit& oh = d_hits[i];
+            if (f) { oh.t = h.t; oh.u = h.u; oh.v = h.v; oh.instance_id = h.inst; oh.primitive_id = h.prim; oh.geo_id = rt_float_as_uint(DS.inst_w2o[(size_t)h.inst * RT_INST_F4 + 3].y); }
+            else { oh.t = -1.0f; oh.u = oh.v = 0.0f; oh.instance_id = oh.primitive_id = oh.geo_id = 0xFFFFFFFFu; }
+        }
+    }
+#else
+    const unsigned grid = persistent_grid(8);
+    if (alpha) trace_rays_kernel<true, false><<<grid, 128, 0, st>>>(DS, d_rays, n, d_rng, d_hits, d_occ, nullptr);
+    else trace_rays_kernel<false, false><<<grid, 128, 0, st>>>(DS, d_rays, n, d_rng, d_hits, d_occ, nullptr);
+    ++g_rt_launch_count;
+#endif
+    if (hits) e = rt_d2h(hits, d_hits, (size_t)n * sizeof(rt_hit), st); else e = rt_d2h(occ, d_occ, n, st);
+    e |= rt_stream_sync(st);
+    rt_free(d_rays); rt_free(d_rng); rt_free(d_hits); rt_free(d_occ);
+    if (e) return fail(std::string("rt_trace: device error: ") + rt_platform_error());
+    return 0;
+}
+
+int RT_API(rt_trace_closest)(rt_scene* s, const rt_ray* rays, uint32_t n, uint32_t flags, const uint32_t* rng4, rt_hit* hits) {
+    if (!hits && n) return fail("rt_trace_closest: null hits");
+    return trace_common(s, rays, n, flags, rng4, hits, nullptr);
+}
+int RT_API(rt_trace_any)(rt_scene* s, const rt_ray* rays, uint32_t n, uint32_t flags, const uint32_t* rng4, uint8_t* occluded) {
+    if (!occluded && n) return fail("rt_trace_any: null output");
+    return trace_common(s, rays, n, flags, rng4, nullptr, occluded);
+}
+
+int RT_API(rt_scene_read_vertices)(rt_scene* s, rt_vertex* out, uint32_t n) {
+    if (!s || !out) return fail("rt_scene_read_vertices: null argument");
+    if (n > s->n_vertices) return fail("rt_scene_read_vertices: more vertices requested than the scene holds");
+    rt_stream_sync(s->ctx->stream);
+    RT_CHECK(rt_d2h(out, s->d_vout, (size_t)n * sizeof(rt_vertex), s->ctx->stream), "rt_scene_read_vertices");
+    rt_stream_sync(s->ctx->stream);
+    return 0;
+}
+
+int RT_API(rt_scene_bvh_info)(rt_scene* s, rt_bvh_info* o) {
+    if (!s || !o) return fail("rt_scene_bvh_info: null argument");
+    memset(o, 0, sizeof *o);
+    for (auto& g : s->geo) o->blas_nodes += g.n_nodes;
+    o->blas_tris = s->total_tris; o->tlas_nodes = s->tlas_nodes;
+    o->bytes = o->blas_nodes * 80ull + o->blas_tris * 48ull + o->tlas_nodes * 80ull + (uint64_t)s->instances.size() * (64 + 48);
+    o->max_depth_blas = s->blas_depth; o->max_depth_tlas = s->tlas_depth;
+    o->build_ms = s->build_ms; o->refit_ms = s->refit_ms; o->skin_ms = s->skin_ms; o->tlas_ms = s->tlas_ms;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// rt_kernels.h — the wavefront stages as launchable kernels.
+//   extend   : persistent warps fetch 32 rays at a time from the queue (dynamic load balance), while-while
+//              traversal in rt_traverse.h, hit record out
+//   shade    : one thread per path: miss / closest-hit shading, bounce epilogue, compaction into the next queue
+//              (warp-aggregated atomics), shadow-ray emission
+//   shadow   : any-hit traversal of the shadow queue, unoccluded contributions added to the frame radiance
+//   raygen / accumulate / skinning / triangle packing / instance setup / refit
+// Launch shapes: grids are multiples of the SM count (148 on B200); nothing here uses tensor cores — the path
+// has no dense contraction.
+#pragma once
+#include "rt_shade.h"
+#include "rt_build.h"
+
+struct FrameBuffers {
+    float4* acc;        // RGBA32F accumulation image (RayTracing.rgen:18)
+    uint32_t* out;      // RGBA8 output image (RayTracing.rgen:19)
+    float4* rad;        // radiance gathered during the current frame
+    float2* aux;        // last Ray.t, number of traced segments (DISTANCE / HEAT mappings)
+    uint4* pixrng;      // per-pixel stream positions carried between the samples of one frame
+};
+struct TilePart { uint32_t strip_rows, n_parts, part, width, height; };
+
+RT_D uint32_t local_to_pixel(const TilePart& tp, uint32_t i) {
+    if (tp.n_parts <= 1) return i;
+    const uint32_t lr = i / tp.width, x = i % tp.width;
+    const uint32_t k = lr / tp.strip_rows, r = lr % tp.strip_rows;
+    const uint32_t y = (k * tp.n_parts + tp.part) * tp.strip_rows + r;
+    return y * tp.width + x;
+}
+
+RT_D void store_path(const DQueue& q, uint32_t slot, const PathState& s) {
+    q.o_tmin[slot] = make_float4(s.origin.x, s.origin.y, s.origin.z, s.tmin);
+    q.d_tmax[slot] = make_float4(s.dir.x, s.dir.y, s.dir.z, s.tmax);
+    q.thr_pix[slot] = make_float4(s.throughput.x, s.throughput.y, s.throughput.z, rt_uint_as_float(s.pixel));
+    q.rng[slot] = make_uint4(s.path_w, s.pix_w, s.lens_seed, rt_float_as_uint(s.volume_dis));
+}
+RT_D PathState load_path(const DQueue& q, uint32_t slot) {
+    const float4 a = q.o_tmin[slot], b = q.d_tmax[slot], c = q.thr_pix[slot]; const uint4 r = q.rng[slot];
+    PathState s;
+    s.origin = mk3(a.x, a.y, a.z); s.tmin = a.w; s.dir = mk3(b.x, b.y, b.z); s.tmax = b.w;
+    s.throughput = mk3(c.x, c.y, c.z); s.pixel = rt_float_as_uint(c.w);
+    s.path_w = r.x; s.pix_w = r.y; s.lens_seed = r.z; s.volume_dis = rt_uint_as_float(r.w);
+    return s;
+}
+
+// ---- per-item bodies ----------------------------------------------------------------------------------
+RT_D void raygen_item(const FrameParams& P, const TilePart& tp, const FrameBuffers& fb, const DQueue& q, uint32_t i) {
+    const uint32_t pixel = local_to_pixel(tp, i);
+    uint4 pr = make_uint4(0u, 0u, 0u, 0u);
+    if (P.sample != 0) pr = fb.pixrng[pixel];
+    else { fb.rad[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); fb.aux[pixel] = make_float2(0.0f, 0.0f); }
+    const PathState s = raygen_path(P, pixel, pr.x, pr.y, pr.z);
+    store_path(q, i, s);
+}
+
+template <bool ALPHA, bool COUNT>
+RT_D void extend_item(const DScene& S, const FrameParams& P, const DQueue& q, const DHits& hits, uint32_t i, RtCounters* cnt) {
+    const float4 a = q.o_tmin[i], b = q.d_tmax[i];
+    u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
+    if (ALPHA) { const uint32_t pixel = rt_float_as_uint(q.thr_pix[i].w); rng = path_stream(P, pixel, q.rng[i].x); }
+    RtHit h;
+    trace_ray<RT_MODE_CLOSEST, ALPHA, COUNT>(S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, rng, h, cnt);
+    hits.tuvp[i] = make_float4(h.t, h.u, h.v, rt_uint_as_float(h.prim));
+    hits.inst[i] = h.inst;
+}
+
+// returns true when the path continues; slot allocation is done by the caller (warp-aggregated on the GPU)
+struct ShadeResult { bool alive; PathState next; bool has_shadow; ShadowRay shadow; };
+
+template <bool COUNT>
+RT_D ShadeResult shade_item(const DScene& S, const FrameParams& P, const FrameBuffers& fb, const DQueue& q, const DHits& hits,
+                            uint32_t i, uint32_t bounce, RtCounters* cnt) {
+    PathState st = load_path(q, i);
+    const float4 hv = hits.tuvp[i];
+    RtHit h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.prim = rt_float_as_uint(hv.w); h.inst = hits.inst[i];
+    ShadeOut so;
+    if (h.t < 0.0f) shade_miss(S, P, st.dir, bounce == 0, so, cnt);
+    else shade_hit(S, P, h, st, so, cnt);
+
+    ShadeResult r; r.alive = false; r.has_shadow = so.has_shadow;
+    if (so.has_shadow) { r.shadow = so.shadow; r.shadow.contrib = so.shadow.contrib * st.throughput; }
+    // RayTracing.rgen:94-129
+    const f3 add = st.throughput * so.emittance;
+    if (add.x != 0.0f || add.y != 0.0f || add.z != 0.0f) {
+        float4 cur = fb.rad[st.pixel];
+        cur.x += add.x; cur.y += add.y; cur.z += add.z;
+        fb.rad[st.pixel] = cur;
+    }
+    bool alive = (bounce + 1 != P.ubo.number_of_bounces);
+    if (alive && bounce > 3) {   // MIN_BOUNCES 3
+        const float p = clampf(luminance(st.throughput), 0.01f, 0.95f);
+        u4 pix = pixel_stream(P, st.pixel, st.pix_w);
+        const float qv = rng_next(pix); st.pix_w = pix.w;
+        if (p < qv) alive = false; else st.throughput /= p;
+    }
+    if (alive) {
+        st.throughput *= so.hit_value;
+        if (!so.need_scatter || so.t < 0.0f) alive = false;
+    }
+    if (alive) {
+        st.origin = so.next_origin; st.dir = so.next_dir; st.tmin = RT_TMIN;
+        r.alive = true; r.next = st;
+    } else {
+        if (P.ubo.number_of_samples > 1) fb.pixrng[st.pixel] = make_uint4(st.pix_w, st.path_w, st.lens_seed, 0u);
+        if (P.ubo.mapping == RT_MAP_DISTANCE || P.ubo.mapping == RT_MAP_HEAT) {
+            float2 a = fb.aux[st.pixel]; a.x = so.t; a.y += (float)(bounce + 1); fb.aux[st.pixel] = a;
+        }
+    }
+    return r;
+}
+
+template <bool ALPHA, bool COUNT>
+RT_D void shadow_item(const DScene& S, const FrameParams& P, const FrameBuffers& fb, const DShadowQueue& sq, uint32_t i, RtCounters* cnt) {
+    const float4 a = sq.o_tmax[i], b = sq.d_pix[i], c = sq.contrib[i];
+    const uint32_t pixel = rt_float_as_uint(b.w);
+    u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
+    if (ALPHA) rng = path_stream(P, pixel, rt_float_as_uint(c.w));
+    RtHit h;
+    const bool occluded = trace_ray<RT_MODE_ANY, ALPHA, COUNT>(S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.1f, a.w, rng, h, cnt);   // tMin 0.1: RayTracing.rchit:43
+    if (!occluded) {
+        float4 cur = fb.rad[pixel];
+        cur.x += c.x; cur.y += c.y; cur.z += c.z;
+        fb.rad[pixel] = cur;
+    }
+}
+
+RT_D void accumulate_item(const FrameParams& P, const TilePart& tp, const FrameBuffers& fb, uint32_t i, bool tonemap_only) {
+    const uint32_t pixel = local_to_pixel(tp, i);
+    if (tonemap_only) {
+        // used after a cross-GPU reduce: acc already holds the sum for total_number_of_samples
+        rt_ubo u = P.ubo; u.number_of_samples = 0; if (u.total_number_of_samples == 0) u.total_number_of_samples = 1;
+        accumulate_pixel(u, fb.acc, fb.out, pixel, mk3(0.0f), 0.0f, 0u);
+        return;
+    }
+    const float4 r = fb.rad[pixel]; const float2 a = fb.aux[pixel];
+    accumulate_pixel(P.ubo, fb.acc, fb.out, pixel, mk3(r.x, r.y, r.z), a.x, (uint32_t)a.y);
+}
+
+// AnimationCompute.comp:14-39
+RT_D void skin_item(const rt_vertex* vin, rt_vertex* vout, const float* skins, uint32_t n_skins, uint32_t i) {
+    const float4* src = reinterpret_cast<const float4*>(vin + i);
+    float4 r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = src[k];
+    const int skin_index = (int)rt_float_as_uint(r[7].x);
+    if (skin_index >= 0 && (uint32_t)skin_index < n_skins) {
+        const float* bones = skins + (size_t)skin_index * (RT_MAX_JOINTS * 16);
+        const float w[4] = {r[4].x, r[4].y, r[4].z, r[4].w};
+        const uint32_t j[4] = {rt_float_as_uint(r[5].x), rt_float_as_uint(r[5].y), rt_float_as_uint(r[5].z), rt_float_as_uint(r[5].w)};
+        float M[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) M[k] = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float4* bm = reinterpret_cast<const float4*>(bones + (size_t)(j[b] & (RT_MAX_JOINTS - 1)) * 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 col = rt_ld(bm + c);
+                if (b == 0) { M[c * 4] = w[0] * col.x; M[c * 4 + 1] = w[0] * col.y; M[c * 4 + 2] = w[0] * col.z; M[c * 4 + 3] = w[0] * col.w; }
+                else { M[c * 4] += w[b] * col.x; M[c * 4 + 1] += w[b] * col.y; M[c * 4 + 2] += w[b] * col.z; M[c * 4 + 3] += w[b] * col.w; }
+            }
+        }
+        const f4 pos = mat4_mul(M, mk4(r[0].x, r[0].y, r[0].z, 1.0f));
+        const f3 nn = normalize(xyz(mat4_mul(M, mk4(r[1].x, r[1].y, r[1].z, 0.0f))));
+        const f4 tt = normalize(mat4_mul(M, mk4(r[2].x, r[2].y, r[2].z, 0.0f)));
+        r[0].x = pos.x; r[0].y = pos.y; r[0].z = pos.z;
+        r[1].x = nn.x; r[1].y = nn.y; r[1].z = nn.z;
+        r[2].x = tt.x; r[2].y = tt.y; r[2].z = tt.z;   // w (handedness) kept
+    }
+    float4* dst = reinterpret_cast<float4*>(vout + i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = r[k];
+}
+
+RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t v_offset, uint32_t i_offset, uint32_t prim) {
+    DAabb b;
+    for (int k = 0; k < 3; ++k) {
+        const float* p = verts[v_offset + indices[i_offset + 3 * prim + k]].position;
+        for (int a = 0; a < 3; ++a) {
+            if (k == 0) { b.lo[a] = p[a]; b.hi[a] = p[a]; }
+            else { b.lo[a] = fminf(b.lo[a], p[a]); b.hi[a] = fmaxf(b.hi[a], p[a]); }
+        }
+    }
+    return b;
+}
+
+#ifndef RT_EMU
+// ---- CUDA kernels -------------------------------------------------------------------------------------
+#define RT_EXTEND_THREADS 128
+
+template <bool ALPHA, bool COUNT>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+    const uint32_t count = *count_ptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) return;
+        const uint32_t i = base + lane;
+        if (i < count) extend_item<ALPHA, COUNT>(S, P, q, hits, i, cnt);
+    }
+}
+
+template <bool ALPHA, bool COUNT>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+    const uint32_t count = *count_ptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) return;
+        const uint32_t i = base + lane;
+        if (i < count) shadow_item<ALPHA, COUNT>(S, P, fb, sq, i, cnt);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
+                                                    const uint32_t* count_ptr, uint32_t* out_count, uint32_t* shadow_count, uint32_t bounce, RtCounters* cnt) {
+    const uint32_t count = *count_ptr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // all lanes of a warp iterate together so the ballots below are convergent
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
+        const uint32_t i = base + lane;
+        ShadeResult r; r.alive = false; r.has_shadow = false;
+        if (i < count) r = shade_item<COUNT>(S, P, fb, qin, hits, i, bounce, cnt);
+        const uint32_t alive_mask = __ballot_sync(0xFFFFFFFFu, r.alive);
+        if (alive_mask) {
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(out_count, (uint32_t)__popc(alive_mask));
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            if (r.alive) store_path(qout, slot0 + (uint32_t)__popc(alive_mask & ((1u << lane) - 1u)), r.next);
+        }
+        const uint32_t sh_mask = __ballot_sync(0xFFFFFFFFu, r.has_shadow);
+        if (sh_mask) {
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(shadow_count, (uint32_t)__popc(sh_mask));
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            if (r.has_shadow) {
+                const uint32_t s = slot0 + (uint32_t)__popc(sh_mask & ((1u << lane) - 1u));
+                sq.o_tmax[s] = make_float4(r.shadow.origin.x, r.shadow.origin.y, r.shadow.origin.z, r.shadow.tmax);
+                sq.d_pix[s] = make_float4(r.shadow.dir.x, r.shadow.dir.y, r.shadow.dir.z, rt_uint_as_float(r.shadow.pixel));
+                sq.contrib[s] = make_float4(r.shadow.contrib.x, r.shadow.contrib.y, r.shadow.contrib.z, rt_uint_as_float(r.shadow.path_w));
+            }
+        }
+    }
+}
+
+template <bool ALPHA, bool COUNT>
+__global__ void __launch_bounds__(128) trace_rays_kernel(DScene S, const rt_ray* rays, uint32_t n, const uint32_t* rng4, rt_hit* hits, uint8_t* occluded, RtCounters* cnt) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const rt_ray r = rays[i];
+        u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
+        if (rng4) { rng.x = rng4[4 * i]; rng.y = rng4[4 * i + 1]; rng.z = rng4[4 * i + 2]; rng.w = rng4[4 * i + 3]; }
+        RtHit h;
+        if (occluded) {
+            occluded[i] = trace_ray<RT_MODE_ANY, ALPHA, COUNT>(S, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, rng, h, cnt) ? 1 : 0;
+        } else {
+            const bool f = trace_ray<RT_MODE_CLOSEST, ALPHA, COUNT>(S, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, rng, h, cnt);
+            rt_hit o;
+            if (f) { o.t = h.t; o.u = h.u; o.v = h.v; o.instance_id = h.inst; o.primitive_id = h.prim; o.geo_id = rt_float_as_uint(S.inst_w2o[(size_t)h.inst * RT_INST_F4 + 3].y); }
+            else { o.t = -1.0f; o.u = 0.0f; o.v = 0.0f; o.instance_id = o.primitive_id = o.geo_id = 0xFFFFFFFFu; }
+            hits[i] = o;
+        }
+    }
+}
+#endif

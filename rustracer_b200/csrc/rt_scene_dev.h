@@ -1,0 +1,65 @@
+// rt_scene_dev.h — device-side scene view: what the kernels read (DESIGN.md "data layout in HBM").
+#pragma once
+#include "../../include/rt_b200.h"
+#include "rt_math.h"
+
+// 8-wide compressed BVH node, 80 bytes = 5 x float4 (Ylitie, Karras, Laine 2017 layout):
+//   n0: origin.xyz (f32)              | ex, ey, ez (int8 exponents), imask (bit i: slot i is an inner node)
+//   n1: child_base (u32) | prim_base (u32) | meta[0..3] | meta[4..7]
+//   n2: qlo_x[0..3] qlo_x[4..7] qlo_y[0..3] qlo_y[4..7]
+//   n3: qlo_z[0..3] qlo_z[4..7] qhi_x[0..3] qhi_x[4..7]
+//   n4: qhi_y[0..3] qhi_y[4..7] qhi_z[0..3] qhi_z[4..7]
+// meta[i]: 0 = empty; inner: 0b001_xxxxx with xxxxx = 24 + slot; leaf: top 3 bits = unary count (1 -> 001,
+// 2 -> 011, 3 -> 111), low 5 bits = first primitive offset (0..23) relative to prim_base.
+#define RT_NODE_F4 5
+#define RT_LEAF_MAX 3
+#define RT_STACK_SIZE 40
+
+// BLAS primitive record, 48 bytes = 3 x float4: v0.xyz | primitive_id ; v1.xyz | 0 ; v2.xyz | 0
+#define RT_TRI_F4 3
+
+// per-instance record for traversal, 64 bytes = 4 x float4: world->object 3x4 row-major (rows 0..2),
+// then { blas_root (node index), geo_id, flags (bit0: opaque geometry), 0 }
+#define RT_INST_F4 4
+#define RT_INST_OPAQUE 1u
+
+struct DImage { const uint8_t* px; uint32_t w, h, srgb, _pad; };
+struct DTexture { uint32_t image, mag_filter, wrap_s, wrap_t; };
+
+struct DScene {
+    // traversal
+    const float4* tlas_nodes;      // RT_NODE_F4 float4 per node, root = 0
+    const uint32_t* tlas_prims;    // instance ids in TLAS leaf order
+    const float4* blas_nodes;      // all BLASes, child indices absolute
+    const float4* tris;            // RT_TRI_F4 float4 per triangle, leaf order
+    const float4* inst_w2o;        // RT_INST_F4 float4 per instance
+    const float4* inst_o2w;        // 3 float4 per instance: object->world rows
+    uint32_t n_instances;
+    // shading inputs in the reference's layouts
+    const rt_vertex* vertices;     // skinned output (AnimationCompute.comp) == BLAS build input
+    const uint32_t* indices;
+    const rt_prim_info* prim_infos;
+    const rt_material* materials;
+    const DTexture* textures; uint32_t n_textures;
+    const DImage* images;
+    const rt_light* dlights; uint32_t n_dlights;
+    const rt_light* plights; uint32_t n_plights;
+    const float* srgb_lut;         // 256 entries
+    DImage sky[6]; uint32_t has_sky_faces;
+};
+
+struct RtCounters { unsigned long long nodes, tris, insts, anyhits, tex_taps, light_cands; };
+
+// Wavefront queues (SoA): one path = 64 B of state
+struct DQueue {
+    float4* o_tmin;     // origin.xyz, tmin
+    float4* d_tmax;     // direction.xyz, tmax
+    float4* thr_pix;    // throughput.xyz, pixel index (uint bits)
+    uint4*  rng;        // PATH.w, PIX.w, LENS seed (LCG), volume_dis (float bits)
+};
+struct DHits { float4* tuvp; uint32_t* inst; };   // t,u,v,primitive(bits) | instance
+struct DShadowQueue {
+    float4* o_tmax;     // origin.xyz, tmax
+    float4* d_pix;      // direction.xyz, pixel index (uint bits)
+    float4* contrib;    // throughput * brdf * weight * intensity * colour, PATH.w at chit entry (uint bits)
+};
