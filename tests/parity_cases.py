@@ -1,0 +1,164 @@
+"""Parity cases shared by the GPU tests (product library through the C ABI, `-m gpu`) and by the pre-GPU
+host-emulation checks (`-m "not gpu"`).  Every case compares against the CPU oracle on the same seeded inputs.
+Tolerances (BASELINE.json north_star): IDs / t / barycentrics bit-exact; images mean relative error < 1 %,
+PSNR >= 40 dB; debug-mapping channels within 1 LSB."""
+import numpy as np
+
+import util
+from oracle import orc
+from rustracer_b200 import _ffi as F, core, host, scenes
+
+MRE_TOL = 0.01
+PSNR_TOL = 40.0
+
+
+def make(api, desc, w=64, h=64):
+    ctx = core.Context(w, h, api=api)
+    return ctx, core.Scene(ctx, desc)
+
+
+def case_trace_golden(api, cornell_desc, cornell_oracle, golden, n_adv=3000):
+    ctx, sc = make(api, cornell_desc)
+    for flags, key in ((1, "hits_opaque"), (0, "hits_alpha")):
+        h = sc.trace_closest(golden["rays"], flags, golden["rng4"])
+        assert util.hits_equal(h, golden[key]).all(), key
+    adv = util.adversarial_rays(cornell_desc, n_adv, seed=11)
+    for flags in (0, 1):
+        a, b = sc.trace_closest(adv, flags), cornell_oracle.trace_closest(adv, flags)
+        assert util.hits_equal(a, b).all()
+    srays = golden["rays"].copy(); srays["tmin"] = 0.1; srays["tmax"] = 6.0
+    assert (sc.trace_any(srays, 0, golden["rng4"]) == golden["any_alpha"]).all()
+    assert len(sc.trace_closest(np.zeros(0, F.RAY_DTYPE))) == 0   # empty input
+
+
+def case_render_golden(api, cornell_desc, golden):
+    ctx, sc = make(api, cornell_desc)
+    for raw in golden["image_ubos"]:
+        ctx.render(sc, F.rt_ubo.from_buffer_copy(raw.tobytes()))
+    acc, out = ctx.readback()
+    assert util.mean_rel_err(acc, golden["image_acc"], 8) < MRE_TOL
+    assert util.psnr(out[..., :3], golden["image_out"][..., :3]) >= PSNR_TOL
+    for name in ("albedo", "normal", "instance", "triangle"):
+        ctx.resize(64, 64)
+        ctx.render(sc, F.rt_ubo.from_buffer_copy(golden["map_" + name + "_ubo"].tobytes()))
+        _, o = ctx.readback()
+        assert np.abs(o.astype(int) - golden["map_" + name].astype(int)).max() <= 1, name
+
+
+def case_tile_partition(api, cornell_desc, golden):
+    ctx, sc = make(api, cornell_desc)
+    u = F.rt_ubo.from_buffer_copy(golden["image_ubos"][0].tobytes())
+    ctx.render(sc, u)
+    acc_full, out_full = ctx.readback()
+    ctx.resize(64, 64)
+    for part in range(3):
+        ctx.render(sc, u, strip_rows=8, n_parts=3, part=part)
+    acc_p, out_p = ctx.readback()
+    assert (acc_full == acc_p).all() and (out_full == out_p).all()
+
+
+def case_instancing(api):
+    b = scenes.SceneBuilder()
+    m = b.add_material(scenes.material((0.8, 0.3, 0.2, 1), metallic=0.0))
+    g = b.add_geometry(*scenes.uv_sphere(1.0, 12, 16), m)
+    rng = np.random.default_rng(4)
+    for _ in range(40):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        b.add_instance(g, scenes.trs(rng.uniform(-8, 8, 3), q, rng.uniform(0.3, 1.5, 3)))
+    d = b.build()
+    o = orc.OracleScene(d)
+    ctx, sc = make(api, d, 32, 32)
+    rays, _ = util.random_rays(4000, seed=8, extent=9.0)
+    assert util.hits_equal(sc.trace_closest(rays, 1), o.trace_closest(rays, 1)).all()
+    assert sc.bvh_info().tlas_nodes >= 2
+    inst = np.frombuffer(util._arr(d.instances, d.n_instances, F.rt_instance), F.INSTANCE_DTYPE).copy()
+    inst["transform"][:, 3] += 1.5
+    sc.update_instances(inst); o.update_instances(inst)
+    assert util.hits_equal(sc.trace_closest(rays, 1), o.trace_closest(rays, 1)).all()
+
+
+def bright_lights():
+    pl = np.zeros(2, F.LIGHT_DTYPE); pl["color"] = [[1, .9, .8, 0], [.2, .4, 1, 0]]; pl["transform"] = [[0, 3, 2, 1], [-3, -2, 3, 1]]
+    pl["kind"], pl["range"], pl["intensity"] = 1, 1e30, [20, 10]
+    dl = np.zeros(1, F.LIGHT_DTYPE); dl["color"], dl["transform"], dl["intensity"] = 1, [[-.5, -1, -.3, 0]], 2.0
+    return dl, pl
+
+
+def case_lights(api, cornell_desc, size=48, frames=2):
+    o = orc.OracleScene(cornell_desc)
+    ctx, sc = make(api, cornell_desc, size, size)
+    dl, pl = bright_lights()
+    o.update_lights(dl, pl); sc.update_lights(dl, pl)
+    cam = host.Camera(size, size).set(position=(0, 0, 14)); gui = host.Gui(number_of_samples=2, number_of_bounces=6)
+    d1, d2 = host.FrameDriver(cam, gui, False), host.FrameDriver(cam, gui, False)
+    acc = None
+    for _ in range(frames):
+        acc, out, st = o.render(d1.next_ubo(), size, size, acc); ctx.render(sc, d2.next_ubo())
+    acc_e, out_e = ctx.readback()
+    s = ctx.stats()
+    assert st.rays_shadow > 0 and abs(int(s.rays_shadow) - int(st.rays_shadow)) <= 0.001 * st.rays_shadow
+    assert util.mean_rel_err(acc_e, acc, 2 * frames) < MRE_TOL and util.psnr(out_e[..., :3], out[..., :3]) >= PSNR_TOL
+
+
+def skinned_scene(seed=3, rows=24, cols=16, joints=8):
+    """Small capsule skinned to a chain of joints (config-4 shape in miniature)."""
+    rng = np.random.default_rng(seed)
+    b = scenes.SceneBuilder()
+    m = b.add_material(scenes.material((0.7, 0.7, 0.9, 1), metallic=0.0))
+    pos, nrm, uv, idx = scenes.uv_sphere(1.0, rows, cols)
+    pos = pos * np.array([0.5, 2.0, 0.5], np.float32)
+    t = (pos[:, 1] + 2.0) / 4.0 * (joints - 1)
+    j0 = np.clip(np.floor(t).astype(np.uint32), 0, joints - 2)
+    w1 = (t - j0).astype(np.float32)
+    weights = np.zeros((len(pos), 4), np.float32); jidx = np.zeros((len(pos), 4), np.uint32)
+    weights[:, 0], weights[:, 1] = 1 - w1, w1
+    jidx[:, 0], jidx[:, 1] = j0, j0 + 1
+    g = b.add_geometry(pos, nrm, uv, idx, m, weights=weights, joints=jidx, skin_index=0)
+    b.add_instance(g, np.eye(4))
+    floor_m = b.add_material(scenes.material(metallic=0.0))
+    gf = b.add_geometry(*scenes.box_mesh((4, 0.1, 4)), floor_m)
+    b.add_instance(gf, scenes.trs((0, -2.6, 0)))
+
+    def pose(phase):
+        mats = np.zeros((1, 256, 16), np.float32)
+        mats[0, :, [0, 5, 10, 15]] = 1.0
+        for j in range(joints):
+            a = 0.35 * np.sin(phase + 0.7 * j)
+            M = scenes.trs((0.3 * np.sin(phase * 1.3 + j), 0.05 * j * np.cos(phase), 0), (0, 0, np.sin(a / 2), np.cos(a / 2)))
+            mats[0, j] = M.T.reshape(16).astype(np.float32)   # column-major
+        return mats
+    b.skins = pose(0.0)
+    return b.build(), pose
+
+
+def case_skinning(api):
+    d, pose = skinned_scene()
+    o = orc.OracleScene(d)
+    ctx, sc = make(api, d, 32, 32)
+    rays, _ = util.random_rays(3000, seed=21, extent=3.0)
+    n = d.n_vertices
+    for k, phase in enumerate((0.0, 0.9, 2.3)):
+        if k:
+            mats = pose(phase)
+            sc.update_skins(mats, rebuild=(k == 2)); o.update_skins(mats)
+        vg, vo = sc.read_vertices(n), o.read_vertices(n)
+        # AnimationCompute.comp: positions within 1 ulp-ish (FMA contraction differs), skin_index etc. untouched
+        np.testing.assert_allclose(vg["position"], vo["position"], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(vg["normal"], vo["normal"], rtol=1e-5, atol=1e-5)
+        assert (vg["joints"] == vo["joints"]).all() and (vg["skin_index"] == vo["skin_index"]).all()
+        # trace against an oracle scene built from the GPU's own skinned vertices would hide skinning errors;
+        # instead compare hit/miss agreement and t within 1e-4 (the vertex positions differ by rounding)
+        hg, ho = sc.trace_closest(rays, 1), o.trace_closest(rays, 1)
+        both = (hg["t"] > 0) & (ho["t"] > 0)
+        assert ((hg["t"] > 0) != (ho["t"] > 0)).mean() < 0.002
+        np.testing.assert_allclose(hg["t"][both], ho["t"][both], rtol=1e-3, atol=1e-4)
+
+
+def case_lucy_ids(api, n_rays=100000, rows=120, cols=121):
+    d = scenes.cornell_box(lucy=True, lucy_rows=rows, lucy_cols=cols)
+    o = orc.OracleScene(d)
+    ctx, sc = make(api, d, 32, 32)
+    rays, _ = util.random_rays(n_rays, seed=5)
+    hg, ho = sc.trace_closest(rays, 1), o.trace_closest(rays, 1)
+    assert util.hits_equal(hg, ho).all()
+    return d, o, ctx, sc

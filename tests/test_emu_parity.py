@@ -1,0 +1,33 @@
+"""Pre-GPU logic checks: the CUDA core sources compiled as a host emulation (tests/emu) against the oracle.
+These do NOT establish GPU parity (tests/test_gpu_parity.py does, on the B200 box); they keep the builder,
+traversal and wavefront shading logic honest on the GPU-less build machine."""
+import parity_cases as pc
+from emu_lib import emu_api
+
+
+def test_emu_trace_ids_bit_exact(cornell_desc, cornell_oracle, golden):
+    pc.case_trace_golden(emu_api(), cornell_desc, cornell_oracle, golden)
+
+
+def test_emu_render_matches_golden(cornell_desc, golden):
+    pc.case_render_golden(emu_api(), cornell_desc, golden)
+
+
+def test_emu_tile_partition_is_bit_identical(cornell_desc, golden):
+    pc.case_tile_partition(emu_api(), cornell_desc, golden)
+
+
+def test_emu_instancing_and_tlas_update():
+    pc.case_instancing(emu_api())
+
+
+def test_emu_lights_and_shadow_rays(cornell_desc):
+    pc.case_lights(emu_api(), cornell_desc)
+
+
+def test_emu_skinning_refit_rebuild():
+    pc.case_skinning(emu_api())
+
+
+def test_emu_lucy_ids():
+    pc.case_lucy_ids(emu_api(), n_rays=20000, rows=60, cols=61)
