@@ -187,7 +187,12 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: its handle is what the C ABI launches on, so torch.cuda.Event timing
+    # brackets exactly our kernels (handle 0 would make rt_render fall back to the context's private stream)
+    tstream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     desc = build_scene_desc()
     ctx = core.Context(WIDTH, HEIGHT, device=local)

@@ -63,6 +63,7 @@ using namespace rtcore;
 struct rt_context {
     int device = 0;
     rt_stream_t stream = nullptr;
+    rt_stream_t last_stream = nullptr;   // stream of the most recent rt_render / rt_tonemap (may be caller-provided)
     uint32_t width = 0, height = 0;
     FrameBuffers fb{};
     DQueue q[2]{};
@@ -241,7 +242,7 @@ static int build_tlas(rt_scene* s) {
     const int e = build_wide_bvh(ib, n, s->scratch, out, st, &info);
     if (e) return fail("TLAS build failed (code " + std::to_string(e) + ")");
     s->tlas_nodes = info.n_nodes; s->tlas_depth = info.depth;
-    if (s->tlas_depth + s->blas_depth + 4 > RT_STACK_SIZE)
+    if (s->tlas_depth + s->blas_depth + 6 > RT_STACK_SIZE)
         return fail("BVH too deep for the traversal stack: tlas " + std::to_string(s->tlas_depth) + " + blas " + std::to_string(s->blas_depth));
     return 0;
 }
@@ -271,6 +272,13 @@ static uint32_t owned_rows(const TilePart& tp) {
     const uint32_t n_strips = (tp.height + tp.strip_rows - 1) / tp.strip_rows;
     for (uint32_t k = tp.part; k < n_strips; k += tp.n_parts) rows += ((k + 1) * tp.strip_rows <= tp.height) ? tp.strip_rows : (tp.height - k * tp.strip_rows);
     return rows;
+}
+
+static int sync_all(rt_context* c) {
+    int e = 0;
+    if (c->last_stream && c->last_stream != c->stream) e |= rt_stream_sync(c->last_stream);
+    e |= rt_stream_sync(c->stream);
+    return e;
 }
 
 static StageEvent* stage_begin(rt_context* c, bool on, int stage, rt_stream_t st) {
@@ -438,7 +446,7 @@ void RT_API(rt_context_destroy)(rt_context* c) {
 
 int RT_API(rt_frame_resize)(rt_context* c, uint32_t width, uint32_t height) {
     if (!c || !width || !height) return fail("rt_frame_resize: bad arguments");
-    rt_stream_sync(c->stream);
+    sync_all(c);
     if (alloc_frame(c, width, height)) return fail(std::string("rt_frame_resize: allocation failed: ") + rt_platform_error());
     return 0;
 }
@@ -622,6 +630,7 @@ int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_re
     cudaSetDevice(c->device);
 #endif
     rt_stream_t st = stream ? (rt_stream_t)stream : c->stream;
+    c->last_stream = st;
     FrameParams P; P.ubo = *ubo; P.width = c->width; P.height = c->height; P.sample = 0;
     P.clk = host_tea16(ubo->total_number_of_samples, ubo->random_seed);   // D1
     TilePart tp; tp.width = c->width; tp.height = c->height; tp.strip_rows = 1; tp.n_parts = 1; tp.part = 0;
@@ -652,6 +661,7 @@ int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_re
 int RT_API(rt_tonemap)(rt_context* c, const rt_ubo* ubo, void* stream) {
     if (!c || !ubo) return fail("rt_tonemap: null argument");
     rt_stream_t st = stream ? (rt_stream_t)stream : c->stream;
+    c->last_stream = st;
     FrameParams P; P.ubo = *ubo; P.width = c->width; P.height = c->height; P.sample = 0; P.clk = 0;
     TilePart tp; tp.width = c->width; tp.height = c->height; tp.strip_rows = 1; tp.n_parts = 1; tp.part = 0;
     const FrameBuffers fb = c->fb;
@@ -661,14 +671,14 @@ int RT_API(rt_tonemap)(rt_context* c, const rt_ubo* ubo, void* stream) {
 
 int RT_API(rt_synchronize)(rt_context* c) {
     if (!c) return fail("rt_synchronize: null context");
-    if (rt_stream_sync(c->stream)) return fail(std::string("rt_synchronize: ") + rt_platform_error());
+    if (sync_all(c)) return fail(std::string("rt_synchronize: ") + rt_platform_error());
     return 0;
 }
 
 int RT_API(rt_readback)(rt_context* c, float* acc, uint8_t* out) {
     if (!c) return fail("rt_readback: null context");
     const size_t n = (size_t)c->width * c->height;
-    if (rt_stream_sync(c->stream)) return fail(std::string("rt_readback: ") + rt_platform_error());
+    if (sync_all(c)) return fail(std::string("rt_readback: ") + rt_platform_error());
     if (acc) RT_CHECK(rt_d2h(acc, c->fb.acc, n * 16, c->stream), "rt_readback");
     if (out) RT_CHECK(rt_d2h(out, c->fb.out, n * 4, c->stream), "rt_readback");
     if (rt_stream_sync(c->stream)) return fail(std::string("rt_readback: ") + rt_platform_error());
@@ -693,7 +703,7 @@ int RT_API(rt_last_frame_stats)(rt_context* c, rt_stats* o) {
     if (!c || !o) return fail("rt_last_frame_stats: null argument");
     memset(o, 0, sizeof *o);
     if (!c->last_valid) return fail("rt_last_frame_stats: no frame rendered yet");
-    if (rt_stream_sync(c->stream)) return fail(std::string("rt_last_frame_stats: ") + rt_platform_error());
+    if (sync_all(c)) return fail(std::string("rt_last_frame_stats: ") + rt_platform_error());
     const size_t per = (size_t)(c->last_S ? c->last_S : 1) * (c->last_B + 1);
     std::vector<uint32_t> h(per * 2);
     RT_CHECK(rt_d2h(h.data(), c->counters, per * 2 * 4, c->stream), "rt_last_frame_stats");

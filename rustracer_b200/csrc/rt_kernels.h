@@ -188,32 +188,87 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 // ---- CUDA kernels -------------------------------------------------------------------------------------
 #define RT_EXTEND_THREADS 128
 
-template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
-    const uint32_t count = *count_ptr;
+// Persistent while-while traversal with per-lane dynamic fetch (Aila & Laine 2009; Ylitie et al. 2017): every lane
+// owns a resumable traversal state; lanes whose ray has finished store their result and, once enough of the warp
+// is idle, the idle lanes pull new rays from the queue with one warp-aggregated atomic.  MODE selects closest-hit
+// (extend) or any-hit (shadow) semantics; the two kernels differ only in how a ray is loaded and retired.
+#define RT_REFILL_BELOW 22   // refill when fewer than this many lanes are still traversing
+
+template <int MODE, bool ALPHA, bool COUNT, class LoadRay, class StoreHit>
+RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetch, RtCounters* cnt, LoadRay load_ray, StoreHit store_hit) {
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint2 stack[RT_STACK_SIZE];
+    unsigned long long c4[4] = {0, 0, 0, 0};
+    Trav tv;
+    bool active = false, exhausted = false;
+    uint32_t idx = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= count) return;
-        const uint32_t i = base + lane;
-        if (i < count) extend_item<ALPHA, COUNT>(S, P, q, hits, i, cnt);
+        if (!exhausted) {
+            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active);
+            if (need) {
+                const int leader = __ffs((int)need) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(need));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (!active) {
+                    idx = base + (uint32_t)__popc(need & lt_mask);
+                    if (idx < count) { load_ray(idx, tv); active = true; }
+                }
+                if (base + (uint32_t)__popc(need) >= count) exhausted = true;
+            }
+        }
+        uint32_t am = __ballot_sync(0xFFFFFFFFu, active);
+        if (!am) break;
+        // traverse until the warp has thinned out enough to be worth refilling
+        do {
+            if (active) {
+                if (trav_step<MODE, ALPHA, COUNT>(tv, S, stack, c4)) {
+                    trav_finish(tv);
+                    store_hit(idx, tv);
+                    active = false;
+                }
+            }
+            am = __ballot_sync(0xFFFFFFFFu, active);
+        } while (am && (exhausted || __popc(am) >= RT_REFILL_BELOW));
+    }
+    if (COUNT && cnt) {
+        atomicAdd(&cnt->nodes, c4[0]); atomicAdd(&cnt->tris, c4[1]); atomicAdd(&cnt->insts, c4[2]); atomicAdd(&cnt->anyhits, c4[3]);
     }
 }
 
 template <bool ALPHA, bool COUNT>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+    persistent_trace<RT_MODE_CLOSEST, ALPHA, COUNT>(S, *count_ptr, fetch, cnt,
+        [&](uint32_t i, Trav& tv) {
+            const float4 a = q.o_tmin[i], b = q.d_tmax[i];
+            u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
+            if (ALPHA) { const uint32_t pixel = rt_float_as_uint(q.thr_pix[i].w); rng = path_stream(P, pixel, q.rng[i].x); }
+            trav_init(tv, S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, rng);
+        },
+        [&](uint32_t i, const Trav& tv) {
+            hits.tuvp[i] = make_float4(tv.hit.t, tv.hit.u, tv.hit.v, rt_uint_as_float(tv.hit.prim));
+            hits.inst[i] = tv.hit.inst;
+        });
+}
+
+template <bool ALPHA, bool COUNT>
 __global__ void __launch_bounds__(RT_EXTEND_THREADS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
-    const uint32_t count = *count_ptr;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= count) return;
-        const uint32_t i = base + lane;
-        if (i < count) shadow_item<ALPHA, COUNT>(S, P, fb, sq, i, cnt);
-    }
+    persistent_trace<RT_MODE_ANY, ALPHA, COUNT>(S, *count_ptr, fetch, cnt,
+        [&](uint32_t i, Trav& tv) {
+            const float4 a = sq.o_tmax[i], b = sq.d_pix[i];
+            u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
+            if (ALPHA) rng = path_stream(P, rt_float_as_uint(b.w), rt_float_as_uint(sq.contrib[i].w));
+            trav_init(tv, S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.1f, a.w, rng);   // tMin 0.1: RayTracing.rchit:43
+        },
+        [&](uint32_t i, const Trav& tv) {
+            if (!tv.found) {   // unoccluded: add the light's contribution to the frame radiance of the pixel
+                const float4 c = sq.contrib[i]; const uint32_t pixel = rt_float_as_uint(sq.d_pix[i].w);
+                float4 cur = fb.rad[pixel];
+                cur.x += c.x; cur.y += c.y; cur.z += c.z;
+                fb.rad[pixel] = cur;
+            }
+        });
 }
 
 template <bool COUNT>

@@ -13,7 +13,7 @@
 // 2 -> 011, 3 -> 111), low 5 bits = first primitive offset (0..23) relative to prim_base.
 #define RT_NODE_F4 5
 #define RT_LEAF_MAX 3
-#define RT_STACK_SIZE 40
+#define RT_STACK_SIZE 48
 
 // BLAS primitive record, 48 bytes = 3 x float4: v0.xyz | primitive_id ; v1.xyz | 0 ; v2.xyz | 0
 #define RT_TRI_F4 3

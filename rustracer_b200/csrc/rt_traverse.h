@@ -66,12 +66,16 @@ RT_D f3 xform_dir_exact(float4 r0, float4 r1, float4 r2, f3 d) {
 }
 
 RT_D uint32_t byte_of(uint32_t v, int i) { return (v >> (8 * i)) & 0xFFu; }
-RT_D float safe_rcp_dir(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
+RT_D float safe_rcp_dir(float d) { return rt_rcp(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
 RT_D uint32_t octant_inv(f3 d) { return 7u - ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u)); }
 
 // Intersects the 8 quantised child boxes of one node.  Returns the hit mask: bits 24..31 inner children in
-// traversal priority order (slot ^ octinv), bits 0..23 leaf primitives.  Slab distances are padded by the
-// worst-case rounding error of the de-quantisation so the test never rejects a box the ray touches.
+// traversal priority order (slot ^ octinv), bits 0..23 leaf primitives.
+// The quantised byte q is turned into the float 2^23 + q by a byte permute (no int->float conversion: those run
+// on the quarter-rate XU pipe and dominated the first version of this kernel) and the 2^23 bias is folded into
+// the per-node plane constants.  Rounding of those constants costs at most half a quantisation step; the slab
+// distances are therefore padded by one full step plus the rounding error of the de-quantisation, so the test
+// never rejects a box the ray touches (conservative; ~1 % larger boxes).
 RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
                              f3 o, f3 idir, uint32_t octinv, float tmin, float tmax) {
     const uint32_t n0w = rt_float_as_uint(n0.w);
@@ -79,8 +83,11 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, 
     const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
     const float ox = (n0.x - o.x) * idir.x, oy = (n0.y - o.y) * idir.y, oz = (n0.z - o.z) * idir.z;
     const float EPS = 1.0e-6f;   // ~16 ulp of the magnitudes involved
-    const float px = EPS * (fabsf(ox) + 255.0f * fabsf(ax)), py = EPS * (fabsf(oy) + 255.0f * fabsf(ay)), pz = EPS * (fabsf(oz) + 255.0f * fabsf(az));
-    const float oxl = ox - px, oxh = ox + px, oyl = oy - py, oyh = oy + py, ozl = oz - pz, ozh = oz + pz;
+    const float px = fmaf(EPS, fabsf(ox) + 255.0f * fabsf(ax), fabsf(ax)), py = fmaf(EPS, fabsf(oy) + 255.0f * fabsf(ay), fabsf(ay)), pz = fmaf(EPS, fabsf(oz) + 255.0f * fabsf(az), fabsf(az));
+    const float BIAS = 8388608.0f;   // 2^23
+    const float cxn = fmaf(-BIAS, ax, ox - px), cxf = fmaf(-BIAS, ax, ox + px);
+    const float cyn = fmaf(-BIAS, ay, oy - py), cyf = fmaf(-BIAS, ay, oy + py);
+    const float czn = fmaf(-BIAS, az, oz - pz), czf = fmaf(-BIAS, az, oz + pz);
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -93,9 +100,9 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t meta = byte_of(meta4, j);
-            const float tnx = fmaf((float)byte_of(nx, j), ax, oxl), tfx = fmaf((float)byte_of(fx, j), ax, oxh);
-            const float tny = fmaf((float)byte_of(ny, j), ay, oyl), tfy = fmaf((float)byte_of(fy, j), ay, oyh);
-            const float tnz = fmaf((float)byte_of(nz, j), az, ozl), tfz = fmaf((float)byte_of(fz, j), az, ozh);
+            const float tnx = fmaf(rt_byte_to_biased_float(nx, j), ax, cxn), tfx = fmaf(rt_byte_to_biased_float(fx, j), ax, cxf);
+            const float tny = fmaf(rt_byte_to_biased_float(ny, j), ay, cyn), tfy = fmaf(rt_byte_to_biased_float(fy, j), ay, cyf);
+            const float tnz = fmaf(rt_byte_to_biased_float(nz, j), az, czn), tfz = fmaf(rt_byte_to_biased_float(fz, j), az, czf);
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
             if (cmin <= cmax) {
@@ -110,107 +117,128 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, 
 
 enum { RT_MODE_CLOSEST = 0, RT_MODE_ANY = 1 };
 
+// Resumable traversal state: init() then step() until it returns true.  The persistent extend kernel keeps one of
+// these per lane and refills finished lanes with new rays (dynamic fetch); trace_ray() below simply loops.
+struct Trav {
+    f3 ow, dw; float tmin, tmax;          // world ray
+    f3 o, idir; uint32_t octinv;          // current-level ray (world in the TLAS, object space inside a BLAS)
+    RayShear sh;
+    const float4* nodes; const float4* tris;
+    int blas_sp;                          // stack height at BLAS entry; -1 = in the TLAS
+    uint32_t cur_inst, cur_geo; bool cur_alpha;
+    uint2 ngroup, tgroup; int sp;
+    RtHit hit; bool found;
+    u4 rng;
+};
+
+RT_D void trav_set_level_ray(Trav& t, f3 o, f3 d) {
+    t.o = o; t.idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z)); t.octinv = octant_inv(d);
+}
+
+RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tmax, u4 rng) {
+    t.ow = ow; t.dw = dw; t.tmin = tmin; t.tmax = tmax; t.rng = rng;
+    trav_set_level_ray(t, ow, dw);
+    t.sh.kx = 0; t.sh.ky = 1; t.sh.kz = 2; t.sh.Sx = t.sh.Sy = t.sh.Sz = 0.0f;
+    t.nodes = S.tlas_nodes; t.tris = S.tris; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false;
+    t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u); t.sp = 0;
+    t.hit.t = tmax; t.hit.u = 0.0f; t.hit.v = 0.0f; t.hit.inst = 0xFFFFFFFFu; t.hit.prim = 0xFFFFFFFFu; t.found = false;
+}
+
+// One iteration of the while-while loop: visit at most one node, then drain (or postpone) its primitive group, then
+// pop.  Returns true when the ray is finished.
 // MODE: closest / any (terminate on first accepted hit).  ALPHA: run the alpha test on non-opaque geometry
 // (false == gl_RayFlagsOpaqueEXT / the reference's `fully_opaque` pipeline without any-hit shaders).
 template <int MODE, bool ALPHA, bool COUNT>
+RT_D bool trav_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
+    if (t.ngroup.y > 0x00FFFFFFu) {
+        const uint32_t hits = t.ngroup.y, imask = t.ngroup.y;
+        const int child_bit = rt_bfind(hits);
+        const uint32_t child_base = t.ngroup.x;
+        t.ngroup.y &= ~(1u << child_bit);
+        if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
+        const uint32_t slot = (uint32_t)(child_bit - 24) ^ (t.octinv & 7u);
+        const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+        const float4* np = t.nodes + (size_t)(child_base + rel) * RT_NODE_F4;
+        const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4);
+        if (COUNT) c4[0]++;
+        const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, t.o, t.idir, t.octinv, t.tmin, t.hit.t);
+        t.ngroup.x = rt_float_as_uint(n1.x); t.tgroup.x = rt_float_as_uint(n1.y);
+        t.ngroup.y = (hm & 0xFF000000u) | (rt_float_as_uint(n0.w) >> 24);
+        t.tgroup.y = hm & 0x00FFFFFFu;
+    } else {
+        t.tgroup = t.ngroup; t.ngroup = make_uint2(0u, 0u);
+    }
+
+    while (t.tgroup.y != 0u) {
+        const int bit = rt_bfind(t.tgroup.y);
+        t.tgroup.y &= ~(1u << bit);
+        if (t.blas_sp < 0) {
+            // TLAS leaf: enter the instance's BLAS.  Remaining TLAS work goes on the stack first.
+            const uint32_t inst = rt_ld(S.tlas_prims + t.tgroup.x + bit);
+            if (t.tgroup.y) stack[t.sp++] = t.tgroup;
+            if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
+            const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
+            const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
+            if (COUNT) c4[2]++;
+            const f3 od = xform_dir_exact(r0, r1, r2, t.dw);
+            trav_set_level_ray(t, xform_point_exact(r0, r1, r2, t.ow), od);
+            t.sh = shear_init(od);
+            t.cur_inst = inst; t.cur_geo = rt_float_as_uint(meta.y);
+            t.cur_alpha = ALPHA && !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
+            // node / primitive indices inside a BLAS are local to it: rebase the array pointers
+            t.nodes = S.blas_nodes + (size_t)rt_float_as_uint(meta.x) * RT_NODE_F4;
+            t.tris = S.tris + (size_t)rt_float_as_uint(meta.w) * RT_TRI_F4;
+            t.blas_sp = t.sp;
+            // the root is entered through a virtual parent whose only inner child is node 0
+            // (child_bit = 31, imask byte = 0 -> relative index 0)
+            t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u);
+            break;
+        } else {
+            const float4* tp = t.tris + (size_t)(t.tgroup.x + bit) * RT_TRI_F4;
+            const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
+            if (COUNT) c4[1]++;
+            float tt, bu, bv;
+            if (!tri_test(t.sh, t.o, xyz(a), xyz(b), xyz(c), t.tmin, t.tmax, tt, bu, bv)) continue;
+            const uint32_t prim = rt_float_as_uint(a.w);
+            if (t.found) {
+                if (tt > t.hit.t) continue;
+                if (tt == t.hit.t && !(t.cur_inst < t.hit.inst || (t.cur_inst == t.hit.inst && prim < t.hit.prim))) continue;
+            }
+            if (ALPHA && t.cur_alpha) {
+                if (COUNT) c4[3]++;
+                if (anyhit_ignore(S, t.cur_inst, prim, t.cur_geo, bu, bv, t.rng)) continue;
+            }
+            t.hit.t = tt; t.hit.u = bu; t.hit.v = bv; t.hit.inst = t.cur_inst; t.hit.prim = prim; t.found = true;
+            if (MODE == RT_MODE_ANY) return true;
+        }
+    }
+
+    if (t.ngroup.y <= 0x00FFFFFFu) {
+        if (t.blas_sp >= 0 && t.sp == t.blas_sp) {
+            // BLAS exhausted: back to world space
+            t.blas_sp = -1; t.nodes = S.tlas_nodes;
+            trav_set_level_ray(t, t.ow, t.dw);
+        }
+        if (t.sp == 0) return true;
+        t.ngroup = stack[--t.sp];
+    }
+    return false;
+}
+
+RT_D void trav_finish(Trav& t) { if (!t.found) t.hit.t = -1.0f; }
+
+template <int MODE, bool ALPHA, bool COUNT>
 RT_D bool trace_ray(const DScene& S, f3 ow, f3 dw, float tmin, float tmax, u4 rng, RtHit& hit, RtCounters* cnt) {
     uint2 stack[RT_STACK_SIZE];
-    int sp = 0;
-    hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.inst = 0xFFFFFFFFu; hit.prim = 0xFFFFFFFFu;
-    bool found = false;
-
-    // current-level ray (world in the TLAS, object space inside a BLAS)
-    f3 o = ow, d = dw;
-    f3 idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-    uint32_t octinv = octant_inv(d);
-    RayShear sh; sh.kx = 0; sh.ky = 1; sh.kz = 2; sh.Sx = sh.Sy = sh.Sz = 0.0f;
-    const float4* nodes = S.tlas_nodes;
-    const float4* tris = S.tris;
-    int blas_sp = -1;            // stack height at BLAS entry; -1 = in the TLAS
-    uint32_t cur_inst = 0, cur_geo = 0; bool cur_alpha = false;
-    unsigned long long c_nodes = 0, c_tris = 0, c_insts = 0, c_any = 0;
-
-    uint2 ngroup = make_uint2(0u, 0x80000000u), tgroup = make_uint2(0u, 0u);
-    for (;;) {
-        if (ngroup.y > 0x00FFFFFFu) {
-            const uint32_t hits = ngroup.y, imask = ngroup.y;
-            const int child_bit = rt_bfind(hits);
-            const uint32_t child_base = ngroup.x;
-            ngroup.y &= ~(1u << child_bit);
-            if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
-            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (octinv & 7u);
-            const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-            const float4* np = nodes + (size_t)(child_base + rel) * RT_NODE_F4;
-            const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4);
-            if (COUNT) c_nodes++;
-            const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, o, idir, octinv, tmin, hit.t);
-            ngroup.x = rt_float_as_uint(n1.x); tgroup.x = rt_float_as_uint(n1.y);
-            ngroup.y = (hm & 0xFF000000u) | (rt_float_as_uint(n0.w) >> 24);
-            tgroup.y = hm & 0x00FFFFFFu;
-        } else {
-            tgroup = ngroup; ngroup = make_uint2(0u, 0u);
-        }
-
-        while (tgroup.y != 0u) {
-            const int bit = rt_bfind(tgroup.y);
-            tgroup.y &= ~(1u << bit);
-            if (blas_sp < 0) {
-                // TLAS leaf: enter the instance's BLAS.  Remaining TLAS work goes on the stack first.
-                const uint32_t inst = rt_ld(S.tlas_prims + tgroup.x + bit);
-                if (tgroup.y) stack[sp++] = tgroup;
-                if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
-                const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
-                const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
-                if (COUNT) c_insts++;
-                o = xform_point_exact(r0, r1, r2, ow); d = xform_dir_exact(r0, r1, r2, dw);
-                idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-                octinv = octant_inv(d);
-                sh = shear_init(d);
-                cur_inst = inst; cur_geo = rt_float_as_uint(meta.y);
-                cur_alpha = ALPHA && !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
-                // node / primitive indices inside a BLAS are local to it: rebase the array pointers
-                nodes = S.blas_nodes + (size_t)rt_float_as_uint(meta.x) * RT_NODE_F4;
-                tris = S.tris + (size_t)rt_float_as_uint(meta.w) * RT_TRI_F4;
-                blas_sp = sp;
-                // the root is entered through a virtual parent whose only inner child is node 0
-                // (child_bit = 31, imask byte = 0 -> relative index 0)
-                ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
-                break;
-            } else {
-                const float4* tp = tris + (size_t)(tgroup.x + bit) * RT_TRI_F4;
-                const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
-                if (COUNT) c_tris++;
-                float t, bu, bv;
-                if (!tri_test(sh, o, xyz(a), xyz(b), xyz(c), tmin, tmax, t, bu, bv)) continue;
-                const uint32_t prim = rt_float_as_uint(a.w);
-                if (found) {
-                    if (t > hit.t) continue;
-                    if (t == hit.t && !(cur_inst < hit.inst || (cur_inst == hit.inst && prim < hit.prim))) continue;
-                }
-                if (ALPHA && cur_alpha) {
-                    if (COUNT) c_any++;
-                    if (anyhit_ignore(S, cur_inst, prim, cur_geo, bu, bv, rng)) continue;
-                }
-                hit.t = t; hit.u = bu; hit.v = bv; hit.inst = cur_inst; hit.prim = prim; found = true;
-                if (MODE == RT_MODE_ANY) goto done;
-            }
-        }
-        if (ngroup.y <= 0x00FFFFFFu) {
-            if (blas_sp >= 0 && sp == blas_sp) {
-                // BLAS exhausted: back to world space
-                blas_sp = -1; nodes = S.tlas_nodes; o = ow; d = dw;
-                idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-                octinv = octant_inv(d);
-            }
-            if (sp == 0) break;
-            ngroup = stack[--sp];
-        }
-    }
-done:
+    unsigned long long c4[4] = {0, 0, 0, 0};
+    Trav t;
+    trav_init(t, S, ow, dw, tmin, tmax, rng);
+    while (!trav_step<MODE, ALPHA, COUNT>(t, S, stack, c4)) {}
+    trav_finish(t);
     if (COUNT && cnt) {
-        rt_atomic_add64(&cnt->nodes, c_nodes); rt_atomic_add64(&cnt->tris, c_tris);
-        rt_atomic_add64(&cnt->insts, c_insts); rt_atomic_add64(&cnt->anyhits, c_any);
+        rt_atomic_add64(&cnt->nodes, c4[0]); rt_atomic_add64(&cnt->tris, c4[1]);
+        rt_atomic_add64(&cnt->insts, c4[2]); rt_atomic_add64(&cnt->anyhits, c4[3]);
     }
-    if (!found) hit.t = -1.0f;
-    return found;
+    hit = t.hit;
+    return t.found;
 }
