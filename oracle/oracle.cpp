@@ -266,7 +266,7 @@ struct RayShear {
         if (std::fabs(d.z) > std::fabs(d[kz])) kz = 2;
         kx = kz + 1; if (kx == 3) kx = 0;
         ky = kx + 1; if (ky == 3) ky = 0;
-        if (d[kz] < 0.0f) std::swap(kx, ky);
+        // kx/ky swap of the paper omitted: result-neutral for the two-sided test (see rt_traverse.h)
         Sx = d[kx] / d[kz]; Sy = d[ky] / d[kz]; Sz = 1.0f / d[kz];
     }
 };
@@ -289,9 +289,10 @@ inline bool tri_test(const RayShear& r, vec3 v0, vec3 v1, vec3 v2, float tmin, f
     if (det == 0.0f) return false;
     const float Az = r.Sz * A[r.kz], Bz = r.Sz * B[r.kz], Cz = r.Sz * C[r.kz];
     const float T = (U * Az + V * Bz) + W * Cz;
-    const float tt = T / det;
+    const float inv = 1.0f / det;
+    const float tt = T * inv;
     if (!(tt > tmin && tt < tmax)) return false;   // open interval (Vulkan: tMin < t < tMax)
-    t = tt; bu = V / det; bv = W / det;
+    t = tt; bu = V * inv; bv = W * inv;
     return true;
 }
 

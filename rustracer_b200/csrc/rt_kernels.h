@@ -220,14 +220,14 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
         }
         uint32_t am = __ballot_sync(0xFFFFFFFFu, active);
         if (!am) break;
-        // traverse until the warp has thinned out enough to be worth refilling
+        // while-while: node phase for every lane that holds no primitives, then primitive phase; repeat until the
+        // warp has thinned out enough to be worth refilling
         do {
-            if (active) {
-                if (trav_step<MODE, ALPHA, COUNT>(tv, S, stack, c4)) {
-                    trav_finish(tv);
-                    store_hit(idx, tv);
-                    active = false;
-                }
+            while (active && tv.tgroup.y == 0u) {
+                if (trav_node_step<COUNT>(tv, S, stack, c4)) { trav_finish(tv); store_hit(idx, tv); active = false; }
+            }
+            while (active && tv.tgroup.y != 0u) {
+                if (trav_prim_step<MODE, ALPHA, COUNT>(tv, S, stack, c4)) { trav_finish(tv); store_hit(idx, tv); active = false; }
             }
             am = __ballot_sync(0xFFFFFFFFu, active);
         } while (am && (exhausted || __popc(am) >= RT_REFILL_BELOW));

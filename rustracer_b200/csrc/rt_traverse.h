@@ -18,7 +18,8 @@ RT_D RayShear shear_init(f3 d) {
     int kx = kz + 1; if (kx == 3) kx = 0;
     int ky = kx + 1; if (ky == 3) ky = 0;
     const float dz = comp(d, kz);
-    if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }
+    // (the paper swaps kx/ky when d[kz] < 0 to preserve winding; for a two-sided test the swap negates U, V, W, det
+    //  and T together and leaves t, u, v bit-identical, so it is omitted here and in the oracle)
     r.kx = kx; r.ky = ky; r.kz = kz;
     r.Sx = rt_fdiv(comp(d, kx), dz); r.Sy = rt_fdiv(comp(d, ky), dz); r.Sz = rt_fdiv(1.0f, dz);
     return r;
@@ -47,9 +48,10 @@ RT_D bool tri_test(const RayShear& r, f3 o, f3 v0, f3 v1, f3 v2, float tmin, flo
     if (det == 0.0f) return false;
     const float Az = rt_fmul(r.Sz, Akz), Bz = rt_fmul(r.Sz, Bkz), Cz = rt_fmul(r.Sz, Ckz);
     const float T = rt_fadd(rt_fadd(rt_fmul(U, Az), rt_fmul(V, Bz)), rt_fmul(W, Cz));
-    const float tt = rt_fdiv(T, det);
+    const float inv = rt_fdiv(1.0f, det);
+    const float tt = rt_fmul(T, inv);
     if (!(tt > tmin && tt < tmax)) return false;
-    t = tt; bu = rt_fdiv(V, det); bv = rt_fdiv(W, det);
+    t = tt; bu = rt_fmul(V, inv); bv = rt_fmul(W, inv);
     return true;
 }
 
@@ -144,12 +146,19 @@ RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tm
     t.hit.t = tmax; t.hit.u = 0.0f; t.hit.v = 0.0f; t.hit.inst = 0xFFFFFFFFu; t.hit.prim = 0xFFFFFFFFu; t.found = false;
 }
 
-// One iteration of the while-while loop: visit at most one node, then drain (or postpone) its primitive group, then
-// pop.  Returns true when the ray is finished.
+// The traversal is a "while-while" loop (Aila & Laine 2009) over two kinds of steps:
+//   node step : precondition tgroup empty.  Visits the next inner child of ngroup (one 80-byte node, 8 box tests) or,
+//               when ngroup holds no more inner children, leaves the BLAS / pops the stack.  Returns true when the
+//               ray has no work left.
+//   prim step : precondition tgroup non-empty.  Takes one primitive of tgroup: a triangle (watertight test, alpha
+//               test, commit) inside a BLAS, or an instance (ray transform, BLAS entry) in the TLAS.  Returns true
+//               when an any-hit ray terminates.
+// A warp runs all its lanes through node steps until every lane holds primitives, then through prim steps: both
+// phases execute with most lanes active instead of interleaving per lane.
 // MODE: closest / any (terminate on first accepted hit).  ALPHA: run the alpha test on non-opaque geometry
 // (false == gl_RayFlagsOpaqueEXT / the reference's `fully_opaque` pipeline without any-hit shaders).
-template <int MODE, bool ALPHA, bool COUNT>
-RT_D bool trav_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
+template <bool COUNT>
+RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
     if (t.ngroup.y > 0x00FFFFFFu) {
         const uint32_t hits = t.ngroup.y, imask = t.ngroup.y;
         const int child_bit = rt_bfind(hits);
@@ -165,64 +174,61 @@ RT_D bool trav_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* 
         t.ngroup.x = rt_float_as_uint(n1.x); t.tgroup.x = rt_float_as_uint(n1.y);
         t.ngroup.y = (hm & 0xFF000000u) | (rt_float_as_uint(n0.w) >> 24);
         t.tgroup.y = hm & 0x00FFFFFFu;
-    } else {
-        t.tgroup = t.ngroup; t.ngroup = make_uint2(0u, 0u);
+        return false;
     }
-
-    while (t.tgroup.y != 0u) {
-        const int bit = rt_bfind(t.tgroup.y);
-        t.tgroup.y &= ~(1u << bit);
-        if (t.blas_sp < 0) {
-            // TLAS leaf: enter the instance's BLAS.  Remaining TLAS work goes on the stack first.
-            const uint32_t inst = rt_ld(S.tlas_prims + t.tgroup.x + bit);
-            if (t.tgroup.y) stack[t.sp++] = t.tgroup;
-            if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
-            const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
-            const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
-            if (COUNT) c4[2]++;
-            const f3 od = xform_dir_exact(r0, r1, r2, t.dw);
-            trav_set_level_ray(t, xform_point_exact(r0, r1, r2, t.ow), od);
-            t.sh = shear_init(od);
-            t.cur_inst = inst; t.cur_geo = rt_float_as_uint(meta.y);
-            t.cur_alpha = ALPHA && !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
-            // node / primitive indices inside a BLAS are local to it: rebase the array pointers
-            t.nodes = S.blas_nodes + (size_t)rt_float_as_uint(meta.x) * RT_NODE_F4;
-            t.tris = S.tris + (size_t)rt_float_as_uint(meta.w) * RT_TRI_F4;
-            t.blas_sp = t.sp;
-            // the root is entered through a virtual parent whose only inner child is node 0
-            // (child_bit = 31, imask byte = 0 -> relative index 0)
-            t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u);
-            break;
-        } else {
-            const float4* tp = t.tris + (size_t)(t.tgroup.x + bit) * RT_TRI_F4;
-            const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
-            if (COUNT) c4[1]++;
-            float tt, bu, bv;
-            if (!tri_test(t.sh, t.o, xyz(a), xyz(b), xyz(c), t.tmin, t.tmax, tt, bu, bv)) continue;
-            const uint32_t prim = rt_float_as_uint(a.w);
-            if (t.found) {
-                if (tt > t.hit.t) continue;
-                if (tt == t.hit.t && !(t.cur_inst < t.hit.inst || (t.cur_inst == t.hit.inst && prim < t.hit.prim))) continue;
-            }
-            if (ALPHA && t.cur_alpha) {
-                if (COUNT) c4[3]++;
-                if (anyhit_ignore(S, t.cur_inst, prim, t.cur_geo, bu, bv, t.rng)) continue;
-            }
-            t.hit.t = tt; t.hit.u = bu; t.hit.v = bv; t.hit.inst = t.cur_inst; t.hit.prim = prim; t.found = true;
-            if (MODE == RT_MODE_ANY) return true;
-        }
+    if (t.blas_sp >= 0 && t.sp == t.blas_sp) {
+        // BLAS exhausted: back to world space
+        t.blas_sp = -1; t.nodes = S.tlas_nodes;
+        trav_set_level_ray(t, t.ow, t.dw);
     }
-
-    if (t.ngroup.y <= 0x00FFFFFFu) {
-        if (t.blas_sp >= 0 && t.sp == t.blas_sp) {
-            // BLAS exhausted: back to world space
-            t.blas_sp = -1; t.nodes = S.tlas_nodes;
-            trav_set_level_ray(t, t.ow, t.dw);
-        }
-        if (t.sp == 0) return true;
-        t.ngroup = stack[--t.sp];
-    }
+    if (t.sp == 0) return true;
+    const uint2 e = stack[--t.sp];
+    if (e.y > 0x00FFFFFFu) { t.ngroup = e; } else { t.tgroup = e; t.ngroup = make_uint2(0u, 0u); }
     return false;
+}
+
+template <int MODE, bool ALPHA, bool COUNT>
+RT_D bool trav_prim_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
+    const int bit = rt_bfind(t.tgroup.y);
+    t.tgroup.y &= ~(1u << bit);
+    if (t.blas_sp < 0) {
+        // TLAS leaf: enter the instance's BLAS.  Remaining TLAS work goes on the stack first.
+        const uint32_t inst = rt_ld(S.tlas_prims + t.tgroup.x + bit);
+        if (t.tgroup.y) stack[t.sp++] = t.tgroup;
+        if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
+        const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
+        const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
+        if (COUNT) c4[2]++;
+        const f3 od = xform_dir_exact(r0, r1, r2, t.dw);
+        trav_set_level_ray(t, xform_point_exact(r0, r1, r2, t.ow), od);
+        t.sh = shear_init(od);
+        t.cur_inst = inst; t.cur_geo = rt_float_as_uint(meta.y);
+        t.cur_alpha = ALPHA && !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
+        // node / primitive indices inside a BLAS are local to it: rebase the array pointers
+        t.nodes = S.blas_nodes + (size_t)rt_float_as_uint(meta.x) * RT_NODE_F4;
+        t.tris = S.tris + (size_t)rt_float_as_uint(meta.w) * RT_TRI_F4;
+        t.blas_sp = t.sp;
+        // the root is entered through a virtual parent whose only inner child is node 0
+        // (child_bit = 31, imask byte = 0 -> relative index 0)
+        t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u);
+        return false;
+    }
+    const float4* tp = t.tris + (size_t)(t.tgroup.x + bit) * RT_TRI_F4;
+    const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
+    if (COUNT) c4[1]++;
+    float tt, bu, bv;
+    if (!tri_test(t.sh, t.o, xyz(a), xyz(b), xyz(c), t.tmin, t.tmax, tt, bu, bv)) return false;
+    const uint32_t prim = rt_float_as_uint(a.w);
+    if (t.found) {
+        if (tt > t.hit.t) return false;
+        if (tt == t.hit.t && !(t.cur_inst < t.hit.inst || (t.cur_inst == t.hit.inst && prim < t.hit.prim))) return false;
+    }
+    if (ALPHA && t.cur_alpha) {
+        if (COUNT) c4[3]++;
+        if (anyhit_ignore(S, t.cur_inst, prim, t.cur_geo, bu, bv, t.rng)) return false;
+    }
+    t.hit.t = tt; t.hit.u = bu; t.hit.v = bv; t.hit.inst = t.cur_inst; t.hit.prim = prim; t.found = true;
+    return MODE == RT_MODE_ANY;
 }
 
 RT_D void trav_finish(Trav& t) { if (!t.found) t.hit.t = -1.0f; }
@@ -233,7 +239,11 @@ RT_D bool trace_ray(const DScene& S, f3 ow, f3 dw, float tmin, float tmax, u4 rn
     unsigned long long c4[4] = {0, 0, 0, 0};
     Trav t;
     trav_init(t, S, ow, dw, tmin, tmax, rng);
-    while (!trav_step<MODE, ALPHA, COUNT>(t, S, stack, c4)) {}
+    bool done = false;
+    while (!done) {
+        while (!done && t.tgroup.y == 0u) done = trav_node_step<COUNT>(t, S, stack, c4);
+        while (!done && t.tgroup.y != 0u) done = trav_prim_step<MODE, ALPHA, COUNT>(t, S, stack, c4);
+    }
     trav_finish(t);
     if (COUNT && cnt) {
         rt_atomic_add64(&cnt->nodes, c4[0]); rt_atomic_add64(&cnt->tris, c4[1]);
