@@ -188,19 +188,104 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 // ---- CUDA kernels -------------------------------------------------------------------------------------
 #define RT_EXTEND_THREADS 128
 
-// Persistent while-while traversal with per-lane dynamic fetch (Aila & Laine 2009; Ylitie et al. 2017): every lane
-// owns a resumable traversal state; lanes whose ray has finished store their result and, once enough of the warp
-// is idle, the idle lanes pull new rays from the queue with one warp-aggregated atomic.  MODE selects closest-hit
-// (extend) or any-hit (shadow) semantics; the two kernels differ only in how a ray is loaded and retired.
-#define RT_REFILL_BELOW 22   // refill when fewer than this many lanes are still traversing
+// Persistent traversal kernel body.
+//  * per-lane dynamic fetch (Aila & Laine 2009; Ylitie et al. 2017): every lane owns a resumable traversal state;
+//    finished lanes store their result and, once enough of the warp is idle, pull new rays from the queue with one
+//    warp-aggregated atomic.
+//  * warp-cooperative triangle tests: a lane that reaches leaves does not test its triangles itself (leaf sizes vary
+//    from 1 to 24 triangles, which left ~3 of 32 lanes busy in the first version of this kernel, profiles/r01).  It
+//    parks them; when the warp has collected enough parked triangles, they are dealt out one (ray, triangle) pair per
+//    lane through shared memory, tested by all lanes at once, and the per-ray winner (min t, then min primitive id)
+//    is resolved with shared-memory atomics and handed back to the owning lane.
+// MODE selects closest-hit (extend) or any-hit (shadow) semantics.
+#define RT_REFILL_BELOW 22     // refill when fewer than this many lanes still hold a ray
+#define RT_COOP_THRESHOLD 24   // run a cooperative round once this many triangles are parked in the warp
+#define RT_WARPS_PER_BLOCK (RT_EXTEND_THREADS / 32)
+
+struct CoopShared {            // one per warp; SoA over the 32 owner lanes
+    float ox[32], oy[32], oz[32], Sx[32], Sy[32], Sz[32], tmin[32], tmax[32], cur_t[32], u[32], v[32];
+    uint32_t kxyz[32], tri_base[32], tmask[32], off[32], best_t[32], best_prim[32];
+    uint32_t inst[32], geo[32], alpha[32], rng[4][32];
+};
+
+template <int MODE, bool ALPHA, bool COUNT>
+RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, bool pending, bool& active, uint32_t lane, unsigned long long* c4) {
+    const uint32_t k = pending ? (uint32_t)__popc(tv.tgroup.y) : 0u;
+    uint32_t incl = k;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += n; }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint32_t off = incl - k;
+    sh.off[lane] = off;
+    if (k) {
+        sh.ox[lane] = tv.o.x; sh.oy[lane] = tv.o.y; sh.oz[lane] = tv.o.z;
+        sh.Sx[lane] = tv.sh.Sx; sh.Sy[lane] = tv.sh.Sy; sh.Sz[lane] = tv.sh.Sz;
+        sh.tmin[lane] = tv.tmin; sh.tmax[lane] = tv.tmax; sh.cur_t[lane] = tv.found ? tv.hit.t : tv.tmax;
+        sh.kxyz[lane] = (uint32_t)tv.sh.kx | ((uint32_t)tv.sh.ky << 2) | ((uint32_t)tv.sh.kz << 4);
+        sh.tri_base[lane] = tv.tri_off + tv.tgroup.x; sh.tmask[lane] = tv.tgroup.y;
+        sh.best_t[lane] = 0xFFFFFFFFu; sh.best_prim[lane] = 0xFFFFFFFFu;
+        if (ALPHA) {
+            sh.inst[lane] = tv.cur_inst; sh.geo[lane] = tv.cur_geo; sh.alpha[lane] = tv.cur_alpha ? 1u : 0u;
+            sh.rng[0][lane] = tv.rng.x; sh.rng[1][lane] = tv.rng.y; sh.rng[2][lane] = tv.rng.z; sh.rng[3][lane] = tv.rng.w;
+        }
+    }
+    __syncwarp();
+    // one (ray, triangle) pair per lane: item j = lane of the first min(total, 32) parked triangles
+    bool hit = false; float tt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t prim = 0, owner = 0, key = 0;
+    if (lane < total) {
+        uint32_t lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) if (sh.off[lo + step] <= lane) lo += step;   // last lane whose offset <= j
+        owner = lo;
+        const uint32_t n = lane - sh.off[owner];
+        const int bit = (int)__fns(sh.tmask[owner], 0u, (int)n + 1);
+        const float4* tp = S.tris + (size_t)(sh.tri_base[owner] + (uint32_t)bit) * RT_TRI_F4;
+        const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
+        if (COUNT) c4[1]++;
+        RayShear rs; const uint32_t kk = sh.kxyz[owner];
+        rs.kx = (int)(kk & 3u); rs.ky = (int)((kk >> 2) & 3u); rs.kz = (int)((kk >> 4) & 3u);
+        rs.Sx = sh.Sx[owner]; rs.Sy = sh.Sy[owner]; rs.Sz = sh.Sz[owner];
+        hit = tri_test(rs, mk3(sh.ox[owner], sh.oy[owner], sh.oz[owner]), xyz(a), xyz(b), xyz(c), sh.tmin[owner], sh.tmax[owner], tt, bu, bv);
+        prim = rt_float_as_uint(a.w);
+        if (hit && tt > sh.cur_t[owner]) hit = false;            // cannot beat the owner's committed hit
+        if (ALPHA && hit && sh.alpha[owner]) {
+            if (COUNT) c4[3]++;
+            u4 rng; rng.x = sh.rng[0][owner]; rng.y = sh.rng[1][owner]; rng.z = sh.rng[2][owner]; rng.w = sh.rng[3][owner];
+            if (anyhit_ignore(S, sh.inst[owner], prim, sh.geo[owner], bu, bv, rng)) hit = false;
+        }
+        if (hit) { key = float_to_ordered(tt); atomicMin(&sh.best_t[owner], key); }
+    }
+    __syncwarp();
+    if (hit && key == sh.best_t[owner]) atomicMin(&sh.best_prim[owner], prim);
+    __syncwarp();
+    if (hit && key == sh.best_t[owner] && prim == sh.best_prim[owner]) { sh.u[owner] = bu; sh.v[owner] = bv; }
+    __syncwarp();
+    if (k) {
+        // retire the triangles that were dealt out this round (the lowest `done` set bits of the mask)
+        const uint32_t done = off >= 32u ? 0u : (k < 32u - off ? k : 32u - off);
+        if (done == k) tv.tgroup.y = 0u;
+        else for (uint32_t i = 0; i < done; ++i) tv.tgroup.y &= tv.tgroup.y - 1u;
+        if (sh.best_t[lane] != 0xFFFFFFFFu) {
+            const float ct = ordered_to_float(sh.best_t[lane]); const uint32_t cp = sh.best_prim[lane];
+            if (trav_candidate_wins(tv, ct, cp)) {
+                trav_commit(tv, ct, sh.u[lane], sh.v[lane], cp);
+                if (MODE == RT_MODE_ANY) active = false;   // caller stores the result
+            }
+        }
+    }
+    __syncwarp();
+}
 
 template <int MODE, bool ALPHA, bool COUNT, class LoadRay, class StoreHit>
 RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetch, RtCounters* cnt, LoadRay load_ray, StoreHit store_hit) {
+    __shared__ CoopShared coop_smem[RT_WARPS_PER_BLOCK];
+    CoopShared& sh = coop_smem[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint2 stack[RT_STACK_SIZE];
     unsigned long long c4[4] = {0, 0, 0, 0};
     Trav tv;
+    tv.tgroup = make_uint2(0u, 0u);
     bool active = false, exhausted = false;
     uint32_t idx = 0;
     for (;;) {
@@ -220,14 +305,25 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
         }
         uint32_t am = __ballot_sync(0xFFFFFFFFu, active);
         if (!am) break;
-        // while-while: node phase for every lane that holds no primitives, then primitive phase; repeat until the
-        // warp has thinned out enough to be worth refilling
         do {
-            while (active && tv.tgroup.y == 0u) {
-                if (trav_node_step<COUNT>(tv, S, stack, c4)) { trav_finish(tv); store_hit(idx, tv); active = false; }
+            bool pending = false;
+            if (active) {
+                if (tv.tgroup.y != 0u) {
+                    if (tv.blas_sp < 0) trav_enter_instance<ALPHA, COUNT>(tv, S, stack, c4);
+                    else pending = true;                       // parked triangles wait for a cooperative round
+                } else if (trav_node_step<COUNT>(tv, S, stack, c4)) {
+                    trav_finish(tv); store_hit(idx, tv); active = false;
+                }
             }
-            while (active && tv.tgroup.y != 0u) {
-                if (trav_prim_step<MODE, ALPHA, COUNT>(tv, S, stack, c4)) { trav_finish(tv); store_hit(idx, tv); active = false; }
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pending);
+            if (pm) {
+                const uint32_t parked = __reduce_add_sync(0xFFFFFFFFu, pending ? (uint32_t)__popc(tv.tgroup.y) : 0u);
+                const uint32_t stepping = __ballot_sync(0xFFFFFFFFu, active && !pending);
+                if (parked >= RT_COOP_THRESHOLD || !stepping) {
+                    const bool was_active = active;
+                    coop_round<MODE, ALPHA, COUNT>(tv, S, sh, pending, active, lane, c4);
+                    if (MODE == RT_MODE_ANY && was_active && !active) { trav_finish(tv); store_hit(idx, tv); }
+                }
             }
             am = __ballot_sync(0xFFFFFFFFu, active);
         } while (am && (exhausted || __popc(am) >= RT_REFILL_BELOW));

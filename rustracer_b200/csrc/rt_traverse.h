@@ -125,7 +125,7 @@ struct Trav {
     f3 ow, dw; float tmin, tmax;          // world ray
     f3 o, idir; uint32_t octinv;          // current-level ray (world in the TLAS, object space inside a BLAS)
     RayShear sh;
-    const float4* nodes; const float4* tris;
+    const float4* nodes; uint32_t tri_off;   // BLAS node array (rebased) and first triangle of the current BLAS
     int blas_sp;                          // stack height at BLAS entry; -1 = in the TLAS
     uint32_t cur_inst, cur_geo; bool cur_alpha;
     uint2 ngroup, tgroup; int sp;
@@ -141,7 +141,7 @@ RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tm
     t.ow = ow; t.dw = dw; t.tmin = tmin; t.tmax = tmax; t.rng = rng;
     trav_set_level_ray(t, ow, dw);
     t.sh.kx = 0; t.sh.ky = 1; t.sh.kz = 2; t.sh.Sx = t.sh.Sy = t.sh.Sz = 0.0f;
-    t.nodes = S.tlas_nodes; t.tris = S.tris; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false;
+    t.nodes = S.tlas_nodes; t.tri_off = 0; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false;
     t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u); t.sp = 0;
     t.hit.t = tmax; t.hit.u = 0.0f; t.hit.v = 0.0f; t.hit.inst = 0xFFFFFFFFu; t.hit.prim = 0xFFFFFFFFu; t.found = false;
 }
@@ -187,47 +187,59 @@ RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
     return false;
 }
 
-template <int MODE, bool ALPHA, bool COUNT>
-RT_D bool trav_prim_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
+// TLAS leaf: enter the BLAS of the instance at bit `bit` of tgroup.  Remaining TLAS work goes on the stack first.
+template <bool ALPHA, bool COUNT>
+RT_D void trav_enter_instance(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
     const int bit = rt_bfind(t.tgroup.y);
     t.tgroup.y &= ~(1u << bit);
-    if (t.blas_sp < 0) {
-        // TLAS leaf: enter the instance's BLAS.  Remaining TLAS work goes on the stack first.
-        const uint32_t inst = rt_ld(S.tlas_prims + t.tgroup.x + bit);
-        if (t.tgroup.y) stack[t.sp++] = t.tgroup;
-        if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
-        const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
-        const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
-        if (COUNT) c4[2]++;
-        const f3 od = xform_dir_exact(r0, r1, r2, t.dw);
-        trav_set_level_ray(t, xform_point_exact(r0, r1, r2, t.ow), od);
-        t.sh = shear_init(od);
-        t.cur_inst = inst; t.cur_geo = rt_float_as_uint(meta.y);
-        t.cur_alpha = ALPHA && !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
-        // node / primitive indices inside a BLAS are local to it: rebase the array pointers
-        t.nodes = S.blas_nodes + (size_t)rt_float_as_uint(meta.x) * RT_NODE_F4;
-        t.tris = S.tris + (size_t)rt_float_as_uint(meta.w) * RT_TRI_F4;
-        t.blas_sp = t.sp;
-        // the root is entered through a virtual parent whose only inner child is node 0
-        // (child_bit = 31, imask byte = 0 -> relative index 0)
-        t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u);
-        return false;
-    }
-    const float4* tp = t.tris + (size_t)(t.tgroup.x + bit) * RT_TRI_F4;
+    const uint32_t inst = rt_ld(S.tlas_prims + t.tgroup.x + bit);
+    if (t.tgroup.y) stack[t.sp++] = t.tgroup;
+    if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
+    const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
+    const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
+    if (COUNT) c4[2]++;
+    const f3 od = xform_dir_exact(r0, r1, r2, t.dw);
+    trav_set_level_ray(t, xform_point_exact(r0, r1, r2, t.ow), od);
+    t.sh = shear_init(od);
+    t.cur_inst = inst; t.cur_geo = rt_float_as_uint(meta.y);
+    t.cur_alpha = ALPHA && !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
+    // node / primitive indices inside a BLAS are local to it: rebase the array pointers
+    t.nodes = S.blas_nodes + (size_t)rt_float_as_uint(meta.x) * RT_NODE_F4;
+    t.tri_off = rt_float_as_uint(meta.w);
+    t.blas_sp = t.sp;
+    // the root is entered through a virtual parent whose only inner child is node 0
+    // (child_bit = 31, imask byte = 0 -> relative index 0)
+    t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u);
+}
+
+// closest-hit acceptance of a geometric candidate of the current instance: lexicographic (t, instance, primitive)
+RT_D bool trav_candidate_wins(const Trav& t, float tt, uint32_t prim) {
+    if (!t.found) return true;
+    if (tt > t.hit.t) return false;
+    if (tt == t.hit.t && !(t.cur_inst < t.hit.inst || (t.cur_inst == t.hit.inst && prim < t.hit.prim))) return false;
+    return true;
+}
+RT_D void trav_commit(Trav& t, float tt, float bu, float bv, uint32_t prim) {
+    t.hit.t = tt; t.hit.u = bu; t.hit.v = bv; t.hit.inst = t.cur_inst; t.hit.prim = prim; t.found = true;
+}
+
+template <int MODE, bool ALPHA, bool COUNT>
+RT_D bool trav_prim_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
+    if (t.blas_sp < 0) { trav_enter_instance<ALPHA, COUNT>(t, S, stack, c4); return false; }
+    const int bit = rt_bfind(t.tgroup.y);
+    t.tgroup.y &= ~(1u << bit);
+    const float4* tp = S.tris + (size_t)(t.tri_off + t.tgroup.x + bit) * RT_TRI_F4;
     const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
     if (COUNT) c4[1]++;
     float tt, bu, bv;
     if (!tri_test(t.sh, t.o, xyz(a), xyz(b), xyz(c), t.tmin, t.tmax, tt, bu, bv)) return false;
     const uint32_t prim = rt_float_as_uint(a.w);
-    if (t.found) {
-        if (tt > t.hit.t) return false;
-        if (tt == t.hit.t && !(t.cur_inst < t.hit.inst || (t.cur_inst == t.hit.inst && prim < t.hit.prim))) return false;
-    }
+    if (!trav_candidate_wins(t, tt, prim)) return false;
     if (ALPHA && t.cur_alpha) {
         if (COUNT) c4[3]++;
         if (anyhit_ignore(S, t.cur_inst, prim, t.cur_geo, bu, bv, t.rng)) return false;
     }
-    t.hit.t = tt; t.hit.u = bu; t.hit.v = bv; t.hit.inst = t.cur_inst; t.hit.prim = prim; t.found = true;
+    trav_commit(t, tt, bu, bv, prim);
     return MODE == RT_MODE_ANY;
 }
 
