@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-RT_LIB = Path(__file__).resolve().parent / "csrc" / "_build" / "librt_b200.so"
+RT_LIB = Path(os.environ.get("RT_B200_LIB") or (Path(__file__).resolve().parent / "csrc" / "_build" / "librt_b200.so"))
 HOST_LIB = ROOT / "host" / "_build" / "libgltf_host.so"
 
 c_f = C.c_float

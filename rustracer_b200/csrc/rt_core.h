@@ -533,7 +533,7 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
         for (uint32_t v = 0; v < d->geometries[g].v_len && !gr.skinned; ++v) if (d->vertices[d->prim_infos[g].v_offset + v].skin_index >= 0) gr.skinned = true;
         node_off += gr.n_tris ? gr.n_tris : 1; tri_off += gr.n_tris; if (gr.n_tris > max_tris) max_tris = gr.n_tris;
     }
-    if (node_off > 0xFFFFFFF0ull || tri_off > 0xFFFFFFF0ull) return bail("rt_scene_create: scene too large for 32-bit BVH indices");
+    if (node_off > 0xFFFFFFF0ull || tri_off >= (1ull << 27)) return bail("rt_scene_create: more than 2^27 unique triangles (instancing does not count) are not supported");
     s->total_nodes = node_off; s->total_tris = tri_off;
     const uint32_t ninst = d->n_instances;
     e = 0;

@@ -192,54 +192,53 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 //  * per-lane dynamic fetch (Aila & Laine 2009; Ylitie et al. 2017): every lane owns a resumable traversal state;
 //    finished lanes store their result and, once enough of the warp is idle, pull new rays from the queue with one
 //    warp-aggregated atomic.
-//  * warp-cooperative triangle tests: a lane that reaches leaves does not test its triangles itself (leaf sizes vary
-//    from 1 to 24 triangles, which left ~3 of 32 lanes busy in the first version of this kernel, profiles/r01).  It
-//    parks them; when the warp has collected enough parked triangles, they are dealt out one (ray, triangle) pair per
-//    lane through shared memory, tested by all lanes at once, and the per-ray winner (min t, then min primitive id)
-//    is resolved with shared-memory atomics and handed back to the owning lane.
+//  * every iteration each lane that holds a ray visits exactly one BVH8 node (popping / leaving a BLAS first if it
+//    has to), so the 8-box test runs with most of the warp active.
+//  * deferred, warp-cooperative triangle tests: leaf sizes vary from 1 to 24 triangles, which left ~3 of 32 lanes
+//    busy when each lane tested its own leaves (profiles/r01).  Instead a lane appends (owner lane, triangle) items
+//    to a per-warp queue in shared memory and keeps traversing with its (conservatively stale) hit distance; whenever
+//    32 items are queued the warp tests them one per lane against the owners' rays (kept in shared memory) and
+//    resolves each owner's winner (min t, then min primitive id) with shared-memory atomics.  A lane drains its
+//    outstanding items before it leaves a BLAS or retires its ray.
 // MODE selects closest-hit (extend) or any-hit (shadow) semantics.
+#ifndef RT_REFILL_BELOW
 #define RT_REFILL_BELOW 22     // refill when fewer than this many lanes still hold a ray
-#define RT_COOP_THRESHOLD 24   // run a cooperative round once this many triangles are parked in the warp
+#endif
 #define RT_WARPS_PER_BLOCK (RT_EXTEND_THREADS / 32)
+#define RT_TQ_CAP 1024u        // per-warp triangle queue capacity (>= 31 + 32 * 24)
+#define RT_TQ_TRI_BITS 27      // item = owner lane << 27 | absolute triangle index
 
 struct CoopShared {            // one per warp; SoA over the 32 owner lanes
     float ox[32], oy[32], oz[32], Sx[32], Sy[32], Sz[32], tmin[32], tmax[32], cur_t[32], u[32], v[32];
-    uint32_t kxyz[32], tri_base[32], tmask[32], off[32], best_t[32], best_prim[32];
+    uint32_t kxyz[32], best_t[32], best_prim[32], done[32];
     uint32_t inst[32], geo[32], alpha[32], rng[4][32];
+    uint32_t items[RT_TQ_CAP];
 };
 
-template <int MODE, bool ALPHA, bool COUNT>
-RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, bool pending, bool& active, uint32_t lane, unsigned long long* c4) {
-    const uint32_t k = pending ? (uint32_t)__popc(tv.tgroup.y) : 0u;
-    uint32_t incl = k;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += n; }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    const uint32_t off = incl - k;
-    sh.off[lane] = off;
-    if (k) {
-        sh.ox[lane] = tv.o.x; sh.oy[lane] = tv.o.y; sh.oz[lane] = tv.o.z;
-        sh.Sx[lane] = tv.sh.Sx; sh.Sy[lane] = tv.sh.Sy; sh.Sz[lane] = tv.sh.Sz;
-        sh.tmin[lane] = tv.tmin; sh.tmax[lane] = tv.tmax; sh.cur_t[lane] = tv.found ? tv.hit.t : tv.tmax;
-        sh.kxyz[lane] = (uint32_t)tv.sh.kx | ((uint32_t)tv.sh.ky << 2) | ((uint32_t)tv.sh.kz << 4);
-        sh.tri_base[lane] = tv.tri_off + tv.tgroup.x; sh.tmask[lane] = tv.tgroup.y;
-        sh.best_t[lane] = 0xFFFFFFFFu; sh.best_prim[lane] = 0xFFFFFFFFu;
-        if (ALPHA) {
-            sh.inst[lane] = tv.cur_inst; sh.geo[lane] = tv.cur_geo; sh.alpha[lane] = tv.cur_alpha ? 1u : 0u;
-            sh.rng[0][lane] = tv.rng.x; sh.rng[1][lane] = tv.rng.y; sh.rng[2][lane] = tv.rng.z; sh.rng[3][lane] = tv.rng.w;
-        }
+template <bool ALPHA>
+RT_D void coop_publish_ray(const Trav& tv, CoopShared& sh, uint32_t lane) {
+    sh.ox[lane] = tv.o.x; sh.oy[lane] = tv.o.y; sh.oz[lane] = tv.o.z;
+    sh.Sx[lane] = tv.sh.Sx; sh.Sy[lane] = tv.sh.Sy; sh.Sz[lane] = tv.sh.Sz;
+    sh.tmin[lane] = tv.tmin; sh.tmax[lane] = tv.tmax; sh.cur_t[lane] = tv.found ? tv.hit.t : tv.tmax;
+    sh.kxyz[lane] = (uint32_t)tv.sh.kx | ((uint32_t)tv.sh.ky << 2) | ((uint32_t)tv.sh.kz << 4);
+    if (ALPHA) {
+        sh.inst[lane] = tv.cur_inst; sh.geo[lane] = tv.cur_geo; sh.alpha[lane] = tv.cur_alpha ? 1u : 0u;
+        sh.rng[0][lane] = tv.rng.x; sh.rng[1][lane] = tv.rng.y; sh.rng[2][lane] = tv.rng.z; sh.rng[3][lane] = tv.rng.w;
     }
+}
+
+// Tests up to 32 queued (owner, triangle) items, one per lane.  Returns through `outstanding` / tv the owner-side
+// bookkeeping.  `usable`: this lane's ray is still live (results of a retired any-hit ray are discarded).
+template <int MODE, bool ALPHA, bool COUNT>
+RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, uint32_t n, uint32_t lane, uint32_t& outstanding, bool usable, bool& terminated,
+                     unsigned long long* c4) {
+    sh.best_t[lane] = 0xFFFFFFFFu; sh.best_prim[lane] = 0xFFFFFFFFu; sh.done[lane] = 0u;
     __syncwarp();
-    // one (ray, triangle) pair per lane: item j = lane of the first min(total, 32) parked triangles
     bool hit = false; float tt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t prim = 0, owner = 0, key = 0;
-    if (lane < total) {
-        uint32_t lo = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) if (sh.off[lo + step] <= lane) lo += step;   // last lane whose offset <= j
-        owner = lo;
-        const uint32_t n = lane - sh.off[owner];
-        const int bit = (int)__fns(sh.tmask[owner], 0u, (int)n + 1);
-        const float4* tp = S.tris + (size_t)(sh.tri_base[owner] + (uint32_t)bit) * RT_TRI_F4;
+    if (lane < n) {
+        const uint32_t item = sh.items[(head + lane) & (RT_TQ_CAP - 1u)];
+        owner = item >> RT_TQ_TRI_BITS;
+        const float4* tp = S.tris + (size_t)(item & ((1u << RT_TQ_TRI_BITS) - 1u)) * RT_TRI_F4;
         const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
         if (COUNT) c4[1]++;
         RayShear rs; const uint32_t kk = sh.kxyz[owner];
@@ -254,22 +253,22 @@ RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, bool pending, bo
             if (anyhit_ignore(S, sh.inst[owner], prim, sh.geo[owner], bu, bv, rng)) hit = false;
         }
         if (hit) { key = float_to_ordered(tt); atomicMin(&sh.best_t[owner], key); }
+        atomicAdd(&sh.done[owner], 1u);
     }
     __syncwarp();
     if (hit && key == sh.best_t[owner]) atomicMin(&sh.best_prim[owner], prim);
     __syncwarp();
     if (hit && key == sh.best_t[owner] && prim == sh.best_prim[owner]) { sh.u[owner] = bu; sh.v[owner] = bv; }
     __syncwarp();
-    if (k) {
-        // retire the triangles that were dealt out this round (the lowest `done` set bits of the mask)
-        const uint32_t done = off >= 32u ? 0u : (k < 32u - off ? k : 32u - off);
-        if (done == k) tv.tgroup.y = 0u;
-        else for (uint32_t i = 0; i < done; ++i) tv.tgroup.y &= tv.tgroup.y - 1u;
-        if (sh.best_t[lane] != 0xFFFFFFFFu) {
+    const uint32_t d = sh.done[lane];
+    if (d) {
+        outstanding -= d;
+        if (usable && sh.best_t[lane] != 0xFFFFFFFFu) {
             const float ct = ordered_to_float(sh.best_t[lane]); const uint32_t cp = sh.best_prim[lane];
             if (trav_candidate_wins(tv, ct, cp)) {
                 trav_commit(tv, ct, sh.u[lane], sh.v[lane], cp);
-                if (MODE == RT_MODE_ANY) active = false;   // caller stores the result
+                sh.cur_t[lane] = ct;
+                if (MODE == RT_MODE_ANY) terminated = true;
             }
         }
     }
@@ -285,48 +284,94 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
     uint2 stack[RT_STACK_SIZE];
     unsigned long long c4[4] = {0, 0, 0, 0};
     Trav tv;
-    tv.tgroup = make_uint2(0u, 0u);
+    tv.tgroup = make_uint2(0u, 0u); tv.ngroup = make_uint2(0u, 0u); tv.sp = 0; tv.blas_sp = -1; tv.found = false;
     bool active = false, exhausted = false;
-    uint32_t idx = 0;
+    uint32_t idx = 0, outstanding = 0;          // outstanding: this lane's items still in the queue
+    uint32_t q_head = 0, q_count = 0;           // warp-uniform queue cursor
     for (;;) {
         if (!exhausted) {
-            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active);
+            const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && outstanding == 0u);
             if (need) {
                 const int leader = __ffs((int)need) - 1;
                 uint32_t base = 0;
                 if ((int)lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(need));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (!active) {
+                if (!active && outstanding == 0u) {
                     idx = base + (uint32_t)__popc(need & lt_mask);
                     if (idx < count) { load_ray(idx, tv); active = true; }
                 }
                 if (base + (uint32_t)__popc(need) >= count) exhausted = true;
             }
         }
-        uint32_t am = __ballot_sync(0xFFFFFFFFu, active);
-        if (!am) break;
+        if (!__ballot_sync(0xFFFFFFFFu, active || outstanding != 0u)) break;
+        uint32_t holding;
         do {
-            bool pending = false;
+            bool want_flush = false; uint32_t leaf_mask = 0u, leaf_base = 0u;
             if (active) {
-                if (tv.tgroup.y != 0u) {
-                    if (tv.blas_sp < 0) trav_enter_instance<ALPHA, COUNT>(tv, S, stack, c4);
-                    else pending = true;                       // parked triangles wait for a cooperative round
-                } else if (trav_node_step<COUNT>(tv, S, stack, c4)) {
-                    trav_finish(tv); store_hit(idx, tv); active = false;
+                // acquire the next node group: leave the BLAS / pop until ngroup holds an inner child or instances are parked
+                while (tv.ngroup.y <= 0x00FFFFFFu && tv.tgroup.y == 0u) {
+                    if (tv.blas_sp >= 0 && tv.sp == tv.blas_sp) {
+                        if (outstanding) { want_flush = true; break; }     // queued triangles refer to the object-space ray
+                        tv.blas_sp = -1; tv.nodes = S.tlas_nodes;
+                        trav_set_level_ray(tv, tv.ow, tv.dw);
+                    }
+                    if (tv.sp == 0) {
+                        if (outstanding) { want_flush = true; break; }
+                        trav_finish(tv); store_hit(idx, tv); active = false; break;
+                    }
+                    const uint2 e = stack[--tv.sp];
+                    if (e.y > 0x00FFFFFFu) tv.ngroup = e; else { tv.tgroup = e; tv.ngroup = make_uint2(0u, 0u); }
+                }
+                if (active && !want_flush) {
+                    if (tv.tgroup.y != 0u) {
+                        // TLAS level: parked instances.  (Triangles are never parked in tgroup: they go to the queue.)
+                        trav_enter_instance<ALPHA, COUNT>(tv, S, stack, c4);
+                        coop_publish_ray<ALPHA>(tv, sh, lane);
+                    } else {
+                        const bool in_blas = tv.blas_sp >= 0;
+                        trav_node_step<COUNT>(tv, S, stack, c4);          // ngroup has an inner child: visits it
+                        if (in_blas) { leaf_mask = tv.tgroup.y; leaf_base = tv.tri_off + tv.tgroup.x; tv.tgroup.y = 0u; }
+                    }
                 }
             }
-            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, pending);
-            if (pm) {
-                const uint32_t parked = __reduce_add_sync(0xFFFFFFFFu, pending ? (uint32_t)__popc(tv.tgroup.y) : 0u);
-                const uint32_t stepping = __ballot_sync(0xFFFFFFFFu, active && !pending);
-                if (parked >= RT_COOP_THRESHOLD || !stepping) {
-                    const bool was_active = active;
-                    coop_round<MODE, ALPHA, COUNT>(tv, S, sh, pending, active, lane, c4);
-                    if (MODE == RT_MODE_ANY && was_active && !active) { trav_finish(tv); store_hit(idx, tv); }
+            // append this iteration's leaf triangles to the warp queue
+            const uint32_t k = (uint32_t)__popc(leaf_mask);
+            uint32_t incl = k;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if ((int)lane >= dd) incl += nn; }
+            const uint32_t pushed = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (k) {
+                uint32_t pos = q_head + q_count + (incl - k);
+                outstanding += k;
+                while (leaf_mask) {
+                    const int bit = 31 - __clz((int)leaf_mask);
+                    leaf_mask &= ~(1u << bit);
+                    sh.items[pos & (RT_TQ_CAP - 1u)] = (lane << RT_TQ_TRI_BITS) | (leaf_base + (uint32_t)bit);
+                    ++pos;
                 }
             }
-            am = __ballot_sync(0xFFFFFFFFu, active);
-        } while (am && (exhausted || __popc(am) >= RT_REFILL_BELOW));
+            q_count += pushed;
+            const bool flush = __any_sync(0xFFFFFFFFu, want_flush);
+            __syncwarp();
+            while (q_count >= 32u || (flush && q_count)) {
+                const uint32_t n = q_count < 32u ? q_count : 32u;
+                bool terminated = false;
+                coop_round<MODE, ALPHA, COUNT>(tv, S, sh, q_head, n, lane, outstanding, active, terminated, c4);
+                if (MODE == RT_MODE_ANY && terminated && active) { trav_finish(tv); store_hit(idx, tv); active = false; }
+                q_head += n; q_count -= n;
+            }
+            holding = __ballot_sync(0xFFFFFFFFu, active);
+        } while (holding && (exhausted || __popc(holding) >= RT_REFILL_BELOW));
+        // lanes whose any-hit ray retired early may still own queued items: drain so they can be refilled
+        if (__any_sync(0xFFFFFFFFu, !active && outstanding != 0u)) {
+            while (q_count) {
+                const uint32_t n = q_count < 32u ? q_count : 32u;
+                bool terminated = false;
+                coop_round<MODE, ALPHA, COUNT>(tv, S, sh, q_head, n, lane, outstanding, active, terminated, c4);
+                if (MODE == RT_MODE_ANY && terminated && active) { trav_finish(tv); store_hit(idx, tv); active = false; }
+                q_head += n; q_count -= n;
+            }
+        }
     }
     if (COUNT && cnt) {
         atomicAdd(&cnt->nodes, c4[0]); atomicAdd(&cnt->tris, c4[1]); atomicAdd(&cnt->insts, c4[2]); atomicAdd(&cnt->anyhits, c4[3]);
