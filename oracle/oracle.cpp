@@ -195,6 +195,12 @@ struct Instance {
     float o2w[12];   // row-major 3x4
     float w2o[12];
     uint32_t geo_id;
+    // Baked instance (rule shared with the CUDA core, rt_core.h classify_instances): when the geometry is referenced
+    // by exactly one instance or has at most 256 triangles, the triangles are transformed to world space once
+    // (fp32, fixed operation order) and the world ray is intersected directly — no per-ray transform.
+    bool baked = false;
+    std::vector<vec3> wpos;   // 3 world-space vertices per triangle
+    Bvh wbvh;
 };
 
 }  // namespace
@@ -658,22 +664,27 @@ struct TraceCtx { bool ray_opaque; bool terminate_first; uvec4 rng; };
 void trace_blas(const orc_scene& s, uint32_t inst_id, vec3 o, vec3 d, float tmin, float tmax, const TraceCtx& c, Hit& best, bool& done) {
     const Instance& in = s.instances[inst_id];
     const Geometry& g = s.geos[in.geo_id];
-    if (g.bvh.nodes.empty()) return;
-    vec3 oo = xform_point(in.w2o, o), od = xform_dir(in.w2o, d);
+    const Bvh& bvh = in.baked ? in.wbvh : g.bvh;
+    if (bvh.nodes.empty()) return;
+    vec3 oo = in.baked ? o : xform_point(in.w2o, o), od = in.baked ? d : xform_dir(in.w2o, d);
     RayShear rs; rs.init(oo, od);
     uint32_t stack[128]; int sp = 0; stack[sp++] = 0;
     const bool need_alpha = !g.opaque && !c.ray_opaque;
     while (sp) {
-        const BNode& n = g.bvh.nodes[stack[--sp]];
+        const BNode& n = bvh.nodes[stack[--sp]];
         float tn;
         if (!box_test(n.box, oo, od, tmin, best.valid ? best.t : tmax, tn)) continue;
         if (n.count) {
             for (uint32_t i = 0; i < n.count; ++i) {
-                uint32_t prim = g.bvh.prim[n.left + i];
+                uint32_t prim = bvh.prim[n.left + i];
                 const uint32_t io = g.i_offset + 3 * prim;
-                vec3 p0 = ld3(s.vertices[g.v_offset + s.indices[io]].position);
-                vec3 p1 = ld3(s.vertices[g.v_offset + s.indices[io + 1]].position);
-                vec3 p2 = ld3(s.vertices[g.v_offset + s.indices[io + 2]].position);
+                vec3 p0, p1, p2;
+                if (in.baked) { p0 = in.wpos[3 * prim]; p1 = in.wpos[3 * prim + 1]; p2 = in.wpos[3 * prim + 2]; }
+                else {
+                    p0 = ld3(s.vertices[g.v_offset + s.indices[io]].position);
+                    p1 = ld3(s.vertices[g.v_offset + s.indices[io + 1]].position);
+                    p2 = ld3(s.vertices[g.v_offset + s.indices[io + 2]].position);
+                }
                 float t, u, v;
                 if (!tri_test(rs, p0, p1, p2, tmin, tmax, t, u, v)) continue;
                 if (best.valid) {
@@ -717,14 +728,18 @@ Hit trace_brute(const orc_scene& s, vec3 o, vec3 d, float tmin, float tmax, cons
     for (uint32_t ii = 0; ii < s.instances.size(); ++ii) {
         const Instance& in = s.instances[ii];
         const Geometry& g = s.geos[in.geo_id];
-        vec3 oo = xform_point(in.w2o, o), od = xform_dir(in.w2o, d);
+        vec3 oo = in.baked ? o : xform_point(in.w2o, o), od = in.baked ? d : xform_dir(in.w2o, d);
         RayShear rs; rs.init(oo, od);
         const bool need_alpha = !g.opaque && !c.ray_opaque;
         for (uint32_t prim = 0; prim < g.i_len / 3; ++prim) {
             const uint32_t io = g.i_offset + 3 * prim;
-            vec3 p0 = ld3(s.vertices[g.v_offset + s.indices[io]].position);
-            vec3 p1 = ld3(s.vertices[g.v_offset + s.indices[io + 1]].position);
-            vec3 p2 = ld3(s.vertices[g.v_offset + s.indices[io + 2]].position);
+            vec3 p0, p1, p2;
+            if (in.baked) { p0 = in.wpos[3 * prim]; p1 = in.wpos[3 * prim + 1]; p2 = in.wpos[3 * prim + 2]; }
+            else {
+                p0 = ld3(s.vertices[g.v_offset + s.indices[io]].position);
+                p1 = ld3(s.vertices[g.v_offset + s.indices[io + 1]].position);
+                p2 = ld3(s.vertices[g.v_offset + s.indices[io + 2]].position);
+            }
             float t, u, v;
             if (!tri_test(rs, p0, p1, p2, tmin, tmax, t, u, v)) continue;
             if (best.valid && (t > best.t || (t == best.t && !(ii < best.inst || (ii == best.inst && prim < best.prim))))) continue;
@@ -1176,10 +1191,27 @@ void build_blas(orc_scene& s, uint32_t g) {
 
 void build_tlas(orc_scene& s) {
     std::vector<Aabb> boxes(s.instances.size());
+    std::vector<uint32_t> refs(s.geos.size(), 0);
+    for (auto& in : s.instances) refs[in.geo_id]++;
     for (size_t i = 0; i < s.instances.size(); ++i) {
         Instance& in = s.instances[i];
         invert_3x4(in.o2w, in.w2o);
         const Geometry& g = s.geos[in.geo_id];
+        in.baked = refs[in.geo_id] == 1 || g.i_len / 3 <= 256;
+        if (in.baked) {
+            const uint32_t ntri = g.i_len / 3;
+            in.wpos.resize((size_t)ntri * 3);
+            std::vector<Aabb> tb(ntri);
+            for (uint32_t t = 0; t < ntri; ++t)
+                for (int k = 0; k < 3; ++k) {
+                    in.wpos[3 * t + k] = xform_point(in.o2w, ld3(s.vertices[g.v_offset + s.indices[g.i_offset + 3 * t + k]].position));
+                    tb[t].grow(in.wpos[3 * t + k]);
+                }
+            in.wbvh.build(tb);
+            if (in.wbvh.nodes.empty()) { boxes[i].lo = V3(0.0f); boxes[i].hi = V3(0.0f); }
+            else { boxes[i] = in.wbvh.nodes[0].box; vec3 e = (boxes[i].hi - boxes[i].lo) * 1e-5f + V3(1e-6f); boxes[i].lo = boxes[i].lo - e; boxes[i].hi = boxes[i].hi + e; }
+            continue;
+        }
         if (g.bvh.nodes.empty()) { boxes[i].lo = V3(0.0f); boxes[i].hi = V3(0.0f); continue; }
         const Aabb& b = g.bvh.nodes[0].box;
         for (int c = 0; c < 8; ++c) {

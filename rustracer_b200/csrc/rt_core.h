@@ -79,13 +79,19 @@ struct rt_context {
     std::vector<void*> ipc_opened;
 };
 
-struct GeoRecord { uint32_t node_off, tri_off, n_tris, n_nodes, depth; bool skinned; };
+// One BLAS: either a geometry's own object-space BLAS (needed only when a non-baked instance references it) or the
+// merged world-space BLAS of all baked instances.
+struct GeoRecord { uint32_t node_off, tri_off, n_tris, n_nodes, depth; bool skinned, needed; };
 
 struct rt_scene {
     rt_context* ctx = nullptr;
     // host mirrors needed for rebuilds
     std::vector<rt_geometry> geometries; std::vector<rt_prim_info> prim_infos; std::vector<rt_instance> instances;
     std::vector<GeoRecord> geo;
+    GeoRecord merged{};                      // world-space BLAS over the baked instances' triangles
+    std::vector<uint8_t> baked;              // per instance
+    uint2* d_bake_src = nullptr;             // per merged primitive: (instance, primitive)
+    bool merged_skinned = false;
     uint32_t n_vertices = 0, n_indices = 0, n_materials = 0, n_skins = 0;
     // device arrays
     rt_vertex *d_vin = nullptr, *d_vout = nullptr; uint32_t* d_indices = nullptr; rt_prim_info* d_prim = nullptr;
@@ -97,7 +103,7 @@ struct rt_scene {
     uint32_t* d_prim_order = nullptr; DAabb* d_leaf_boxes = nullptr; DAabb* d_prim_boxes = nullptr; uint32_t* d_pending = nullptr;
     uint64_t total_nodes = 0, total_tris = 0;
     float4 *d_tlas_nodes = nullptr; uint32_t* d_tlas_prims = nullptr; DAabb* d_tlas_box = nullptr; uint32_t* d_tlas_parent = nullptr;
-    DAabb* d_inst_boxes = nullptr; float4 *d_inst_w2o = nullptr, *d_inst_o2w = nullptr; uint32_t* d_inst_root = nullptr;
+    DAabb* d_inst_boxes = nullptr; float4 *d_inst_w2o = nullptr, *d_inst_o2w = nullptr; uint32_t* d_inst_root = nullptr; uint32_t* d_entry_rec = nullptr;
     uint32_t tlas_nodes = 0, tlas_depth = 0, blas_depth = 0;
     BuildScratch scratch;
     DScene ds{};
@@ -145,7 +151,19 @@ static int run_skinning(rt_scene* s) {
     return 0;
 }
 
-// (re)packs the triangles of geometry g in leaf order and refreshes the per-leaf boxes
+// Baking rule (must match oracle/oracle.cpp): an instance is intersected in world space through the merged BLAS when
+// its geometry is referenced by exactly one instance or has at most RT_BAKE_MAX_TRIS triangles.
+static void classify_instances(rt_scene* s) {
+    std::vector<uint32_t> refs(s->geometries.size(), 0);
+    for (auto& in : s->instances) refs[in.geo_id]++;
+    s->baked.assign(s->instances.size(), 0);
+    for (size_t i = 0; i < s->instances.size(); ++i) {
+        const uint32_t g = s->instances[i].geo_id;
+        s->baked[i] = (refs[g] == 1 || s->geometries[g].i_len / 3 <= RT_BAKE_MAX_TRIS) ? 1 : 0;
+    }
+}
+
+// (re)packs the triangles of geometry g in leaf order (object space) and refreshes the per-leaf boxes
 static void pack_tris(rt_scene* s, uint32_t g) {
     const GeoRecord& gr = s->geo[g]; const rt_prim_info pi = s->prim_infos[g];
     const rt_vertex* verts = s->d_vout; const uint32_t* indices = s->d_indices;
@@ -163,26 +181,76 @@ static void pack_tris(rt_scene* s, uint32_t g) {
     });
 }
 
-static int build_blas(rt_scene* s, uint32_t g) {
-    GeoRecord& gr = s->geo[g]; const rt_prim_info pi = s->prim_infos[g];
-    rt_stream_t st = s->ctx->stream;
-    const rt_vertex* verts = s->d_vout; const uint32_t* indices = s->d_indices; DAabb* pb = s->d_prim_boxes;
-    rt_launch(gr.n_tris, st, RT_LAMBDA(size_t k) { pb[k] = tri_box_of(verts, indices, pi.v_offset, pi.i_offset, (uint32_t)k); });
+// world-space vertices of merged primitive `src` = (instance, primitive): object->world with the oracle's operation order
+RT_D void baked_triangle(const rt_vertex* verts, const uint32_t* indices, const rt_prim_info* prims, const float4* inst_w2o, const float4* inst_o2w,
+                         uint2 src, f3& w0, f3& w1, f3& w2) {
+    const uint32_t geo = rt_float_as_uint(inst_w2o[(size_t)src.x * RT_INST_F4 + 3].y);
+    const rt_prim_info pi = prims[geo];
+    const float4 m0 = inst_o2w[(size_t)src.x * 3], m1 = inst_o2w[(size_t)src.x * 3 + 1], m2 = inst_o2w[(size_t)src.x * 3 + 2];
+    const uint32_t io = pi.i_offset + 3 * src.y;
+    const float* p0 = verts[pi.v_offset + indices[io]].position; const float* p1 = verts[pi.v_offset + indices[io + 1]].position; const float* p2 = verts[pi.v_offset + indices[io + 2]].position;
+    w0 = xform_point_exact(m0, m1, m2, mk3(p0[0], p0[1], p0[2]));
+    w1 = xform_point_exact(m0, m1, m2, mk3(p1[0], p1[1], p1[2]));
+    w2 = xform_point_exact(m0, m1, m2, mk3(p2[0], p2[1], p2[2]));
+}
+
+static void pack_merged(rt_scene* s) {
+    const GeoRecord& gr = s->merged;
+    const rt_vertex* verts = s->d_vout; const uint32_t* indices = s->d_indices; const rt_prim_info* prims = s->d_prim;
+    const float4* w2o = s->d_inst_w2o; const float4* o2w = s->d_inst_o2w; const uint2* src = s->d_bake_src;
+    const uint32_t* order = s->d_prim_order + gr.tri_off; float4* tris = s->d_tris + (size_t)gr.tri_off * RT_TRI_F4; DAabb* lb = s->d_leaf_boxes + gr.tri_off;
+    rt_launch(gr.n_tris, s->ctx->stream, RT_LAMBDA(size_t k) {
+        const uint2 sp = src[order[k]];
+        f3 a, b, c; baked_triangle(verts, indices, prims, w2o, o2w, sp, a, b, c);
+        tris[k * RT_TRI_F4 + 0] = make_float4(a.x, a.y, a.z, rt_uint_as_float(sp.y));
+        tris[k * RT_TRI_F4 + 1] = make_float4(b.x, b.y, b.z, rt_uint_as_float(sp.x));
+        tris[k * RT_TRI_F4 + 2] = make_float4(c.x, c.y, c.z, 0.0f);
+        DAabb bb;
+        bb.lo[0] = fminf(a.x, fminf(b.x, c.x)); bb.lo[1] = fminf(a.y, fminf(b.y, c.y)); bb.lo[2] = fminf(a.z, fminf(b.z, c.z));
+        bb.hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)); bb.hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)); bb.hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+        lb[k] = bb;
+    });
+}
+
+static int build_one(rt_scene* s, GeoRecord& gr, const char* what) {
     WideOut out;
     out.nodes = s->d_blas_nodes + (size_t)gr.node_off * RT_NODE_F4; out.prim_order = s->d_prim_order + gr.tri_off;
     out.node_box = s->d_node_box + gr.node_off; out.node_parent = s->d_node_parent + gr.node_off; out.max_nodes = gr.n_tris ? gr.n_tris : 1u;
     WideBvhInfo info;
-    const int e = build_wide_bvh(pb, gr.n_tris, s->scratch, out, st, &info);
-    if (e) return fail("BLAS build failed for geometry " + std::to_string(g) + " (code " + std::to_string(e) + ")");
+    const int e = build_wide_bvh(s->d_prim_boxes, gr.n_tris, s->scratch, out, s->ctx->stream, &info);
+    if (e) return fail(std::string(what) + " build failed (code " + std::to_string(e) + ")");
     gr.n_nodes = info.n_nodes; gr.depth = info.depth;
+    return 0;
+}
+
+static int build_blas(rt_scene* s, uint32_t g) {
+    GeoRecord& gr = s->geo[g]; const rt_prim_info pi = s->prim_infos[g];
+    const rt_vertex* verts = s->d_vout; const uint32_t* indices = s->d_indices; DAabb* pb = s->d_prim_boxes;
+    rt_launch(gr.n_tris, s->ctx->stream, RT_LAMBDA(size_t k) { pb[k] = tri_box_of(verts, indices, pi.v_offset, pi.i_offset, (uint32_t)k); });
+    if (build_one(s, gr, "BLAS")) return 1;
     pack_tris(s, g);
     return 0;
 }
 
-static void refit_blas(rt_scene* s, uint32_t g) {
-    const GeoRecord& gr = s->geo[g];
+static int build_merged(rt_scene* s) {
+    GeoRecord& gr = s->merged;
+    const rt_vertex* verts = s->d_vout; const uint32_t* indices = s->d_indices; const rt_prim_info* prims = s->d_prim;
+    const float4* w2o = s->d_inst_w2o; const float4* o2w = s->d_inst_o2w; const uint2* src = s->d_bake_src; DAabb* pb = s->d_prim_boxes;
+    rt_launch(gr.n_tris, s->ctx->stream, RT_LAMBDA(size_t k) {
+        f3 a, b, c; baked_triangle(verts, indices, prims, w2o, o2w, src[k], a, b, c);
+        DAabb bb;
+        bb.lo[0] = fminf(a.x, fminf(b.x, c.x)); bb.lo[1] = fminf(a.y, fminf(b.y, c.y)); bb.lo[2] = fminf(a.z, fminf(b.z, c.z));
+        bb.hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)); bb.hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)); bb.hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+        pb[k] = bb;
+    });
+    if (build_one(s, gr, "merged BLAS")) return 1;
+    pack_merged(s);
+    return 0;
+}
+
+// bottom-up refit of one BLAS whose triangles / leaf boxes were just re-packed
+static void refit_nodes(rt_scene* s, const GeoRecord& gr) {
     rt_stream_t st = s->ctx->stream;
-    pack_tris(s, g);
     float4* nodes = s->d_blas_nodes + (size_t)gr.node_off * RT_NODE_F4; DAabb* nb = s->d_node_box + gr.node_off;
     const uint32_t* parent = s->d_node_parent + gr.node_off; uint32_t* pending = s->d_pending + gr.node_off;
     const DAabb* lb = s->d_leaf_boxes + gr.tri_off;
@@ -202,11 +270,14 @@ static void refit_blas(rt_scene* s, uint32_t g) {
         }
     });
 }
+static void refit_blas(rt_scene* s, uint32_t g) { pack_tris(s, g); refit_nodes(s, s->geo[g]); }
+static void refit_merged(rt_scene* s) { pack_merged(s); refit_nodes(s, s->merged); }
 
-static int build_tlas(rt_scene* s) {
+// uploads the instance records (transform inverses, BLAS offsets, flags); record n_instances is the merged BLAS
+static int upload_instance_records(rt_scene* s) {
     rt_stream_t st = s->ctx->stream;
     const uint32_t n = (uint32_t)s->instances.size();
-    std::vector<float> w2o((size_t)n * 16), o2w((size_t)n * 12); std::vector<uint32_t> roots(n);
+    std::vector<float> w2o((size_t)(n + 1) * 16), o2w((size_t)(n ? n : 1) * 12);
     for (uint32_t i = 0; i < n; ++i) {
         const rt_instance& in = s->instances[i];
         float inv[12]; invert_3x4(in.transform, inv);
@@ -215,33 +286,59 @@ static int build_tlas(rt_scene* s) {
         uint32_t meta[4] = {gr.node_off, in.geo_id, s->geometries[in.geo_id].opaque ? RT_INST_OPAQUE : 0u, gr.tri_off};
         memcpy(&w2o[(size_t)i * 16 + 12], meta, 16);
         memcpy(&o2w[(size_t)i * 12], in.transform, 48);
-        roots[i] = gr.node_off;
     }
+    const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    memcpy(&w2o[(size_t)n * 16], ident, 48);
+    uint32_t meta[4] = {s->merged.node_off, 0u, RT_INST_IDENTITY | RT_INST_MERGED, s->merged.tri_off};
+    memcpy(&w2o[(size_t)n * 16 + 12], meta, 16);
     RT_CHECK(rt_h2d(s->d_inst_w2o, w2o.data(), w2o.size() * 4, st), "upload instances");
-    RT_CHECK(rt_h2d(s->d_inst_o2w, o2w.data(), o2w.size() * 4, st), "upload instances");
-    RT_CHECK(rt_h2d(s->d_inst_root, roots.data(), roots.size() * 4, st), "upload instances");
-    const float4* o2wd = s->d_inst_o2w; const uint32_t* rootd = s->d_inst_root; const DAabb* nb = s->d_node_box; DAabb* ib = s->d_inst_boxes;
-    rt_launch(n, st, RT_LAMBDA(size_t i) {
-        const float4 m0 = o2wd[i * 3], m1 = o2wd[i * 3 + 1], m2 = o2wd[i * 3 + 2];
-        const DAabb b = nb[rootd[i]];
+    if (n) RT_CHECK(rt_h2d(s->d_inst_o2w, o2w.data(), (size_t)n * 48, st), "upload instances");
+    return 0;
+}
+
+// TLAS over the non-baked instances plus (when it has triangles) the merged world-space BLAS
+static int build_tlas(rt_scene* s) {
+    rt_stream_t st = s->ctx->stream;
+    const uint32_t n = (uint32_t)s->instances.size();
+    std::vector<uint32_t> entry_rec, entry_root;
+    for (uint32_t i = 0; i < n; ++i) if (!s->baked[i]) { entry_rec.push_back(i); entry_root.push_back(s->geo[s->instances[i].geo_id].node_off); }
+    if (s->merged.n_tris) { entry_rec.push_back(n); entry_root.push_back(s->merged.node_off); }
+    const uint32_t ne = (uint32_t)entry_rec.size();
+    if (ne) {
+        RT_CHECK(rt_h2d(s->d_inst_root, entry_root.data(), (size_t)ne * 4, st), "upload TLAS entries");
+        RT_CHECK(rt_h2d(s->d_entry_rec, entry_rec.data(), (size_t)ne * 4, st), "upload TLAS entries");
+    }
+    const float4* o2wd = s->d_inst_o2w; const uint32_t* rootd = s->d_inst_root; const uint32_t* recd = s->d_entry_rec; const DAabb* nb = s->d_node_box; DAabb* ib = s->d_inst_boxes;
+    rt_launch(ne, st, RT_LAMBDA(size_t e) {
+        const DAabb b = nb[rootd[e]];
+        const uint32_t rec = recd[e];
         DAabb w;
-        for (int c = 0; c < 8; ++c) {
-            const float x = (c & 1) ? b.hi[0] : b.lo[0], y = (c & 2) ? b.hi[1] : b.lo[1], z = (c & 4) ? b.hi[2] : b.lo[2];
-            const float p[3] = {m0.x * x + m0.y * y + m0.z * z + m0.w, m1.x * x + m1.y * y + m1.z * z + m1.w, m2.x * x + m2.y * y + m2.z * z + m2.w};
-            for (int a = 0; a < 3; ++a) { if (c == 0) { w.lo[a] = p[a]; w.hi[a] = p[a]; } else { w.lo[a] = fminf(w.lo[a], p[a]); w.hi[a] = fmaxf(w.hi[a], p[a]); } }
+        if (rec == n) { w = b; }      // merged BLAS: already world space
+        else {
+            const float4 m0 = o2wd[(size_t)rec * 3], m1 = o2wd[(size_t)rec * 3 + 1], m2 = o2wd[(size_t)rec * 3 + 2];
+            for (int c = 0; c < 8; ++c) {
+                const float x = (c & 1) ? b.hi[0] : b.lo[0], y = (c & 2) ? b.hi[1] : b.lo[1], z = (c & 4) ? b.hi[2] : b.lo[2];
+                const float p[3] = {m0.x * x + m0.y * y + m0.z * z + m0.w, m1.x * x + m1.y * y + m1.z * z + m1.w, m2.x * x + m2.y * y + m2.z * z + m2.w};
+                for (int a = 0; a < 3; ++a) { if (c == 0) { w.lo[a] = p[a]; w.hi[a] = p[a]; } else { w.lo[a] = fminf(w.lo[a], p[a]); w.hi[a] = fmaxf(w.hi[a], p[a]); } }
+            }
         }
         // the corners were rounded and the object-space ray is rounded too: keep the world box conservative
         for (int a = 0; a < 3; ++a) {
             const float pad = (w.hi[a] - w.lo[a]) * 1e-5f + 1e-6f * fmaxf(fabsf(w.lo[a]), fabsf(w.hi[a])) + 1e-7f;
             w.lo[a] -= pad; w.hi[a] += pad;
         }
-        ib[i] = w;
+        ib[e] = w;
     });
-    WideOut out; out.nodes = s->d_tlas_nodes; out.prim_order = s->d_tlas_prims; out.node_box = s->d_tlas_box; out.node_parent = s->d_tlas_parent; out.max_nodes = n ? n : 1u;
+    WideOut out; out.nodes = s->d_tlas_nodes; out.prim_order = s->d_tlas_prims; out.node_box = s->d_tlas_box; out.node_parent = s->d_tlas_parent; out.max_nodes = ne ? ne : 1u;
     WideBvhInfo info;
-    const int e = build_wide_bvh(ib, n, s->scratch, out, st, &info);
+    const int e = build_wide_bvh(ib, ne, s->scratch, out, st, &info);
     if (e) return fail("TLAS build failed (code " + std::to_string(e) + ")");
+    uint32_t* tp = s->d_tlas_prims;
+    rt_launch(ne, st, RT_LAMBDA(size_t k) { tp[k] = recd[tp[k]]; });   // TLAS leaf -> instance record index
     s->tlas_nodes = info.n_nodes; s->tlas_depth = info.depth;
+    uint32_t bd = s->merged.depth;
+    for (auto& g : s->geo) if (g.needed && g.depth > bd) bd = g.depth;
+    s->blas_depth = bd;
     if (s->tlas_depth + s->blas_depth + 6 > RT_STACK_SIZE)
         return fail("BVH too deep for the traversal stack: tlas " + std::to_string(s->tlas_depth) + " + blas " + std::to_string(s->blas_depth));
     return 0;
@@ -456,7 +553,7 @@ void RT_API(rt_scene_destroy)(rt_scene* s) {
     rt_stream_sync(s->ctx->stream);
     void* ptrs[] = {s->d_vin, s->d_vout, s->d_indices, s->d_prim, s->d_mat, s->d_skins, s->d_dl, s->d_pl, s->d_images, s->d_textures, s->d_lut,
                     s->d_blas_nodes, s->d_tris, s->d_node_box, s->d_node_parent, s->d_prim_order, s->d_leaf_boxes, s->d_prim_boxes, s->d_pending,
-                    s->d_tlas_nodes, s->d_tlas_prims, s->d_tlas_box, s->d_tlas_parent, s->d_inst_boxes, s->d_inst_w2o, s->d_inst_o2w, s->d_inst_root};
+                    s->d_tlas_nodes, s->d_tlas_prims, s->d_tlas_box, s->d_tlas_parent, s->d_inst_boxes, s->d_inst_w2o, s->d_inst_o2w, s->d_inst_root, s->d_entry_rec, s->d_bake_src};
     for (void* p : ptrs) if (p) rt_free(p);
     for (uint8_t* p : s->d_image_px) if (p) rt_free(p);
     for (int f = 0; f < 6; ++f) if (s->d_sky[f]) rt_free(s->d_sky[f]);
@@ -523,36 +620,56 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
     s->ds.n_textures = d->n_textures;
     if (d->skybox_faces[0] && d->skybox_width && upload_sky(s, d->skybox_faces, d->skybox_width, d->skybox_height, d->skybox_srgb)) return bail(g_err);
 
-    // ---- geometry records and BVH storage ----
+    // ---- geometry records, baking classification and BVH storage ----
+    classify_instances(s);
     uint64_t node_off = 0, tri_off = 0; uint32_t max_tris = 0;
     s->geo.resize(d->n_geometries);
-    std::vector<uint8_t> vskinned;
     for (uint32_t g = 0; g < d->n_geometries; ++g) {
         GeoRecord& gr = s->geo[g];
-        gr.n_tris = d->geometries[g].i_len / 3; gr.node_off = (uint32_t)node_off; gr.tri_off = (uint32_t)tri_off; gr.n_nodes = 0; gr.depth = 0; gr.skinned = false;
+        gr.n_tris = d->geometries[g].i_len / 3; gr.node_off = 0; gr.tri_off = 0; gr.n_nodes = 0; gr.depth = 0; gr.skinned = false; gr.needed = false;
         for (uint32_t v = 0; v < d->geometries[g].v_len && !gr.skinned; ++v) if (d->vertices[d->prim_infos[g].v_offset + v].skin_index >= 0) gr.skinned = true;
+    }
+    std::vector<uint2> bake_src;
+    s->merged_skinned = false;
+    for (uint32_t i = 0; i < d->n_instances; ++i) {
+        const uint32_t g = d->instances[i].geo_id;
+        if (!s->baked[i]) { s->geo[g].needed = true; continue; }
+        for (uint32_t p = 0; p < s->geo[g].n_tris; ++p) bake_src.push_back(make_uint2(i, p));
+        if (s->geo[g].skinned) s->merged_skinned = true;
+    }
+    for (uint32_t g = 0; g < d->n_geometries; ++g) {
+        GeoRecord& gr = s->geo[g];
+        if (!gr.needed) continue;
+        gr.node_off = (uint32_t)node_off; gr.tri_off = (uint32_t)tri_off;
         node_off += gr.n_tris ? gr.n_tris : 1; tri_off += gr.n_tris; if (gr.n_tris > max_tris) max_tris = gr.n_tris;
     }
-    if (node_off > 0xFFFFFFF0ull || tri_off >= (1ull << 27)) return bail("rt_scene_create: more than 2^27 unique triangles (instancing does not count) are not supported");
+    s->merged = GeoRecord{};
+    s->merged.n_tris = (uint32_t)bake_src.size(); s->merged.node_off = (uint32_t)node_off; s->merged.tri_off = (uint32_t)tri_off; s->merged.needed = true; s->merged.skinned = s->merged_skinned;
+    node_off += s->merged.n_tris ? s->merged.n_tris : 1; tri_off += s->merged.n_tris; if (s->merged.n_tris > max_tris) max_tris = s->merged.n_tris;
+    if (node_off > 0xFFFFFFF0ull || tri_off >= (1ull << 27) || bake_src.size() >= (1ull << 27))
+        return bail("rt_scene_create: more than 2^27 unique (baked + instanced) triangles are not supported");
     s->total_nodes = node_off; s->total_tris = tri_off;
     const uint32_t ninst = d->n_instances;
     e = 0;
     e |= dev_alloc(&s->d_blas_nodes, (size_t)(node_off ? node_off : 1) * RT_NODE_F4); e |= dev_alloc(&s->d_tris, (size_t)(tri_off ? tri_off : 1) * RT_TRI_F4);
     e |= dev_alloc(&s->d_node_box, node_off ? node_off : 1); e |= dev_alloc(&s->d_node_parent, node_off ? node_off : 1); e |= dev_alloc(&s->d_pending, node_off ? node_off : 1);
     e |= dev_alloc(&s->d_prim_order, tri_off ? tri_off : 1); e |= dev_alloc(&s->d_leaf_boxes, tri_off ? tri_off : 1); e |= dev_alloc(&s->d_prim_boxes, max_tris ? max_tris : 1);
-    e |= dev_alloc(&s->d_tlas_nodes, (size_t)(ninst ? ninst : 1) * RT_NODE_F4); e |= dev_alloc(&s->d_tlas_prims, ninst ? ninst : 1);
-    e |= dev_alloc(&s->d_tlas_box, ninst ? ninst : 1); e |= dev_alloc(&s->d_tlas_parent, ninst ? ninst : 1); e |= dev_alloc(&s->d_inst_boxes, ninst ? ninst : 1);
-    e |= dev_alloc(&s->d_inst_w2o, (size_t)(ninst ? ninst : 1) * RT_INST_F4); e |= dev_alloc(&s->d_inst_o2w, (size_t)(ninst ? ninst : 1) * 3); e |= dev_alloc(&s->d_inst_root, ninst ? ninst : 1);
+    e |= dev_upload(&s->d_bake_src, bake_src.data(), bake_src.size(), st);
+    e |= dev_alloc(&s->d_tlas_nodes, (size_t)(ninst + 1) * RT_NODE_F4); e |= dev_alloc(&s->d_tlas_prims, ninst + 1);
+    e |= dev_alloc(&s->d_tlas_box, ninst + 1); e |= dev_alloc(&s->d_tlas_parent, ninst + 1); e |= dev_alloc(&s->d_inst_boxes, ninst + 1);
+    e |= dev_alloc(&s->d_inst_w2o, (size_t)(ninst + 1) * RT_INST_F4); e |= dev_alloc(&s->d_inst_o2w, (size_t)(ninst ? ninst : 1) * 3);
+    e |= dev_alloc(&s->d_inst_root, ninst + 1); e |= dev_alloc(&s->d_entry_rec, ninst + 1);
     if (e) return bail(std::string("rt_scene_create: BVH allocation failed: ") + rt_platform_error());
 
     rt_timer t0, t1, t2; t0.create(); t1.create(); t2.create();
     t0.record(st);
     run_skinning(s);   // initial ComputeUnit::dispatch (main.rs:85-91); copy-through when nothing is skinned
-    s->blas_depth = 0;
+    if (upload_instance_records(s)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(g_err); }
     for (uint32_t g = 0; g < d->n_geometries; ++g) {
+        if (!s->geo[g].needed) continue;
         if (build_blas(s, g)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(g_err); }
-        if (s->geo[g].depth > s->blas_depth) s->blas_depth = s->geo[g].depth;
     }
+    if (build_merged(s)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(g_err); }
     t1.record(st);
     if (build_tlas(s)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(g_err); }
     t2.record(st);
@@ -568,8 +685,11 @@ int RT_API(rt_scene_update_instances)(rt_scene* s, const rt_instance* inst, uint
     if (!s || !inst) return fail("rt_scene_update_instances: null argument");
     if (n != s->instances.size()) return fail("rt_scene_update_instances: instance count differs from the scene's");
     for (uint32_t i = 0; i < n; ++i) if (inst[i].geo_id >= s->geo.size()) return fail("rt_scene_update_instances: geo_id out of range");
+    for (uint32_t i = 0; i < n; ++i) if (inst[i].geo_id != s->instances[i].geo_id) return fail("rt_scene_update_instances: geo_id of an instance may not change");
     s->instances.assign(inst, inst + n);
     rt_timer t0, t1; t0.create(); t1.create(); t0.record(s->ctx->stream);
+    if (upload_instance_records(s)) { t0.destroy(); t1.destroy(); return 1; }
+    if (s->merged.n_tris) refit_merged(s);        // baked instances moved: re-bake their triangles, refit the merged BLAS
     const int e = build_tlas(s);
     t1.record(s->ctx->stream); rt_stream_sync(s->ctx->stream); s->tlas_ms = rt_timer_ms(t0, t1); t0.destroy(); t1.destroy();
     if (e) return 1;
@@ -587,10 +707,10 @@ int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_ski
     run_skinning(s);
     t1.record(st);
     for (uint32_t g = 0; g < s->geo.size(); ++g) {
-        if (!s->geo[g].skinned) continue;
+        if (!s->geo[g].skinned || !s->geo[g].needed) continue;
         if (rebuild) { if (build_blas(s, g)) return 1; } else refit_blas(s, g);
     }
-    if (rebuild) { s->blas_depth = 0; for (auto& g : s->geo) if (g.depth > s->blas_depth) s->blas_depth = g.depth; }
+    if (s->merged_skinned && s->merged.n_tris) { if (rebuild) { if (build_merged(s)) return 1; } else refit_merged(s); }
     t2.record(st);
     const int e = build_tlas(s);
     t3.record(st);
@@ -788,7 +908,8 @@ int RT_API(rt_scene_read_vertices)(rt_scene* s, rt_vertex* out, uint32_t n) {
 int RT_API(rt_scene_bvh_info)(rt_scene* s, rt_bvh_info* o) {
     if (!s || !o) return fail("rt_scene_bvh_info: null argument");
     memset(o, 0, sizeof *o);
-    for (auto& g : s->geo) o->blas_nodes += g.n_nodes;
+    for (auto& g : s->geo) if (g.needed) o->blas_nodes += g.n_nodes;
+    o->blas_nodes += s->merged.n_nodes;
     o->blas_tris = s->total_tris; o->tlas_nodes = s->tlas_nodes;
     o->bytes = o->blas_nodes * 80ull + o->blas_tris * 48ull + o->tlas_nodes * 80ull + (uint64_t)s->instances.size() * (64 + 48);
     o->max_depth_blas = s->blas_depth; o->max_depth_tlas = s->tlas_depth;

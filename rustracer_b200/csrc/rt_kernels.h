@@ -210,8 +210,9 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 
 struct CoopShared {            // one per warp; SoA over the 32 owner lanes
     float ox[32], oy[32], oz[32], Sx[32], Sy[32], Sz[32], tmin[32], tmax[32], cur_t[32], u[32], v[32];
-    uint32_t kxyz[32], best_t[32], best_prim[32], done[32];
-    uint32_t inst[32], geo[32], alpha[32], rng[4][32];
+    unsigned long long best_ip[32];          // (instance << 32 | primitive) of the best candidate: lexicographic tie-break
+    uint32_t kxyz[32], best_t[32], done[32];
+    uint32_t inst[32], geo[32], alpha[32], rng[4][32];   // inst: 0xFFFFFFFF = merged BLAS (instance id in the triangle record)
     uint32_t items[RT_TQ_CAP];
 };
 
@@ -221,8 +222,9 @@ RT_D void coop_publish_ray(const Trav& tv, CoopShared& sh, uint32_t lane) {
     sh.Sx[lane] = tv.sh.Sx; sh.Sy[lane] = tv.sh.Sy; sh.Sz[lane] = tv.sh.Sz;
     sh.tmin[lane] = tv.tmin; sh.tmax[lane] = tv.tmax; sh.cur_t[lane] = tv.found ? tv.hit.t : tv.tmax;
     sh.kxyz[lane] = (uint32_t)tv.sh.kx | ((uint32_t)tv.sh.ky << 2) | ((uint32_t)tv.sh.kz << 4);
+    sh.inst[lane] = tv.merged ? 0xFFFFFFFFu : tv.cur_inst;
     if (ALPHA) {
-        sh.inst[lane] = tv.cur_inst; sh.geo[lane] = tv.cur_geo; sh.alpha[lane] = tv.cur_alpha ? 1u : 0u;
+        sh.geo[lane] = tv.cur_geo; sh.alpha[lane] = tv.cur_alpha ? 1u : 0u;
         sh.rng[0][lane] = tv.rng.x; sh.rng[1][lane] = tv.rng.y; sh.rng[2][lane] = tv.rng.z; sh.rng[3][lane] = tv.rng.w;
     }
 }
@@ -232,9 +234,9 @@ RT_D void coop_publish_ray(const Trav& tv, CoopShared& sh, uint32_t lane) {
 template <int MODE, bool ALPHA, bool COUNT>
 RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, uint32_t n, uint32_t lane, uint32_t& outstanding, bool usable, bool& terminated,
                      unsigned long long* c4) {
-    sh.best_t[lane] = 0xFFFFFFFFu; sh.best_prim[lane] = 0xFFFFFFFFu; sh.done[lane] = 0u;
+    sh.best_t[lane] = 0xFFFFFFFFu; sh.best_ip[lane] = ~0ull; sh.done[lane] = 0u;
     __syncwarp();
-    bool hit = false; float tt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t prim = 0, owner = 0, key = 0;
+    bool hit = false; float tt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t owner = 0, key = 0; unsigned long long ip = 0;
     if (lane < n) {
         const uint32_t item = sh.items[(head + lane) & (RT_TQ_CAP - 1u)];
         owner = item >> RT_TQ_TRI_BITS;
@@ -245,28 +247,36 @@ RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, u
         rs.kx = (int)(kk & 3u); rs.ky = (int)((kk >> 2) & 3u); rs.kz = (int)((kk >> 4) & 3u);
         rs.Sx = sh.Sx[owner]; rs.Sy = sh.Sy[owner]; rs.Sz = sh.Sz[owner];
         hit = tri_test(rs, mk3(sh.ox[owner], sh.oy[owner], sh.oz[owner]), xyz(a), xyz(b), xyz(c), sh.tmin[owner], sh.tmax[owner], tt, bu, bv);
-        prim = rt_float_as_uint(a.w);
+        const uint32_t prim = rt_float_as_uint(a.w);
+        const bool merged = sh.inst[owner] == 0xFFFFFFFFu;
+        const uint32_t inst = merged ? rt_float_as_uint(b.w) : sh.inst[owner];
+        ip = ((unsigned long long)inst << 32) | prim;
         if (hit && tt > sh.cur_t[owner]) hit = false;            // cannot beat the owner's committed hit
-        if (ALPHA && hit && sh.alpha[owner]) {
-            if (COUNT) c4[3]++;
-            u4 rng; rng.x = sh.rng[0][owner]; rng.y = sh.rng[1][owner]; rng.z = sh.rng[2][owner]; rng.w = sh.rng[3][owner];
-            if (anyhit_ignore(S, sh.inst[owner], prim, sh.geo[owner], bu, bv, rng)) hit = false;
+        if (ALPHA && hit) {
+            uint32_t geo; bool alpha;
+            trav_alpha_context(S, merged, inst, sh.geo[owner], sh.alpha[owner] != 0u, geo, alpha);
+            if (alpha) {
+                if (COUNT) c4[3]++;
+                u4 rng; rng.x = sh.rng[0][owner]; rng.y = sh.rng[1][owner]; rng.z = sh.rng[2][owner]; rng.w = sh.rng[3][owner];
+                if (anyhit_ignore(S, inst, prim, geo, bu, bv, rng)) hit = false;
+            }
         }
         if (hit) { key = float_to_ordered(tt); atomicMin(&sh.best_t[owner], key); }
         atomicAdd(&sh.done[owner], 1u);
     }
     __syncwarp();
-    if (hit && key == sh.best_t[owner]) atomicMin(&sh.best_prim[owner], prim);
+    if (hit && key == sh.best_t[owner]) atomicMin(&sh.best_ip[owner], ip);
     __syncwarp();
-    if (hit && key == sh.best_t[owner] && prim == sh.best_prim[owner]) { sh.u[owner] = bu; sh.v[owner] = bv; }
+    if (hit && key == sh.best_t[owner] && ip == sh.best_ip[owner]) { sh.u[owner] = bu; sh.v[owner] = bv; }
     __syncwarp();
     const uint32_t d = sh.done[lane];
     if (d) {
         outstanding -= d;
         if (usable && sh.best_t[lane] != 0xFFFFFFFFu) {
-            const float ct = ordered_to_float(sh.best_t[lane]); const uint32_t cp = sh.best_prim[lane];
-            if (trav_candidate_wins(tv, ct, cp)) {
-                trav_commit(tv, ct, sh.u[lane], sh.v[lane], cp);
+            const float ct = ordered_to_float(sh.best_t[lane]);
+            const uint32_t ci = (uint32_t)(sh.best_ip[lane] >> 32), cp = (uint32_t)sh.best_ip[lane];
+            if (trav_candidate_wins(tv, ct, ci, cp)) {
+                trav_commit(tv, ct, sh.u[lane], sh.v[lane], ci, cp);
                 sh.cur_t[lane] = ct;
                 if (MODE == RT_MODE_ANY) terminated = true;
             }
@@ -312,8 +322,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                 while (tv.ngroup.y <= 0x00FFFFFFu && tv.tgroup.y == 0u) {
                     if (tv.blas_sp >= 0 && tv.sp == tv.blas_sp) {
                         if (outstanding) { want_flush = true; break; }     // queued triangles refer to the object-space ray
-                        tv.blas_sp = -1; tv.nodes = S.tlas_nodes;
-                        trav_set_level_ray(tv, tv.ow, tv.dw);
+                        trav_leave_blas(tv, S);
                     }
                     if (tv.sp == 0) {
                         if (outstanding) { want_flush = true; break; }

@@ -52,6 +52,7 @@ static inline double rt_dmul(double a, double b) { return a * b; }
 static inline double rt_dsub(double a, double b) { return a - b; }
 static inline float rt_rsqrt(float x) { return 1.0f / sqrtf(x); }
 static inline float rt_rcp(float x) { return 1.0f / x; }
+static inline float rt_rcp_approx(float x) { return 1.0f / x; }
 static inline float rt_fma(float a, float b, float c) { return fmaf(a, b, c); }
 static inline uint32_t rt_float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float rt_uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -112,6 +113,7 @@ RT_D double rt_dmul(double a, double b) { return __dmul_rn(a, b); }
 RT_D double rt_dsub(double a, double b) { return __dsub_rn(a, b); }
 RT_D float rt_rsqrt(float x) { return rsqrtf(x); }
 RT_D float rt_rcp(float x) { return __frcp_rn(x); }
+RT_D float rt_rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // byte i of v -> float(2^23 + byte) with one PRMT (no I2F)
 RT_D float rt_byte_to_biased_float(uint32_t v, int i) { return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | (uint32_t)i)); }
 RT_D float rt_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }

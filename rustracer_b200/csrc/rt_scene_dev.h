@@ -15,13 +15,19 @@
 #define RT_LEAF_MAX 3
 #define RT_STACK_SIZE 48
 
-// BLAS primitive record, 48 bytes = 3 x float4: v0.xyz | primitive_id ; v1.xyz | 0 ; v2.xyz | 0
+// BLAS primitive record, 48 bytes = 3 x float4: v0.xyz | primitive_id ; v1.xyz | instance_id (merged BLAS only) ; v2.xyz | 0
 #define RT_TRI_F4 3
 
 // per-instance record for traversal, 64 bytes = 4 x float4: world->object 3x4 row-major (rows 0..2),
 // then { blas_root (node index), geo_id, flags (bit0: opaque geometry), 0 }
 #define RT_INST_F4 4
 #define RT_INST_OPAQUE 1u
+// The merged world-space BLAS: instances whose geometry is referenced once (or is tiny) are baked to world space
+// and share one BLAS, entered through a pseudo instance record with an identity transform (no ray transform, the
+// instance id comes from the triangle record).  DESIGN.md "baked instances".
+#define RT_INST_IDENTITY 2u
+#define RT_INST_MERGED 4u
+#define RT_BAKE_MAX_TRIS 256u
 
 struct DImage { const uint8_t* px; uint32_t w, h, srgb, _pad; };
 struct DTexture { uint32_t image, mag_filter, wrap_s, wrap_t; };

@@ -68,7 +68,7 @@ RT_D f3 xform_dir_exact(float4 r0, float4 r1, float4 r2, f3 d) {
 }
 
 RT_D uint32_t byte_of(uint32_t v, int i) { return (v >> (8 * i)) & 0xFFu; }
-RT_D float safe_rcp_dir(float d) { return rt_rcp(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
+RT_D float safe_rcp_dir(float d) { return rt_rcp_approx(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }   // slab test is padded: 1-ulp rcp is fine
 RT_D uint32_t octant_inv(f3 d) { return 7u - ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u)); }
 
 // Intersects the 8 quantised child boxes of one node.  Returns the hit mask: bits 24..31 inner children in
@@ -128,6 +128,7 @@ struct Trav {
     const float4* nodes; uint32_t tri_off;   // BLAS node array (rebased) and first triangle of the current BLAS
     int blas_sp;                          // stack height at BLAS entry; -1 = in the TLAS
     uint32_t cur_inst, cur_geo; bool cur_alpha;
+    bool merged, identity;                // current BLAS is the merged world-space BLAS / has an identity transform
     uint2 ngroup, tgroup; int sp;
     RtHit hit; bool found;
     u4 rng;
@@ -141,9 +142,15 @@ RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tm
     t.ow = ow; t.dw = dw; t.tmin = tmin; t.tmax = tmax; t.rng = rng;
     trav_set_level_ray(t, ow, dw);
     t.sh.kx = 0; t.sh.ky = 1; t.sh.kz = 2; t.sh.Sx = t.sh.Sy = t.sh.Sz = 0.0f;
-    t.nodes = S.tlas_nodes; t.tri_off = 0; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false;
+    t.nodes = S.tlas_nodes; t.tri_off = 0; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false; t.merged = false; t.identity = false;
     t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u); t.sp = 0;
     t.hit.t = tmax; t.hit.u = 0.0f; t.hit.v = 0.0f; t.hit.inst = 0xFFFFFFFFu; t.hit.prim = 0xFFFFFFFFu; t.found = false;
+}
+
+// BLAS exhausted: back to world space (nothing to recompute after an identity instance)
+RT_D void trav_leave_blas(Trav& t, const DScene& S) {
+    t.blas_sp = -1; t.nodes = S.tlas_nodes;
+    if (!t.identity) trav_set_level_ray(t, t.ow, t.dw);
 }
 
 // The traversal is a "while-while" loop (Aila & Laine 2009) over two kinds of steps:
@@ -176,11 +183,7 @@ RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
         t.tgroup.y = hm & 0x00FFFFFFu;
         return false;
     }
-    if (t.blas_sp >= 0 && t.sp == t.blas_sp) {
-        // BLAS exhausted: back to world space
-        t.blas_sp = -1; t.nodes = S.tlas_nodes;
-        trav_set_level_ray(t, t.ow, t.dw);
-    }
+    if (t.blas_sp >= 0 && t.sp == t.blas_sp) trav_leave_blas(t, S);
     if (t.sp == 0) return true;
     const uint2 e = stack[--t.sp];
     if (e.y > 0x00FFFFFFu) { t.ngroup = e; } else { t.tgroup = e; t.ngroup = make_uint2(0u, 0u); }
@@ -198,11 +201,17 @@ RT_D void trav_enter_instance(Trav& t, const DScene& S, uint2* stack, unsigned l
     const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
     const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
     if (COUNT) c4[2]++;
-    const f3 od = xform_dir_exact(r0, r1, r2, t.dw);
-    trav_set_level_ray(t, xform_point_exact(r0, r1, r2, t.ow), od);
-    t.sh = shear_init(od);
+    const uint32_t flags = rt_float_as_uint(meta.z);
+    t.identity = (flags & RT_INST_IDENTITY) != 0u; t.merged = (flags & RT_INST_MERGED) != 0u;
+    if (t.identity) {
+        t.sh = shear_init(t.dw);              // world ray is used as is
+    } else {
+        const f3 od = xform_dir_exact(r0, r1, r2, t.dw);
+        trav_set_level_ray(t, xform_point_exact(r0, r1, r2, t.ow), od);
+        t.sh = shear_init(od);
+    }
     t.cur_inst = inst; t.cur_geo = rt_float_as_uint(meta.y);
-    t.cur_alpha = ALPHA && !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
+    t.cur_alpha = ALPHA && !(flags & RT_INST_OPAQUE);
     // node / primitive indices inside a BLAS are local to it: rebase the array pointers
     t.nodes = S.blas_nodes + (size_t)rt_float_as_uint(meta.x) * RT_NODE_F4;
     t.tri_off = rt_float_as_uint(meta.w);
@@ -213,14 +222,22 @@ RT_D void trav_enter_instance(Trav& t, const DScene& S, uint2* stack, unsigned l
 }
 
 // closest-hit acceptance of a geometric candidate of the current instance: lexicographic (t, instance, primitive)
-RT_D bool trav_candidate_wins(const Trav& t, float tt, uint32_t prim) {
+RT_D bool trav_candidate_wins(const Trav& t, float tt, uint32_t inst, uint32_t prim) {
     if (!t.found) return true;
     if (tt > t.hit.t) return false;
-    if (tt == t.hit.t && !(t.cur_inst < t.hit.inst || (t.cur_inst == t.hit.inst && prim < t.hit.prim))) return false;
+    if (tt == t.hit.t && !(inst < t.hit.inst || (inst == t.hit.inst && prim < t.hit.prim))) return false;
     return true;
 }
-RT_D void trav_commit(Trav& t, float tt, float bu, float bv, uint32_t prim) {
-    t.hit.t = tt; t.hit.u = bu; t.hit.v = bv; t.hit.inst = t.cur_inst; t.hit.prim = prim; t.found = true;
+RT_D void trav_commit(Trav& t, float tt, float bu, float bv, uint32_t inst, uint32_t prim) {
+    t.hit.t = tt; t.hit.u = bu; t.hit.v = bv; t.hit.inst = inst; t.hit.prim = prim; t.found = true;
+}
+// alpha-test context of a triangle: per instance record for the merged BLAS, else the current instance's
+RT_D void trav_alpha_context(const DScene& S, bool merged, uint32_t inst, uint32_t cur_geo, bool cur_alpha, uint32_t& geo, bool& alpha) {
+    geo = cur_geo; alpha = cur_alpha;
+    if (merged) {
+        const float4 meta = rt_ld(S.inst_w2o + (size_t)inst * RT_INST_F4 + 3);
+        geo = rt_float_as_uint(meta.y); alpha = !(rt_float_as_uint(meta.z) & RT_INST_OPAQUE);
+    }
 }
 
 template <int MODE, bool ALPHA, bool COUNT>
@@ -234,12 +251,17 @@ RT_D bool trav_prim_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
     float tt, bu, bv;
     if (!tri_test(t.sh, t.o, xyz(a), xyz(b), xyz(c), t.tmin, t.tmax, tt, bu, bv)) return false;
     const uint32_t prim = rt_float_as_uint(a.w);
-    if (!trav_candidate_wins(t, tt, prim)) return false;
-    if (ALPHA && t.cur_alpha) {
-        if (COUNT) c4[3]++;
-        if (anyhit_ignore(S, t.cur_inst, prim, t.cur_geo, bu, bv, t.rng)) return false;
+    const uint32_t inst = t.merged ? rt_float_as_uint(b.w) : t.cur_inst;
+    if (!trav_candidate_wins(t, tt, inst, prim)) return false;
+    if (ALPHA) {
+        uint32_t geo; bool alpha;
+        trav_alpha_context(S, t.merged, inst, t.cur_geo, t.cur_alpha, geo, alpha);
+        if (alpha) {
+            if (COUNT) c4[3]++;
+            if (anyhit_ignore(S, inst, prim, geo, bu, bv, t.rng)) return false;
+        }
     }
-    trav_commit(t, tt, bu, bv, prim);
+    trav_commit(t, tt, bu, bv, inst, prim);
     return MODE == RT_MODE_ANY;
 }
 

@@ -65,6 +65,11 @@ def case_instancing(api):
     for _ in range(40):
         q = rng.normal(size=4); q /= np.linalg.norm(q)
         b.add_instance(g, scenes.trs(rng.uniform(-8, 8, 3), q, rng.uniform(0.3, 1.5, 3)))
+    # baked instances next to the instanced ones: a single-use floor and a tiny (<= 256 triangles) mesh used twice
+    gf = b.add_geometry(*scenes.box_mesh((9, 0.1, 9)), m)
+    b.add_instance(gf, scenes.trs((0, -9, 0)))
+    gs = b.add_geometry(*scenes.uv_sphere(1.0, 6, 8), m)
+    b.add_instance(gs, scenes.trs((0, 5, 0), scale=(3, 3, 3))); b.add_instance(gs, scenes.trs((4, 5, 1), scale=(2, 1, 2)))
     d = b.build()
     o = orc.OracleScene(d)
     ctx, sc = make(api, d, 32, 32)
