@@ -187,6 +187,9 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 #ifndef RT_EMU
 // ---- CUDA kernels -------------------------------------------------------------------------------------
 #define RT_EXTEND_THREADS 128
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 6   // <= 85 registers: 24 warps per SM
+#endif
 
 // Persistent traversal kernel body.
 //  * per-lane dynamic fetch (Aila & Laine 2009; Ylitie et al. 2017): every lane owns a resumable traversal state;
@@ -388,7 +391,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
 }
 
 template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
     persistent_trace<RT_MODE_CLOSEST, ALPHA, COUNT>(S, *count_ptr, fetch, cnt,
         [&](uint32_t i, Trav& tv) {
             const float4 a = q.o_tmin[i], b = q.d_tmax[i];
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS) extend_kernel(DScene S, Fra
 }
 
 template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
     persistent_trace<RT_MODE_ANY, ALPHA, COUNT>(S, *count_ptr, fetch, cnt,
         [&](uint32_t i, Trav& tv) {
             const float4 a = sq.o_tmax[i], b = sq.d_pix[i];
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS) shadow_kernel(DScene S, Fra
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
+__global__ void __launch_bounds__(128, 4) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
                                                     const uint32_t* count_ptr, uint32_t* out_count, uint32_t* shadow_count, uint32_t bounce, RtCounters* cnt) {
     const uint32_t count = *count_ptr;
     const uint32_t lane = threadIdx.x & 31u;

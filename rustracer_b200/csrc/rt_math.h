@@ -23,7 +23,7 @@ RT_D f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
 RT_D f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 RT_D f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 RT_D f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
-RT_D f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+RT_D f3 operator/(f3 a, float s) { const float r = 1.0f / s; return mk3(a.x * r, a.y * r, a.z * r); }
 RT_D f3 operator+(f3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
 RT_D f3 operator-(f3 a, float s) { return mk3(a.x - s, a.y - s, a.z - s); }
 RT_D f3 operator-(float s, f3 a) { return mk3(s - a.x, s - a.y, s - a.z); }
@@ -46,8 +46,23 @@ RT_D float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 RT_D float dot(f4 a, f4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 RT_D f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
 RT_D float length(f3 a) { return sqrtf(dot(a, a)); }
-RT_D f3 normalize(f3 a) { return a / length(a); }
-RT_D f4 normalize(f4 a) { float l = sqrtf(dot(a, a)); return mk4(a.x / l, a.y / l, a.z / l, a.w / l); }
+RT_D f3 normalize(f3 a) { const float r = rt_rsqrt(dot(a, a)); return mk3(a.x * r, a.y * r, a.z * r); }
+RT_D f4 normalize(f4 a) { const float r = rt_rsqrt(dot(a, a)); return mk4(a.x * r, a.y * r, a.z * r, a.w * r); }
+// bit-exact counterparts used by raygen so that primary rays are identical to the oracle's (debug channels and hit
+// ids of primary rays then match exactly): explicitly rounded ops, oracle operation order
+RT_D f3 normalize_exact(f3 a) {
+    const float l = sqrtf(rt_fadd(rt_fadd(rt_fmul(a.x, a.x), rt_fmul(a.y, a.y)), rt_fmul(a.z, a.z)));
+    return mk3(rt_fdiv(a.x, l), rt_fdiv(a.y, l), rt_fdiv(a.z, l));
+}
+RT_D f4 mat4_mul_exact(const float* M, f4 v) {
+    f4 r;
+    r.x = rt_fadd(rt_fadd(rt_fadd(rt_fmul(M[0], v.x), rt_fmul(M[4], v.y)), rt_fmul(M[8], v.z)), rt_fmul(M[12], v.w));
+    r.y = rt_fadd(rt_fadd(rt_fadd(rt_fmul(M[1], v.x), rt_fmul(M[5], v.y)), rt_fmul(M[9], v.z)), rt_fmul(M[13], v.w));
+    r.z = rt_fadd(rt_fadd(rt_fadd(rt_fmul(M[2], v.x), rt_fmul(M[6], v.y)), rt_fmul(M[10], v.z)), rt_fmul(M[14], v.w));
+    r.w = rt_fadd(rt_fadd(rt_fadd(rt_fmul(M[3], v.x), rt_fmul(M[7], v.y)), rt_fmul(M[11], v.z)), rt_fmul(M[15], v.w));
+    return r;
+}
+RT_D float pow5(float x) { const float x2 = x * x; return x2 * x2 * x; }
 RT_D float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 RT_D float saturate(float x) { return clampf(x, 0.0f, 1.0f); }
 RT_D f3 min3(f3 a, f3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }

@@ -25,7 +25,7 @@ struct Surface {           // MaterialBrdf (PBR.glsl:173-193), only the fields t
     f3 attenuation_color; float attenuation_distance;
     bool volume, front_face;
 };
-RT_D f3 fresnel_schlick(f3 f0, float f90, float NdotS) { return f0 + (f90 - f0) * powf(1.0f - NdotS, 5.0f); }   // :228-231
+RT_D f3 fresnel_schlick(f3 f0, float f90, float NdotS) { return f0 + (f90 - f0) * pow5(1.0f - NdotS); }   // :228-231
 RT_D float shadowed_f90(f3 F90) { return fminf(1.0f, luminance(F90)); }                                           // :312-322
 RT_D float smith_g_a(float alpha, float NdotS) { return NdotS / (fmaxf(0.00001f, alpha) * sqrtf(1.0f - fminf(0.99999f, NdotS * NdotS))); }
 RT_D float smith_lambda_ggx(float a) { return (-1.0f + sqrtf(1.0f + (1.0f / (a * a)))) * 0.5f; }
@@ -54,8 +54,8 @@ RT_D BrdfTerms prepare_brdf(f3 N, f3 L, f3 V, const Surface& m) {   // prepareBR
 RT_D float frostbite_diffuse(const BrdfTerms& d, float roughness) {   // :486-496
     const float energyBias = 0.5f * roughness, energyFactor = mixf(1.0f, 1.0f / 1.51f, roughness);
     const float FD90MinusOne = energyBias + 2.0f * d.LdotH * d.LdotH * roughness - 1.0f;
-    const float FDL = 1.0f + (FD90MinusOne * powf(1.0f - d.NdotL, 5.0f));
-    const float FDV = 1.0f + (FD90MinusOne * powf(1.0f - d.NdotV, 5.0f));
+    const float FDL = 1.0f + (FD90MinusOne * pow5(1.0f - d.NdotL));
+    const float FDV = 1.0f + (FD90MinusOne * pow5(1.0f - d.NdotV));
     return FDL * FDV * energyFactor;
 }
 RT_D f3 eval_combined_brdf(f3 N, f3 L, f3 V, const Surface& m) {   // evalCombinedBRDF :731-745
@@ -197,18 +197,22 @@ RT_D PathState raygen_path(const FrameParams& P, uint32_t pixel, uint32_t pix_w,
     if (P.sample == 0) { pix_w = 0; path_w = 0; lens_seed = tea16(tea16(px, py), P.clk); }
     u4 pix = pixel_stream(P, pixel, pix_w);
     f2 pc = mk2((float)px + 0.5f, (float)py + 0.5f);
-    if (ubo.antialiasing) { const float ox = rng_next(pix), oy = rng_next(pix); pc = mk2(pc.x + (ox - 0.5f), pc.y + (oy - 0.5f)); }
-    const f2 uv = mk2((pc.x / (float)P.width) * 2.0f - 1.0f, (pc.y / (float)P.height) * 2.0f - 1.0f);
+    if (ubo.antialiasing) { const float ox = rng_next(pix), oy = rng_next(pix); pc = mk2(rt_fadd(pc.x, rt_fsub(ox, 0.5f)), rt_fadd(pc.y, rt_fsub(oy, 0.5f))); }
+    // everything up to the primary ray is evaluated with explicitly rounded operations in the oracle's order
+    const f2 uv = mk2(rt_fsub(rt_fmul(rt_fdiv(pc.x, (float)P.width), 2.0f), 1.0f), rt_fsub(rt_fmul(rt_fdiv(pc.y, (float)P.height), 2.0f), 1.0f));
     const f2 disk = random_in_unit_disk(lens_seed);
-    const f2 offset = mk2(ubo.aperture / 2 * disk.x, ubo.aperture / 2 * disk.y);
-    f4 origin = mat4_mul(ubo.model_view_inverse, mk4(offset.x, offset.y, 0.0f, 1.0f));
-    const f4 target = mat4_mul(ubo.projection_inverse, mk4(uv.x, uv.y, 1.0f, 1.0f));
-    f4 direction = mat4_mul(ubo.model_view_inverse, mk4(normalize(xyz(target) * ubo.focus_distance - mk3(offset.x, offset.y, 0.0f)), 0.0f));
+    const float half_ap = rt_fdiv(ubo.aperture, 2.0f);
+    const f2 offset = mk2(rt_fmul(half_ap, disk.x), rt_fmul(half_ap, disk.y));
+    f4 origin = mat4_mul_exact(ubo.model_view_inverse, mk4(offset.x, offset.y, 0.0f, 1.0f));
+    const f4 target = mat4_mul_exact(ubo.projection_inverse, mk4(uv.x, uv.y, 1.0f, 1.0f));
+    const f3 tdir = mk3(rt_fsub(rt_fmul(target.x, ubo.focus_distance), offset.x), rt_fsub(rt_fmul(target.y, ubo.focus_distance), offset.y), rt_fsub(rt_fmul(target.z, ubo.focus_distance), 0.0f));
+    f4 direction = mat4_mul_exact(ubo.model_view_inverse, mk4(normalize_exact(tdir), 0.0f));
     float tFar = RT_TMAX;
     if (ubo.orthographic_fov_dis > 0.0f) {
-        const f2 nuv = mk2((1.0f + ubo.orthographic_fov_dis) * uv.x, (1.0f + ubo.orthographic_fov_dis) * uv.y);
-        origin = mat4_mul(ubo.model_view_inverse, mk4(nuv.x, -nuv.y, 0.0f, 1.0f));
-        direction = mat4_mul(ubo.model_view_inverse, mk4(0.0f, 0.0f, -1.0f, 0.0f));
+        const float k = rt_fadd(1.0f, ubo.orthographic_fov_dis);
+        const f2 nuv = mk2(rt_fmul(k, uv.x), rt_fmul(k, uv.y));
+        origin = mat4_mul_exact(ubo.model_view_inverse, mk4(nuv.x, -nuv.y, 0.0f, 1.0f));
+        direction = mat4_mul_exact(ubo.model_view_inverse, mk4(0.0f, 0.0f, -1.0f, 0.0f));
         tFar = 10.0f * RT_TMAX;
     }
     PathState s;
@@ -415,7 +419,7 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
             const float eta = front_face ? 1.0f / mat.ior : mat.ior;
             const f3 refr = refract3(wd, N, eta);
             float r0 = (1.0f - eta) / (1.0f + eta); r0 *= r0;
-            const float reflectProb = !is_zero(refr) ? (r0 + (1.0f - r0) * powf(1.0f - fabsf(cosv), 5.0f)) : 1.0f;
+            const float reflectProb = !is_zero(refr) ? (r0 + (1.0f - r0) * pow5(1.0f - fabsf(cosv))) : 1.0f;
             o.hit_value = color; o.need_scatter = true;
             if (lcg_float(seed) < reflectProb) o.next_dir = reflect3(wd, normal); else o.next_dir = refr;
         } else if (length(emissive) < 0.01f && roughness == 1.0f) {

@@ -23,7 +23,7 @@ RT_D f2 random_in_unit_disk(uint32_t& seed) {   // :44-54
     for (;;) {
         float a = lcg_float(seed), b = lcg_float(seed);
         f2 p = mk2(2.0f * a - 1.0f, 2.0f * b - 1.0f);
-        if (p.x * p.x + p.y * p.y < 1.0f) return p;
+        if (rt_fadd(rt_fmul(p.x, p.x), rt_fmul(p.y, p.y)) < 1.0f) return p;   // same rounding as the oracle
     }
 }
 RT_D f3 random_in_unit_sphere(uint32_t& seed) {   // :56-66
