@@ -314,8 +314,16 @@ def run_ours(args):
         trav_bytes, frame_bytes = algorithmic_bytes(tot)
         ext_bytes = 48 * tot["rays_extend"] + 80 * tot["nodes"] + 48 * tot["tris"] + 64 * tot["insts"]   # shadow rays: none in this scene
         achieved = ext_bytes / (stage["extend"] * 1e-3) / 1e9 if stage["extend"] > 0 else None
+        traffic = None
+        tj = ROOT / "profiles" / "r01_extend_traffic.json"     # dram__bytes_read+write per launch from the committed ncu capture
+        if tj.exists():
+            try:
+                traffic = float(json.loads(tj.read_text())["mean_dram_bytes_per_launch"])
+            except Exception:
+                traffic = None
         roof = {"bound": "hbm", "kernel": "extend_kernel (BVH8 traversal + watertight test)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_extend_traffic.json)",
+                "algorithmic_bytes_per_launch": ext_bytes / max(1, n_ext), "peak_source": peak_src,
                 "algorithmic_bytes_per_ray": ext_bytes / max(1, tot["rays_extend"]), "avg_launch_ms": stage["extend"] / max(1, n_ext), "launches": n_ext,
                 "nodes_per_ray": tot["nodes"] / max(1, rays_rank), "tris_per_ray": tot["tris"] / max(1, rays_rank),
                 "whole_frame_algorithmic_gbs": frame_bytes / (ms * 1e-3) / 1e9, "whole_frame_frac": frame_bytes / (ms * 1e-3) / 1e9 / peak,
