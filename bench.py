@@ -202,7 +202,8 @@ def run_ours(args):
     gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES)
     K, Wm = args.steps, args.warmup
     # sample-pass sharding (§8e B): global frame g = step * world + rank; every rank starts from a zero accumulation
-    ubos = [frame_ubo(cam, gui, (s * world + rank), desc.fully_opaque) for s in range(Wm + K)]
+    from rustracer_b200 import sharding
+    ubos = [frame_ubo(cam, gui, sharding.global_frame(s, rank, world), desc.fully_opaque) for s in range(Wm + K)]
     final_ubo = frame_ubo(cam, gui, (Wm + K) * world - 1, desc.fully_opaque)
 
     peers = []
@@ -218,8 +219,7 @@ def run_ours(args):
             ctx.api.check(ctx.api.rt_ipc_open(ctx._h, buf, C.byref(p)))
             peers.append(p.value)
     peer_arr = (C.c_void_p * max(1, len(peers)))(*peers)
-    rows_per = (HEIGHT + world - 1) // world
-    row0, row1 = min(HEIGHT, rank * rows_per), min(HEIGHT, (rank + 1) * rows_per)
+    row0, row1 = sharding.reduce_rows(rank, world, HEIGHT)
 
     def barrier():
         torch.cuda.synchronize()
