@@ -329,7 +329,7 @@ def run_ours(args):
                 "whole_frame_algorithmic_gbs": frame_bytes / (ms * 1e-3) / 1e9, "whole_frame_frac": frame_bytes / (ms * 1e-3) / 1e9 / peak,
                 "stage_ms_per_step": {k: v / K for k, v in stage.items()}}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported at N=1 only (torchrun pins OMP_NUM_THREADS=1)
             try:
                 from oracle import orc
                 m, rays, secs = cpu_sample(desc, 1, (0, HEIGHT))
