@@ -208,7 +208,10 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 #define RT_REFILL_BELOW 22     // refill when fewer than this many lanes still hold a ray
 #endif
 #define RT_WARPS_PER_BLOCK (RT_EXTEND_THREADS / 32)
-#define RT_TQ_CAP 1024u        // per-warp triangle queue capacity (>= 31 + 32 * 24)
+#ifndef RT_TQ_PUSH_MAX
+#define RT_TQ_PUSH_MAX 7        // triangles a lane may queue per iteration (the rest stay parked in its tgroup)
+#endif
+#define RT_TQ_CAP 256u         // per-warp triangle queue capacity (power of two, >= 31 + 32 * RT_TQ_PUSH_MAX)
 #define RT_TQ_TRI_BITS 27      // item = owner lane << 27 | absolute triangle index
 
 struct CoopShared {            // one per warp; SoA over the 32 owner lanes
@@ -335,14 +338,24 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                     if (e.y > 0x00FFFFFFu) tv.ngroup = e; else { tv.tgroup = e; tv.ngroup = make_uint2(0u, 0u); }
                 }
                 if (active && !want_flush) {
-                    if (tv.tgroup.y != 0u) {
-                        // TLAS level: parked instances.  (Triangles are never parked in tgroup: they go to the queue.)
+                    if (tv.tgroup.y != 0u && tv.blas_sp < 0) {
+                        // TLAS level: parked instances
                         trav_enter_instance<ALPHA, COUNT>(tv, S, stack, c4);
                         coop_publish_ray<ALPHA>(tv, sh, lane);
                     } else {
-                        const bool in_blas = tv.blas_sp >= 0;
-                        trav_node_step<COUNT>(tv, S, stack, c4);          // ngroup has an inner child: visits it
-                        if (in_blas) { leaf_mask = tv.tgroup.y; leaf_base = tv.tri_off + tv.tgroup.x; tv.tgroup.y = 0u; }
+                        // BLAS level with leftover leaf triangles parked: queue those first; else visit the next node
+                        if (tv.tgroup.y == 0u) trav_node_step<COUNT>(tv, S, stack, c4);
+                        if (tv.blas_sp >= 0 && tv.tgroup.y != 0u) {
+                            leaf_base = tv.tri_off + tv.tgroup.x;
+                            leaf_mask = tv.tgroup.y;
+                            if (__popc(leaf_mask) > RT_TQ_PUSH_MAX) {     // keep the RT_TQ_PUSH_MAX highest bits, park the rest
+                                uint32_t keep = 0u, m = leaf_mask;
+#pragma unroll
+                                for (int q = 0; q < RT_TQ_PUSH_MAX; ++q) { const uint32_t b = 1u << (31 - __clz((int)m)); keep |= b; m &= ~b; }
+                                leaf_mask = keep;
+                            }
+                            tv.tgroup.y &= ~leaf_mask;
+                        }
                     }
                 }
             }

@@ -94,6 +94,11 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, 
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const uint32_t meta4 = rt_float_as_uint(half ? n1.w : n1.z);
+        // per byte: inner children (low 5 bits >= 24) take priority slot ^ octinv, leaves keep their primitive offset
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
+        const uint32_t bit_index4 = (meta4 ^ ((octinv * 0x01010101u) & inner_mask4 & 0x07070707u)) & 0x1F1F1F1Fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t qlox = rt_float_as_uint(half ? n2.y : n2.x), qloy = rt_float_as_uint(half ? n2.w : n2.z), qloz = rt_float_as_uint(half ? n3.y : n3.x);
         const uint32_t qhix = rt_float_as_uint(half ? n3.w : n3.z), qhiy = rt_float_as_uint(half ? n4.y : n4.x), qhiz = rt_float_as_uint(half ? n4.w : n4.z);
         const uint32_t nx = idir.x < 0.0f ? qhix : qlox, fx = idir.x < 0.0f ? qlox : qhix;
@@ -101,17 +106,12 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, 
         const uint32_t nz = idir.z < 0.0f ? qhiz : qloz, fz = idir.z < 0.0f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t meta = byte_of(meta4, j);
             const float tnx = fmaf(rt_byte_to_biased_float(nx, j), ax, cxn), tfx = fmaf(rt_byte_to_biased_float(fx, j), ax, cxf);
             const float tny = fmaf(rt_byte_to_biased_float(ny, j), ay, cyn), tfy = fmaf(rt_byte_to_biased_float(fy, j), ay, cyf);
             const float tnz = fmaf(rt_byte_to_biased_float(nz, j), az, czn), tfz = fmaf(rt_byte_to_biased_float(fz, j), az, czf);
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (cmin <= cmax) {
-                const bool inner = (meta & 0x18u) == 0x18u;
-                const uint32_t bit_index = (inner ? (meta ^ (octinv & 7u)) : meta) & 0x1Fu;
-                hitmask |= (meta >> 5) << bit_index;
-            }
+            if (cmin <= cmax) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
         }
     }
     return hitmask;
