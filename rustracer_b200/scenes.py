@@ -314,3 +314,169 @@ def cornell_box(lucy: bool = False, blend_sphere: bool = True, lucy_rows=474, lu
                                    (0.007677134592086077,) * 3))
     b.normalize()
     return b.build()
+
+
+# ----------------------------------------------------------------------------------------------------
+# config 3: instanced foliage
+# ----------------------------------------------------------------------------------------------------
+def leaf_mask_texture(size=1024, seed=11) -> np.ndarray:
+    """Procedural RGBA8 sRGB leaf-mask: green leaves with alpha 255 inside blobs, 0 outside."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32) / size
+    a = np.zeros((size, size), np.float32)
+    for _ in range(24):
+        cx, cy, r, e = rng.uniform(0.1, 0.9), rng.uniform(0.1, 0.9), rng.uniform(0.05, 0.16), rng.uniform(0.3, 1.0)
+        a = np.maximum(a, (((x - cx) / r) ** 2 + ((y - cy) / (r * e)) ** 2 < 1.0).astype(np.float32))
+    img = np.zeros((size, size, 4), np.uint8)
+    img[..., 0] = 40 + 30 * np.sin(x * 40); img[..., 1] = 140 + 60 * np.cos(y * 33); img[..., 2] = 50
+    img[..., 3] = (a * 255).astype(np.uint8)
+    return img
+
+
+def displaced_icosphere_like(n_tris_target=100_000, seed=1):
+    """One BLAS: displaced sphere with ~n_tris_target triangles (grid tessellation)."""
+    rows = max(4, int(math.sqrt(n_tris_target / 2)))
+    cols = max(4, n_tris_target // (2 * rows))
+    rng = np.random.default_rng(seed)
+    p, n, uv, idx = uv_sphere(1.0, rows, cols)
+    th = np.arccos(np.clip(n[:, 1], -1, 1)); ph = np.arctan2(n[:, 2], n[:, 0])
+    d = np.ones(len(p))
+    for k in range(1, 6):
+        d += (0.12 / k) * np.sin(k * 5 * th + rng.uniform(0, 6.28)) * np.cos(k * 7 * ph + rng.uniform(0, 6.28))
+    return (p * d[:, None].astype(np.float32)), n, uv, idx
+
+
+def foliage_cards(n_cards=64, seed=5):
+    """Alpha-tested quads (2 triangles each) with random orientation around the unit sphere."""
+    rng = np.random.default_rng(seed)
+    pos, nrm, uv, idx = [], [], [], []
+    for c in range(n_cards):
+        centre = rng.normal(size=3); centre *= rng.uniform(1.0, 1.6) / np.linalg.norm(centre)
+        t = rng.normal(size=3); t -= centre * np.dot(t, centre) / np.dot(centre, centre); t /= np.linalg.norm(t)
+        b = np.cross(centre / np.linalg.norm(centre), t)
+        s = rng.uniform(0.25, 0.5)
+        base = len(pos)
+        for (su, sv) in ((-1, -1), (1, -1), (1, 1), (-1, 1)):
+            pos.append(centre + s * (su * t + sv * b)); nrm.append(centre / np.linalg.norm(centre)); uv.append(((su + 1) / 2 * 0.5 + rng.integers(2) * 0.5, (sv + 1) / 2))
+        idx += [base, base + 1, base + 2, base, base + 2, base + 3]
+    return np.array(pos, np.float32), np.array(nrm, np.float32), np.array(uv, np.float32), np.array(idx, np.uint32)
+
+
+def instanced_foliage(n_side=100, tris_per_mesh=100_000, cards=64, tex_size=1024, seed=2, sky=None) -> F.rt_scene_desc:
+    """Config 3: n_side^2 instances of one ~tris_per_mesh BLAS on a jittered grid (random yaw, scale in [0.5,1.5]),
+    a metallic-roughness material and an alpha-MASK foliage-card geometry with a procedural leaf texture."""
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder()
+    metal = b.add_material(material((0.9, 0.6, 0.3, 1.0), metallic=1.0, roughness=0.25))
+    img = b.add_image(leaf_mask_texture(tex_size), srgb=True)
+    tex = b.add_texture(img, mag=1, wrap_s=2, wrap_t=2)
+    leaf = b.add_material(material((1, 1, 1, 1), metallic=0.0, roughness=0.8, alpha_mode=2, alpha_cutoff=0.5, base_color_texture=tex))
+    ground = b.add_material(material((0.4, 0.4, 0.4, 1), metallic=0.0, roughness=0.9))
+    g_body = b.add_geometry(*displaced_icosphere_like(tris_per_mesh, seed=1), metal)
+    g_leaf = b.add_geometry(*foliage_cards(cards), leaf)
+    g_ground = b.add_geometry(*box_mesh((n_side * 2.0, 0.1, n_side * 2.0)), ground)
+    b.add_instance(g_ground, trs((0, -1.8, 0)))
+    for i in range(n_side):
+        for j in range(n_side):
+            yaw = rng.uniform(0, 2 * math.pi); s = rng.uniform(0.5, 1.5)
+            T = trs(((i - n_side / 2 + rng.uniform(-0.3, 0.3)) * 3.5, 0.0, (j - n_side / 2 + rng.uniform(-0.3, 0.3)) * 3.5),
+                    (0, math.sin(yaw / 2), 0, math.cos(yaw / 2)), (s, s, s))
+            b.add_instance(g_body, T); b.add_instance(g_leaf, T)
+    b.normalize()
+    dl = np.zeros(1, F.LIGHT_DTYPE); dl["color"], dl["transform"], dl["kind"], dl["range"], dl["intensity"] = 1.0, [[-0.4, -1.0, -0.3, 0.0]], 0, np.inf, 1.0
+    b.set_lights(dlights=dl)
+    if sky is not None:
+        b.sky = (sky, True)
+    return b.build()
+
+
+def procedural_sky(size=64, seed=3):
+    """Six RGBA8 faces (+x,-x,+y,-y,+z,-z): vertical gradient with a bright patch, stands in for the Yokohama skybox."""
+    rng = np.random.default_rng(seed)
+    faces = []
+    for f in range(6):
+        y = np.linspace(0, 1, size, dtype=np.float32)[:, None] * np.ones((1, size), np.float32)
+        img = np.zeros((size, size, 4), np.uint8)
+        base = np.array([90, 140, 220]) if f != 3 else np.array([60, 50, 40])
+        img[..., :3] = np.clip(base[None, None, :] * (1.2 - 0.6 * y[..., None]) + rng.integers(0, 6, (size, size, 3)), 0, 255)
+        if f == 2:
+            img[size // 3: size // 2, size // 3: size // 2, :3] = 255
+        img[..., 3] = 255
+        faces.append(img)
+    return faces
+
+
+# ----------------------------------------------------------------------------------------------------
+# config 4: skinned character
+# ----------------------------------------------------------------------------------------------------
+def skinned_character(n_tris=1_000_000, joints=256, seed=3):
+    """Capsule-limb rig: one skin x `joints` joints, 4 normalised weights per vertex.  Returns (desc, pose_fn) where
+    pose_fn(frame) -> (1,256,16) column-major skin matrices of a looping 60-frame animation."""
+    rng = np.random.default_rng(seed)
+    rows = max(8, int(math.sqrt(n_tris / 2) * 2)); cols = max(8, n_tris // (2 * rows))
+    p, n, uv, idx = uv_sphere(1.0, rows, cols)
+    p = p * np.array([0.6, 3.0, 0.6], np.float32)          # tall capsule, y in [-3, 3]
+    t = (p[:, 1] + 3.0) / 6.0 * (joints - 1)
+    j0 = np.clip(np.floor(t).astype(np.int64), 1, joints - 3)
+    w = np.zeros((len(p), 4), np.float32); jj = np.zeros((len(p), 4), np.uint32)
+    f = (t - j0).astype(np.float32)
+    w[:, 0] = np.clip(0.5 - 0.5 * f, 0, 1) * 0.5; w[:, 1] = 1 - f * 0.5 - w[:, 0]; w[:, 2] = f * 0.5; w[:, 3] = 0.0
+    w[:, 3] = rng.uniform(0, 0.1, len(p)).astype(np.float32)
+    w /= w.sum(1, keepdims=True)
+    jj[:, 0], jj[:, 1], jj[:, 2], jj[:, 3] = j0 - 1, j0, j0 + 1, j0 + 2
+    b = SceneBuilder()
+    skin_m = b.add_material(material((0.8, 0.7, 0.6, 1), metallic=0.0, roughness=0.6))
+    g = b.add_geometry(p, n, uv, idx, skin_m, weights=w, joints=jj, skin_index=0)
+    b.add_instance(g, np.eye(4))                            # skinned nodes get the identity instance transform
+    floor = b.add_material(material((0.5, 0.5, 0.5, 1), metallic=0.0))
+    gf = b.add_geometry(*box_mesh((6, 0.1, 6)), floor)
+    b.add_instance(gf, trs((0, -3.6, 0)))
+    lamp = b.add_material(material(metallic=0.0, roughness=0.0, emissive=(1, 1, 1)))
+    gl = b.add_geometry(*box_mesh((2, 0.05, 2)), lamp)
+    b.add_instance(gl, trs((0, 5.0, 0)))
+
+    def pose(frame: int):
+        ph = 2 * math.pi * (frame % 60) / 60.0
+        mats = np.zeros((1, 256, 16), np.float32)
+        mats[0, :, [0, 5, 10, 15]] = 1.0
+        for j in range(joints):
+            a = 0.25 * math.sin(ph + 0.05 * j) * (j / joints)
+            M = trs((0.4 * math.sin(ph + 0.03 * j) * (j / joints), 0.0, 0.3 * math.cos(ph * 2 + 0.02 * j) * (j / joints)), (0, 0, math.sin(a / 2), math.cos(a / 2)))
+            mats[0, j] = M.T.reshape(16).astype(np.float32)
+        return mats
+    b.skins = pose(0)
+    return b.build(), pose
+
+
+# ----------------------------------------------------------------------------------------------------
+# config 5: transmission / volume scene
+# ----------------------------------------------------------------------------------------------------
+def glass_box(n_objects=64, seed=9, sphere_res=(48, 49)) -> F.rt_scene_desc:
+    """Cornell-type box holding n_objects glass spheres (transmission 1, volume on, attDist in [0.5,2], random
+    attenuation colour, ior 1.5, roughness 0) and one emissive quad."""
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder()
+    white = b.add_material(material(metallic=0.0)); red = b.add_material(material((0.9, 0.1, 0.1, 1), metallic=0.0))
+    green = b.add_material(material((0.1, 0.9, 0.1, 1), metallic=0.0)); light = b.add_material(material(metallic=0.0, roughness=0.0, emissive=(1, 1, 1)))
+    e = 0.05
+    for geo, T in ((box_mesh((5, 5, e)), trs((0, 0, -5))), (box_mesh((5, e, 5)), trs((0, -5, 0))), (box_mesh((5, e, 5)), trs((0, 5, 0)))):
+        b.add_instance(b.add_geometry(*geo, white), T)
+    b.add_instance(b.add_geometry(*box_mesh((e, 5, 5)), green), trs((-5, 0, 0)))
+    b.add_instance(b.add_geometry(*box_mesh((e, 5, 5)), red), trs((5, 0, 0)))
+    b.add_instance(b.add_geometry(*box_mesh((1.5, e, 1.5)), light), trs((0, 4.9, 0)))
+    side = int(math.ceil(n_objects ** (1 / 3)))
+    k = 0
+    for ix in range(side):
+        for iy in range(side):
+            for iz in range(side):
+                if k >= n_objects:
+                    break
+                m = b.add_material(material(metallic=0.0, roughness=0.0, ior=1.5, transmission=1.0,
+                                            volume=(tuple(rng.uniform(0.5, 1.0, 3)), rng.uniform(0.5, 2.0))))
+                g = b.add_geometry(*uv_sphere(1.0, *sphere_res), m)
+                r = 3.6 / side
+                c = (np.array([ix, iy, iz]) + 0.5) / side * 8.0 - 4.0 + rng.uniform(-0.15, 0.15, 3)
+                b.add_instance(g, trs(c, scale=(r, r, r)))
+                k += 1
+    b.normalize()
+    return b.build()

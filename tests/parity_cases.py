@@ -167,3 +167,55 @@ def case_lucy_ids(api, n_rays=100000, rows=120, cols=121):
     hg, ho = sc.trace_closest(rays, 1), o.trace_closest(rays, 1)
     assert util.hits_equal(hg, ho).all()
     return d, o, ctx, sc
+
+
+def render_compare(api, d, o, W, H, gui_kw, frames, cam_pos=(0, 0, 14.0), opaque=None, tol_mre=MRE_TOL, tol_psnr=PSNR_TOL):
+    opaque = d.fully_opaque if opaque is None else opaque
+    ctx, sc = make(api, d, W, H)
+    cam = host.Camera(W, H).set(position=cam_pos); gui = host.Gui(**gui_kw)
+    d1, d2 = host.FrameDriver(cam, gui, opaque), host.FrameDriver(cam, gui, opaque)
+    acc = None
+    for _ in range(frames):
+        ctx.render(sc, d1.next_ubo()); acc, out, st = o.render(d2.next_ubo(), W, H, acc)
+    acc_g, out_g = ctx.readback()
+    total = d1.total.value
+    mre, ps = util.mean_rel_err(acc_g, acc, total), util.psnr(out_g[..., :3], out[..., :3])
+    assert mre < tol_mre and ps >= tol_psnr, (mre, ps)
+    return ctx, sc, st
+
+
+def case_foliage(api, n_side=6, tris=2000, size=64, n_rays=20000):
+    """Config-3 shape in miniature: instanced BLAS + alpha-MASK textured cards + sky + directional light."""
+    d = scenes.instanced_foliage(n_side=n_side, tris_per_mesh=tris, cards=16, tex_size=64, sky=scenes.procedural_sky(16))
+    o = orc.OracleScene(d)
+    ctx, sc = make(api, d, 16, 16)
+    rays, rng4 = util.random_rays(n_rays, seed=31, extent=4.0)
+    for flags in (0, 1):
+        assert util.hits_equal(sc.trace_closest(rays, flags, rng4), o.trace_closest(rays, flags, rng4)).all()
+    srays = rays.copy(); srays["tmin"] = 0.1; srays["tmax"] = 3.0
+    assert (sc.trace_any(srays, 0, rng4) == o.trace_any(srays, 0, rng4)).all()
+    assert not d.fully_opaque
+    render_compare(api, d, o, size, size, dict(number_of_samples=2, number_of_bounces=6, sky=1), 3, cam_pos=(0, 1.0, 6.0))
+
+
+def case_glass(api, n_objects=8, size=64, res=(16, 17)):
+    """Config-5 shape in miniature: transmission + volume attenuation + refraction."""
+    d = scenes.glass_box(n_objects=n_objects, sphere_res=res)
+    o = orc.OracleScene(d)
+    render_compare(api, d, o, size, size, dict(number_of_samples=2, number_of_bounces=8), 4)
+
+
+def case_skinned_character(api, n_tris=20000, joints=64, size=48, frames=3):
+    """Config-4 shape in miniature: per frame skinning kernel + BLAS refit + TLAS rebuild + render, accumulation off."""
+    d, pose = scenes.skinned_character(n_tris=n_tris, joints=joints)
+    o = orc.OracleScene(d)
+    ctx, sc = make(api, d, size, size)
+    cam = host.Camera(size, size).set(position=(0, 0, 9.0)); gui = host.Gui(number_of_samples=2, number_of_bounces=5, animation=1)
+    d1, d2 = host.FrameDriver(cam, gui, True), host.FrameDriver(cam, gui, True)
+    for f in range(1, frames + 1):
+        mats = pose(f * 7)
+        sc.update_skins(mats); o.update_skins(mats)
+        ctx.render(sc, d1.next_ubo()); acc, out, st = o.render(d2.next_ubo(), size, size, None)
+        acc_g, out_g = ctx.readback()
+        # vertices differ by rounding (FMA contraction in the skinning kernel) -> silhouettes may move by a pixel
+        assert util.mean_rel_err(acc_g, acc, 2) < 0.02 and util.psnr(out_g[..., :3], out[..., :3]) >= 35.0

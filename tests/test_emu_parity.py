@@ -31,3 +31,15 @@ def test_emu_skinning_refit_rebuild():
 
 def test_emu_lucy_ids():
     pc.case_lucy_ids(emu_api(), n_rays=20000, rows=60, cols=61)
+
+
+def test_emu_foliage_alpha_mask_sky():
+    pc.case_foliage(emu_api(), n_side=4, tris=800, size=40, n_rays=8000)
+
+
+def test_emu_glass_volume():
+    pc.case_glass(emu_api(), n_objects=6, size=40, res=(12, 13))
+
+
+def test_emu_skinned_character():
+    pc.case_skinned_character(emu_api(), n_tris=4000, joints=32, size=32, frames=2)

@@ -96,3 +96,18 @@ def test_errors_are_reported_not_swallowed(api, cornell_desc):
     bad.n_materials = 0
     with pytest.raises(core.RtError):
         core.Scene(ctx, bad)
+
+
+def test_foliage_instances_alpha_mask_sky(api):
+    """Config-3 shape: 400 instances of a 20k-triangle BLAS + alpha-MASK textured cards, sky, directional light."""
+    pc.case_foliage(api, n_side=20, tris=20000, size=128, n_rays=200000)
+
+
+def test_glass_volume_scene(api):
+    """Config-5 shape: 27 glass spheres with volume attenuation in a Cornell-type box."""
+    pc.case_glass(api, n_objects=27, size=128, res=(32, 33))
+
+
+def test_skinned_character_per_frame(api):
+    """Config-4 shape: skinning kernel + BLAS refit + TLAS rebuild + render every frame."""
+    pc.case_skinned_character(api, n_tris=200000, joints=256, size=96, frames=3)
