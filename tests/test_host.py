@@ -1,0 +1,165 @@
+"""Host layer (host/gltf_host.cpp): glTF import rules, scene normalisation, camera / UBO construction, animation."""
+import base64
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import util
+from rustracer_b200 import _ffi as F, host
+
+REF = Path("/root/reference/assets/models")
+
+
+def arr(ptr, n, ctype, dtype):
+    return np.frombuffer(util._arr(ptr, n, ctype), dtype)
+
+
+def write_gltf(tmp_path, with_ext=True):
+    """Tiny self-contained glTF: two triangles (u16 indices, u8-normalised colours), TRS node, material extensions."""
+    pos = np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [2, 2, 0]], np.float32)
+    col = np.array([[255, 0, 0, 255], [0, 255, 0, 255], [0, 0, 255, 255], [255, 255, 255, 128]], np.uint8)
+    idx = np.array([0, 1, 2, 2, 1, 3], np.uint16)
+    blob = pos.tobytes() + col.tobytes() + idx.tobytes()
+    ext = {"KHR_materials_ior": {"ior": 1.33}, "KHR_materials_transmission": {"transmissionFactor": 0.9},
+           "KHR_materials_volume": {"attenuationDistance": 2.5, "attenuationColor": [0.9, 0.8, 0.7], "thicknessFactor": 1.0}} if with_ext else {}
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+         "nodes": [{"mesh": 0, "translation": [1, 2, 3], "scale": [2, 2, 2], "rotation": [0, 0, 0.70710678, 0.70710678]}],
+         "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "COLOR_0": 1}, "indices": 2, "material": 0}]}],
+         "materials": [{"alphaMode": "MASK", "alphaCutoff": 0.3, "pbrMetallicRoughness": {"baseColorFactor": [0.5, 0.6, 0.7, 0.8], "metallicFactor": 0.25},
+                        "emissiveFactor": [0.1, 0.2, 0.3], "extensions": ext}],
+         "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3", "min": [0, 0, 0], "max": [2, 2, 0]},
+                       {"bufferView": 1, "componentType": 5121, "normalized": True, "count": 4, "type": "VEC4"},
+                       {"bufferView": 2, "componentType": 5123, "count": 6, "type": "SCALAR"}],
+         "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 48}, {"buffer": 0, "byteOffset": 48, "byteLength": 16}, {"buffer": 0, "byteOffset": 64, "byteLength": 12}],
+         "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    p = tmp_path / "tiny.gltf"
+    p.write_text(json.dumps(g))
+    return p
+
+
+def test_tiny_gltf_import_rules(tmp_path):
+    doc = host.load_file(write_gltf(tmp_path))
+    d = doc.scene_desc()
+    assert (d.n_vertices, d.n_indices, d.n_geometries, d.n_instances, d.n_materials) == (4, 6, 1, 1, 1)
+    v = arr(d.vertices, 4, F.rt_vertex, F.VERTEX_DTYPE)
+    np.testing.assert_allclose(v["color"][3], [1, 1, 1, 128 / 255], rtol=1e-6)            # normalised u8 colours
+    assert (v["skin_index"] == -1).all() and (v["tangent"][:, 0] == 1).all()                # defaults geometry.rs:195,246
+    np.testing.assert_allclose(v["normal"][:, :3], [[0, 0, 1]] * 4, atol=1e-6)               # create_geo_normal
+    assert list(arr(d.indices, 6, F.c_u32, np.uint32)) == [0, 1, 2, 2, 1, 3]                 # u16 -> u32
+    m = d.materials[0]
+    assert m.alpha_mode == 2 and abs(m.alpha_cutoff - 0.3) < 1e-6 and not doc.fully_opaque()
+    assert abs(m.ior - 1.33) < 1e-6 and m.transmission_exist == 1 and abs(m.transmission_factor - 0.9) < 1e-6
+    assert m.volume_exists == 1 and abs(m.attenuation_distance - 2.5) < 1e-6 and abs(m.attenuation_color[1] - 0.8) < 1e-6
+    assert m.base_color_texture.index == -1 and abs(m.metallic_factor - 0.25) < 1e-6 and abs(m.roughness_factor - 1.0) < 1e-6
+    assert d.geometries[0].opaque == 0
+    # default lights: 5 zero-intensity point lights + 1 zero-intensity directional (scene_graph.rs:69-79)
+    assert d.n_plights == 5 and d.n_dlights == 1 and all(d.plights[i].intensity == 0 for i in range(5))
+    # scene normalisation: only min/max corners are transformed; longest side -> 10, centred (aabb.rs:65-85)
+    inst = arr(d.instances, 1, F.rt_instance, F.INSTANCE_DTYPE)
+    M = inst["transform"][0].reshape(3, 4).astype(np.float64)
+    # node = T(1,2,3) R(90 deg about z) S(2): local corners (0,0,0),(2,2,0) -> world (1,2,3) and (-3,6,3)
+    lo, hi = np.array([-3, 2, 3.0]), np.array([1, 6, 3.0])
+    s = 10.0 / 4.0
+    expect = np.diag([s, s, s]) @ (np.array([[0, -2, 0], [2, 0, 0], [0, 0, 2.0]]))
+    np.testing.assert_allclose(M[:, :3], expect, atol=1e-5)
+    np.testing.assert_allclose(M[:, 3], s * (np.array([1, 2, 3.0]) - (lo + (hi - lo) / 2)), atol=1e-5)
+    assert inst["mask"][0] == 0xFF and inst["geo_id"][0] == 0
+
+
+def test_camera_and_ubo_match_reference_formulas():
+    cam = host.Camera(1920, 1080).set(position=(1, 2, 5), direction=(0.1, -0.2, -1))
+    V, P = cam.view_matrix().astype(np.float64), cam.projection_matrix().astype(np.float64)
+    f = np.array([0.1, -0.2, -1]); f /= np.linalg.norm(f)
+    s = np.cross(f, [0, 1, 0]); s /= np.linalg.norm(s); u = np.cross(s, f)
+    e = np.array([1, 2, 5.0])
+    np.testing.assert_allclose(V[:3, :3], np.stack([s, u, -f]), atol=1e-6)                  # look_at_rh
+    np.testing.assert_allclose(V[:3, 3], [-s @ e, -u @ e, f @ e], atol=1e-5)
+    t = np.tan(np.radians(60) / 2); a = 1920 / 1080; n, fa = 0.1, 10.0
+    GL = np.array([[1 / (a * t), 0, 0, 0], [0, 1 / t, 0, 0], [0, 0, (fa + n) / (n - fa), 2 * fa * n / (n - fa)], [0, 0, -1, 0]])
+    Cm = np.array([[1, 0, 0, 0], [0, -1, 0, 0], [0, 0, .5, .5], [0, 0, 0, 1.0]])                 # OPENGL_TO_VULKAN_RT camera.rs:116-118
+    np.testing.assert_allclose(P, Cm @ GL, atol=1e-6)
+    gui = host.Gui()
+    drv = host.FrameDriver(cam, gui, True)
+    u0 = drv.next_ubo()
+    assert (u0.number_of_samples, u0.total_number_of_samples, u0.number_of_bounces, u0.frame_count) == (3, 3, 5, 0)   # Gui::new defaults
+    assert u0.exposure == 5.0 and u0.random_seed == 3 and u0.has_sky == 0 and u0.antialiasing == 1 and u0.fully_opaque == 1
+    MVI = np.array(u0.model_view_inverse[:], np.float64).reshape(4, 4).T
+    np.testing.assert_allclose(MVI @ V, np.eye(4), atol=1e-5)
+    PI = np.array(u0.projection_inverse[:], np.float64).reshape(4, 4).T
+    np.testing.assert_allclose(PI @ P, np.eye(4), atol=1e-4)
+    u1 = drv.next_ubo()
+    assert (u1.total_number_of_samples, u1.frame_count) == (6, 1)
+    # sample budget: stops at max_number_of_samples; mapping != Render disables accumulation and forces 1 bounce
+    g2 = host.Gui(number_of_samples=4, max_number_of_samples=10)
+    d2 = host.FrameDriver(cam, g2, True)
+    assert [d2.next_ubo().number_of_samples for _ in range(4)] == [4, 4, 2, 0]
+    g3 = host.Gui(mapping=5); d3 = host.FrameDriver(cam, g3, True)
+    u = d3.next_ubo(); u = d3.next_ubo()
+    assert u.number_of_bounces == 1 and u.total_number_of_samples == u.number_of_samples
+
+
+def test_png_decoder_roundtrip():
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    lib = F.load_host()
+    for mode, ch in (("RGBA", 4), ("RGB", 3), ("L", 1), ("LA", 2)):
+        a = rng.integers(0, 256, (13, 17, ch), dtype=np.uint8)
+        im = Image.fromarray(a[..., 0] if ch == 1 else a, mode)
+        buf = io.BytesIO(); im.save(buf, "PNG")
+        raw = buf.getvalue()
+        out = F.c_u8p(); w, h = F.c_u32(), F.c_u32()
+        data = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        assert lib.gv_decode_png(data, len(raw), C.byref(out), C.byref(w), C.byref(h)) == 0, lib.gv_last_error()
+        px = np.ctypeslib.as_array(out, shape=(h.value, w.value, 4)).copy(); lib.gv_free(out)
+        assert (px == np.asarray(im.convert("RGBA"))).all(), mode
+
+
+def test_load_errors_are_reported(tmp_path):
+    with pytest.raises(host.HostError):
+        host.load_file(tmp_path / "missing.gltf")
+    (tmp_path / "bad.gltf").write_text("{ not json")
+    with pytest.raises(host.HostError):
+        host.load_file(tmp_path / "bad.gltf")
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference assets only exist in the build container")
+def test_bundled_cornell_box_matches_fixture(cornell_desc):
+    d = host.load_file(REF / "CornellBox/cornellBox.gltf").scene_desc()
+    assert (d.n_vertices, d.n_indices // 3, d.n_geometries, d.n_instances, d.n_materials) == (16808, 16720, 9, 10, 9)
+    for name, ct, dt in (("vertices", F.rt_vertex, F.VERTEX_DTYPE), ("instances", F.rt_instance, F.INSTANCE_DTYPE)):
+        a = arr(getattr(d, name), getattr(d, "n_" + name), ct, dt); b = arr(getattr(cornell_desc, name), getattr(cornell_desc, "n_" + name), ct, dt)
+        assert a.tobytes() == b.tobytes(), name
+    assert d.materials[7].alpha_mode == 3 and abs(d.materials[7].base_color[3] - 0.05) < 1e-6   # the BLEND sphere
+    assert abs(d.materials[8].ior - 1.76) < 1e-6 and d.materials[4].emissive_factor[0] == 1.0
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference assets only exist in the build container")
+def test_skinned_animated_glb_end_to_end():
+    """shadows.glb (CesiumMan): skin tagging, PNG texture, default-material fallback, spot light as point light,
+    animation sampling -> skin matrices; the emulated CUDA core must agree with the oracle after animating."""
+    from emu_lib import emu_api
+    from oracle import orc
+    from rustracer_b200 import core
+    doc = host.load_file(REF / "shadows.glb")
+    d = doc.scene_desc()
+    v = arr(d.vertices, d.n_vertices, F.rt_vertex, F.VERTEX_DTYPE)
+    assert (v["skin_index"] >= 0).sum() == 5697 and v["joints"].max() == 18 and d.n_skins == 1
+    assert d.n_images == 2 and d.images[1].width == 1024 and d.images[1].srgb == 1 and d.n_plights == 1 and d.plights[0].intensity == 20.0
+    assert not doc.static_scene() and doc.need_compute()
+    inst = doc.get_instances()
+    assert any(np.allclose(t.reshape(3, 4), np.eye(4)[:3]) for t in inst["transform"])           # skinned node -> identity instance
+    o = orc.OracleScene(d)
+    ctx = core.Context(64, 48, api=emu_api()); sc = core.Scene(ctx, d)
+    k0 = doc.get_skins().copy()
+    doc.animate(0.7)
+    k1 = doc.get_skins()
+    assert np.abs(k1 - k0).max() > 1e-3
+    o.update_skins(k1); sc.update_skins(k1)
+    np.testing.assert_allclose(sc.read_vertices()["position"], o.read_vertices(d.n_vertices)["position"], rtol=1e-6, atol=1e-6)
+    rays, _ = util.random_rays(3000, seed=2, extent=3.0)
+    a, b = sc.trace_closest(rays, 1), o.trace_closest(rays, 1)
+    assert util.hits_equal(a, b).all()
