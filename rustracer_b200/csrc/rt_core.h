@@ -336,6 +336,8 @@ static int build_tlas(rt_scene* s) {
     uint32_t* tp = s->d_tlas_prims;
     rt_launch(ne, st, RT_LAMBDA(size_t k) { tp[k] = recd[tp[k]]; });   // TLAS leaf -> instance record index
     s->tlas_nodes = info.n_nodes; s->tlas_depth = info.depth;
+    s->ds.single_merged = (ne == 1 && s->merged.n_tris) ? 1u : 0u;
+    s->ds.merged_node_off = s->merged.node_off; s->ds.merged_tri_off = s->merged.tri_off;
     uint32_t bd = s->merged.depth;
     for (auto& g : s->geo) if (g.needed && g.depth > bd) bd = g.depth;
     s->blas_depth = bd;

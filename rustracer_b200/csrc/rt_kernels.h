@@ -314,7 +314,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
                 if (!active && outstanding == 0u) {
                     idx = base + (uint32_t)__popc(need & lt_mask);
-                    if (idx < count) { load_ray(idx, tv); active = true; }
+                    if (idx < count) { load_ray(idx, tv); active = true; if (tv.blas_sp >= 0) coop_publish_ray<ALPHA>(tv, sh, lane); }
                 }
                 if (base + (uint32_t)__popc(need) >= count) exhausted = true;
             }
@@ -384,6 +384,11 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                 coop_round<MODE, ALPHA, COUNT>(tv, S, sh, q_head, n, lane, outstanding, active, terminated, c4);
                 if (MODE == RT_MODE_ANY && terminated && active) { trav_finish(tv); store_hit(idx, tv); active = false; }
                 q_head += n; q_count -= n;
+            }
+            // a lane that only waited for its last triangles can retire now instead of spending another iteration
+            if (want_flush && active && outstanding == 0u && tv.sp == 0 && tv.ngroup.y <= 0x00FFFFFFu && tv.tgroup.y == 0u &&
+                (tv.blas_sp <= 0)) {
+                trav_finish(tv); store_hit(idx, tv); active = false;
             }
             holding = __ballot_sync(0xFFFFFFFFu, active);
         } while (holding && (exhausted || __popc(holding) >= RT_REFILL_BELOW));

@@ -41,6 +41,8 @@ struct DScene {
     const float4* inst_w2o;        // RT_INST_F4 float4 per instance
     const float4* inst_o2w;        // 3 float4 per instance: object->world rows
     uint32_t n_instances;
+    // when the TLAS holds nothing but the merged world-space BLAS, rays start inside it (no TLAS visit, no instance entry)
+    uint32_t single_merged, merged_node_off, merged_tri_off;
     // shading inputs in the reference's layouts
     const rt_vertex* vertices;     // skinned output (AnimationCompute.comp) == BLAS build input
     const uint32_t* indices;

@@ -145,6 +145,12 @@ RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tm
     t.nodes = S.tlas_nodes; t.tri_off = 0; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false; t.merged = false; t.identity = false;
     t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u); t.sp = 0;
     t.hit.t = tmax; t.hit.u = 0.0f; t.hit.v = 0.0f; t.hit.inst = 0xFFFFFFFFu; t.hit.prim = 0xFFFFFFFFu; t.found = false;
+    if (S.single_merged) {
+        // the whole scene is the merged world-space BLAS: start inside it
+        t.nodes = S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4; t.tri_off = S.merged_tri_off;
+        t.blas_sp = 0; t.identity = true; t.merged = true; t.cur_inst = S.n_instances;
+        t.sh = shear_init(dw);
+    }
 }
 
 // BLAS exhausted: back to world space (nothing to recompute after an identity instance)
