@@ -442,8 +442,11 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) shado
         });
 }
 
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 4
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128, 4) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
+__global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
                                                     const uint32_t* count_ptr, uint32_t* out_count, uint32_t* shadow_count, uint32_t bounce, RtCounters* cnt) {
     const uint32_t count = *count_ptr;
     const uint32_t lane = threadIdx.x & 31u;

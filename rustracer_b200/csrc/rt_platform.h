@@ -22,6 +22,7 @@
 using std::min; using std::max;
 #define RT_HD inline
 #define RT_D inline
+#define RT_D_COLD inline
 #define RT_LAMBDA [=]
 #define RT_RESTRICT
 typedef void* rt_stream_t;
@@ -92,6 +93,7 @@ inline float rt_timer_ms(rt_timer&, rt_timer&) { return 0.0f; }
 #include <cuda_runtime.h>
 #define RT_HD __host__ __device__ __forceinline__
 #define RT_D __device__ __forceinline__
+#define RT_D_COLD __device__ __noinline__   // rarely executed helpers kept out of line: smaller hot path, fewer registers
 #define RT_LAMBDA [=] __device__
 #define RT_RESTRICT __restrict__
 typedef cudaStream_t rt_stream_t;
