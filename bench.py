@@ -29,6 +29,28 @@ sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 
 WIDTH, HEIGHT, BOUNCES, SPP = 1920, 1080, 8, 1
+CONFIG = 2          # BASELINE.json configs[1] is the headline workload; --config selects the others (extra, not the driver's line)
+POSE = None         # config 4: per-frame skin matrices
+GUI_KW = {}
+CAM_POS = (0, 0, 14.0)
+NAMES = {1: "procedural Cornell box (configs[0]) 512x512, 1 spp/frame, max depth 8",
+         2: "Lucy-in-Cornell stand-in (BASELINE configs[1]) 1920x1080, 1 spp/frame accumulated, max depth 8",
+         3: "10k instances of a 100k-triangle BLAS + alpha-MASK foliage cards (configs[2]) 1920x1080, sky + directional light, max depth 8",
+         4: "skinned ~1M-triangle character, 256 joints (configs[3]): per frame skinning + BLAS refit + TLAS + 1 spp render 1920x1080",
+         5: "64 glass/volume objects in a Cornell-type box (configs[4]) 3840x2160, 1 spp/frame, max depth 8"}
+
+
+def select_config(c: int):
+    global WIDTH, HEIGHT, CONFIG, GUI_KW, CAM_POS
+    CONFIG = c
+    if c == 1:
+        WIDTH, HEIGHT = 512, 512
+    elif c == 3:
+        GUI_KW = {"sky": 1}; CAM_POS = (0, 1.2, 7.0)
+    elif c == 4:
+        GUI_KW = {"animation": 1}; CAM_POS = (0, 0, 9.0)
+    elif c == 5:
+        WIDTH, HEIGHT = 3840, 2160
 
 
 def measured_peak():
@@ -85,7 +107,17 @@ class ClockSampler:
 
 
 def build_scene_desc():
+    global POSE
     from rustracer_b200 import scenes
+    if CONFIG == 1:
+        return scenes.cornell_box(lucy=False)
+    if CONFIG == 3:
+        return scenes.instanced_foliage(n_side=100, tris_per_mesh=100_000, cards=64, tex_size=1024, sky=scenes.procedural_sky(256))
+    if CONFIG == 4:
+        d, POSE = scenes.skinned_character(n_tris=1_000_000, joints=256)
+        return d
+    if CONFIG == 5:
+        return scenes.glass_box(n_objects=64)
     return scenes.cornell_box(lucy=True)
 
 
@@ -119,8 +151,8 @@ def cpu_sample(desc, frames: int, rows, warm: int = 0):
     from oracle import orc
     from rustracer_b200 import host
     s = orc.OracleScene(desc)
-    cam = host.Camera(WIDTH, HEIGHT).set(position=(0, 0, 14.0))
-    gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES)
+    cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS)
+    gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES, **GUI_KW)
     acc = np.zeros((HEIGHT, WIDTH, 4), np.float32)
     rays, secs = 0, 0.0
     for f in range(warm + frames):
@@ -141,12 +173,12 @@ def run_reference(args):
     desc = build_scene_desc()
     cores = orc.lib().orc_num_threads() if hasattr(orc.lib(), "orc_num_threads") else os.cpu_count()
     # calibrate a row band so that one step takes ~1 s
-    m, rays, secs = cpu_sample(desc, 1, (520, 560))
+    m, rays, secs = cpu_sample(desc, 1, (HEIGHT // 2 - 20, HEIGHT // 2 + 20))
     band = int(max(8, min(HEIGHT, 40 * (1.0 / max(secs, 1e-3)))))
     r0 = (HEIGHT - band) // 2
     from rustracer_b200 import host
     s = orc.OracleScene(desc)
-    cam = host.Camera(WIDTH, HEIGHT).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES)
+    cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS); gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES, **GUI_KW)
     acc = np.zeros((HEIGHT, WIDTH, 4), np.float32)
     total_rays, t_total, samples = 0, 0.0, 0
     for f in range(args.warmup + args.steps):
@@ -155,7 +187,7 @@ def run_reference(args):
         if f >= args.warmup:
             total_rays += st.rays_extend + st.rays_shadow; t_total += dt; samples += st.pixel_samples
     v = total_rays / t_total / 1e6
-    sample = f"rows {r0}..{r0 + band} of each 1920x1080 frame, {args.steps} frames x 1 spp, depth 8, all host threads"
+    sample = f"rows {r0}..{r0 + band} of each {WIDTH}x{HEIGHT} frame, {args.steps} frames x 1 spp, depth 8, all host threads"
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(desc) | {"note": "reference cannot be built/run here (Rust+Vulkan RT, no toolchain): CPU oracle port stands in (BASELINE.md §3)"},
@@ -166,7 +198,7 @@ def run_reference(args):
 
 
 def workload_config(desc):
-    return {"workload": "Lucy-in-Cornell stand-in (BASELINE configs[1]) 1920x1080, 1 spp/frame accumulated, max depth 8",
+    return {"workload": NAMES[CONFIG],
             "triangles": int(desc.n_indices // 3), "instances": int(desc.n_instances), "width": WIDTH, "height": HEIGHT, "spp_per_step": SPP, "max_depth": BOUNCES,
             "l2": "per-frame path-state/hit streams (~480 MB at 1080p) exceed the 126 MB L2; the ~28 MB BVH is L2-resident by design (SURVEY.md App. G)"}
 
@@ -198,8 +230,8 @@ def run_ours(args):
     ctx = core.Context(WIDTH, HEIGHT, device=local)
     t0 = time.perf_counter(); scene = core.Scene(ctx, desc); build_s = time.perf_counter() - t0
     info = scene.bvh_info()
-    cam = host.Camera(WIDTH, HEIGHT).set(position=(0, 0, 14.0))
-    gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES)
+    cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS)
+    gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES, **GUI_KW)
     K, Wm = args.steps, args.warmup
     # sample-pass sharding (§8e B): global frame g = step * world + rank; every rank starts from a zero accumulation
     from rustracer_b200 import sharding
@@ -227,8 +259,13 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def pre_step(s):
+        if POSE is not None:      # config 4: skinning kernel + BLAS refit + TLAS rebuild belong to the step
+            scene.update_skins(POSE(s))
+
     def frames(lo, hi, flags=0):
         for s in range(lo, hi):
+            pre_step(s)
             ctx.render(scene, ubos[s], flags=flags, stream=stream)
 
     def combine():
@@ -244,6 +281,7 @@ def run_ours(args):
     per = []
     e0.record()
     for s in range(Wm, Wm + K):
+        pre_step(s)
         ctx.render(scene, ubos[s], flags=4, stream=stream)   # 4 = per-stage CUDA events on the launching stream
         if args.per_step_stats:
             per.append(ctx.stats())
@@ -267,6 +305,7 @@ def run_ours(args):
     tot = dict.fromkeys(("rays_extend", "rays_shadow", "shaded_hits", "pixel_samples", "nodes", "tris", "insts", "anyhits"), 0)
     ext_ms, launches, n_ext = 0.0, 0, 0
     for s in range(Wm, Wm + K):
+        pre_step(s)
         ctx.render(scene, ubos[s], flags=1 | 4, stream=stream)
         st = ctx.stats()
         for k, v in stats_dict(st).items():
@@ -277,6 +316,7 @@ def run_ours(args):
     frames(0, Wm)
     stage = dict(raygen=0.0, extend=0.0, shade=0.0, shadow=0.0, accum=0.0)
     for s in range(Wm, Wm + K):
+        pre_step(s)
         ctx.render(scene, ubos[s], flags=4, stream=stream)
         st = ctx.stats()
         stage["raygen"] += st.ms_raygen; stage["extend"] += st.ms_extend; stage["shade"] += st.ms_shade; stage["shadow"] += st.ms_shadow; stage["accum"] += st.ms_accum
@@ -293,12 +333,13 @@ def run_ours(args):
     out_np = pinned.numpy()
     ctx.resize(WIDTH, HEIGHT)
     for s in range(0, Wm):
-        ctx.render(scene, ubos[s], stream=stream); ctx.readback(want_acc=False, out_buf=out_np)
+        pre_step(s); ctx.render(scene, ubos[s], stream=stream); ctx.readback(want_acc=False, out_buf=out_np)
     barrier()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for s in range(Wm, Wm + K):
+        pre_step(s)                                        # config 4: 256 mat4 (16 KB) host -> device per step
         ctx.render(scene, ubos[s], stream=stream)
         torch.cuda.current_stream().synchronize()
         ctx.readback(want_acc=False, out_buf=out_np)       # device -> pinned host, 4 B/pixel
@@ -337,7 +378,7 @@ def run_ours(args):
                 if nfr > 1:
                     m, rays, secs = cpu_sample(desc, nfr, (0, HEIGHT), warm=0)
                 cpu = {"value": m, "unit": "Mrays/s", "cores": int(orc.lib().orc_num_threads()), "kind": "port",
-                       "sample": f"{nfr} full 1920x1080 frames x 1 spp, depth 8 ({rays} rays, {secs:.1f} s), oracle/oracle.cpp, OpenMP all host threads"}
+                       "sample": f"{nfr} full {WIDTH}x{HEIGHT} frames x 1 spp, depth 8 ({rays} rays, {secs:.1f} s), oracle/oracle.cpp, OpenMP all host threads"}
             except Exception as ex:   # the oracle is test infrastructure; its absence must not break the GPU arm
                 cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
@@ -345,7 +386,8 @@ def run_ours(args):
                 "config": workload_config(desc) | {"parallelism": f"sample-pass sharding x{world} (frames g = step*{world}+rank), fused peer-memory reduce+tonemap at the end",
                                                    "bvh": {"nodes": int(info.blas_nodes), "depth": int(info.max_depth_blas), "bytes": int(info.bytes), "build_s": build_s}},
                 "samples_per_s": samples_all / (ms_max * 1e-3),
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 324, "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 324 + (16384 if POSE is not None else 0), "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
+                "refit": ({"skin_ms": scene.bvh_info().skin_ms, "refit_ms": scene.bvh_info().refit_ms, "tlas_ms": scene.bvh_info().tlas_ms} if POSE is not None else None),
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "rays_per_step": rays_rank / K}
@@ -363,7 +405,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-step-stats", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (default 2 = the headline workload)")
     args = ap.parse_args()
+    select_config(args.config)
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
         run_reference(args)

@@ -1358,6 +1358,8 @@ int orc_trace_any(orc_scene* s, const rt_ray* rays, uint32_t n, uint32_t flags, 
 // one frame (RayTracing.rgen over W x H).  rows [row0,row1) only when row1 > row0 (bounded CPU-baseline samples).
 int orc_render(orc_scene* s, const rt_ubo* ubo, uint32_t W, uint32_t H, float* acc, uint8_t* out, uint32_t row0, uint32_t row1, rt_stats* stats) {
     if (row1 <= row0) { row0 = 0; row1 = H; }
+    if (row1 > H) row1 = H;
+    if (row0 > row1) row0 = row1;
     if (ubo->total_number_of_samples == 0) return fail("total_number_of_samples must be > 0");
     s->rays_extend = 0; s->rays_shadow = 0; s->shaded = 0;
     auto t0 = std::chrono::steady_clock::now();

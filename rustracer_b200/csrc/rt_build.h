@@ -229,6 +229,50 @@ RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, c
 
 struct WideBvhInfo { uint32_t n_nodes = 0, n_prims = 0, depth = 0; };
 
+#ifdef RT_EMU
+#include <functional>
+// EXPERIMENT (emulation only, RT_EMU_SAH=1): binned-SAH top-down build into the LBVH's binary-tree arrays.
+inline void emu_sah_binary_build(const DAabb* boxes, int n, uint32_t* vals, int2* children, uint32_t* parent, uint2* range, DAabb* bin_box) {
+    std::vector<uint32_t> order(n);
+    for (int i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    int next_internal = 0;
+    auto grow = [&](DAabb& a, const DAabb& b) { for (int k = 0; k < 3; ++k) { a.lo[k] = fminf(a.lo[k], b.lo[k]); a.hi[k] = fmaxf(a.hi[k], b.hi[k]); } };
+    auto empty = []() { DAabb b; for (int k = 0; k < 3; ++k) { b.lo[k] = 3e38f; b.hi[k] = -3e38f; } return b; };
+    std::function<uint32_t(int, int, uint32_t)> rec = [&](int first, int count, uint32_t par) -> uint32_t {
+        if (count == 1) { const uint32_t id = (uint32_t)(n - 1 + first); bin_box[id] = boxes[order[first]]; parent[id] = par; return id; }
+        const uint32_t id = (uint32_t)next_internal++;
+        parent[id] = par;
+        DAabb cb = empty(), nb = empty();
+        for (int i = 0; i < count; ++i) { const DAabb& b = boxes[order[first + i]]; grow(nb, b); DAabb c; for (int k = 0; k < 3; ++k) c.lo[k] = c.hi[k] = 0.5f * (b.lo[k] + b.hi[k]); grow(cb, c); }
+        const int NB = 16; int bestAxis = -1, bestSplit = 0; float bestCost = 3e38f;
+        for (int ax = 0; ax < 3; ++ax) {
+            const float lo = cb.lo[ax], hi = cb.hi[ax]; if (!(hi > lo)) continue;
+            DAabb bb[NB]; int bc[NB]; for (int b = 0; b < NB; ++b) { bb[b] = empty(); bc[b] = 0; }
+            const float scale = NB / (hi - lo);
+            for (int i = 0; i < count; ++i) { const DAabb& b = boxes[order[first + i]]; int k = std::min(NB - 1, (int)((0.5f * (b.lo[ax] + b.hi[ax]) - lo) * scale)); grow(bb[k], b); bc[k]++; }
+            float la[NB], ra[NB]; int lc[NB], rc[NB]; DAabb l = empty(), r = empty(); int ls = 0, rs = 0;
+            for (int i = 0; i < NB - 1; ++i) { ls += bc[i]; if (bc[i]) grow(l, bb[i]); lc[i] = ls; la[i] = ls ? aabb_half_area(l) : 0.f;
+                                               rs += bc[NB - 1 - i]; if (bc[NB - 1 - i]) grow(r, bb[NB - 1 - i]); rc[NB - 2 - i] = rs; ra[NB - 2 - i] = rs ? aabb_half_area(r) : 0.f; }
+            for (int i = 0; i < NB - 1; ++i) { if (!lc[i] || !rc[i]) continue; const float c = lc[i] * la[i] + rc[i] * ra[i]; if (c < bestCost) { bestCost = c; bestAxis = ax; bestSplit = i; } }
+        }
+        int mid;
+        if (bestAxis < 0) mid = first + count / 2;
+        else {
+            const float lo = cb.lo[bestAxis], scale = NB / (cb.hi[bestAxis] - lo);
+            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
+                const DAabb& b = boxes[p]; return std::min(NB - 1, (int)((0.5f * (b.lo[bestAxis] + b.hi[bestAxis]) - lo) * scale)) <= bestSplit; });
+            mid = (int)(it - order.begin());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        }
+        const uint32_t l = rec(first, mid - first, id), r = rec(mid, first + count - mid, id);
+        children[id] = make_int2((int)l, (int)r); range[id] = make_uint2((uint32_t)first, (uint32_t)(first + count - 1)); bin_box[id] = nb;
+        return id;
+    };
+    rec(0, n, 0xFFFFFFFFu);
+    for (int i = 0; i < n; ++i) vals[i] = order[i];
+}
+#endif
+
 // Builds an 8-wide BVH over n primitive boxes (device pointer).  Synchronises the stream once per tree level.
 inline int build_wide_bvh(const DAabb* prim_boxes, uint32_t n, BuildScratch& sc, WideOut out, rt_stream_t stream, WideBvhInfo* info) {
     info->n_nodes = 0; info->n_prims = n; info->depth = 0;
@@ -272,6 +316,13 @@ inline int build_wide_bvh(const DAabb* prim_boxes, uint32_t n, BuildScratch& sc,
     int2* bin_children = sc.bin_children; uint32_t* bin_parent = sc.bin_parent; uint2* bin_range = sc.bin_range;
     DAabb* bin_box = sc.bin_box; uint32_t* flags = sc.flags;
     const int ni = (int)n;
+#ifdef RT_EMU
+    if (n > 1 && getenv("RT_EMU_SAH")) {
+        // EXPERIMENT (emulation only): top-down binned-SAH binary tree instead of the LBVH, to measure how much
+        // traversal work a higher-quality builder would save.  Not part of the product.
+        emu_sah_binary_build(prim_boxes, ni, vals, bin_children, bin_parent, bin_range, bin_box);
+    } else
+#endif
     if (n > 1) {
         rt_memset(flags, 0, (size_t)(n - 1) * 4, stream);
         rt_launch(n - 1, stream, RT_LAMBDA(size_t i) { lbvh_build_node(keys, ni, (int)i, bin_children, bin_parent, bin_range); });
