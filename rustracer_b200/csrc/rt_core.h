@@ -108,6 +108,7 @@ struct rt_scene {
     BuildScratch scratch;
     DScene ds{};
     bool has_nee = false;
+    bool plain_materials = false;            // no texture reference and no specular-glossiness material anywhere
     float build_ms = 0, refit_ms = 0, skin_ms = 0, tlas_ms = 0;
 };
 
@@ -415,13 +416,13 @@ static void launch_shadow(rt_context* c, const DScene& S, const FrameParams& P, 
     ++g_rt_launch_count;
 #endif
 }
-template <bool COUNT>
+template <bool SIMPLE, bool COUNT>
 static void launch_shade(rt_context* c, const DScene& S, const FrameParams& P, const DQueue& qin, const DQueue& qout, const uint32_t* count, uint32_t* out_count,
                          uint32_t* shadow_count, uint32_t bounce, rt_stream_t st) {
 #ifdef RT_EMU
     const uint32_t n = *count;
     for (uint32_t i = 0; i < n; ++i) {
-        ShadeResult r = shade_item<COUNT>(S, P, c->fb, qin, c->hits, i, bounce, c->dev_cnt);
+        ShadeResult r = shade_item<SIMPLE, COUNT>(S, P, c->fb, qin, c->hits, i, bounce, c->dev_cnt);
         if (r.alive) store_path(qout, (*out_count)++, r.next);
         if (r.has_shadow) {
             const uint32_t k = (*shadow_count)++;
@@ -432,7 +433,7 @@ static void launch_shade(rt_context* c, const DScene& S, const FrameParams& P, c
     }
     (void)st;
 #else
-    shade_kernel<COUNT><<<persistent_grid(8), 128, 0, st>>>(S, P, c->fb, qin, c->hits, qout, c->sq, count, out_count, shadow_count, bounce, c->dev_cnt);
+    shade_kernel<SIMPLE, COUNT><<<persistent_grid(8), 128, 0, st>>>(S, P, c->fb, qin, c->hits, qout, c->sq, count, out_count, shadow_count, bounce, c->dev_cnt);
     ++g_rt_launch_count;
 #endif
 }
@@ -453,6 +454,7 @@ static int render_frame(rt_context* c, rt_scene* s, const FrameParams& P0, const
     if (COUNT) rt_memset(c->dev_cnt, 0, sizeof(RtCounters), st);
     const bool timing = (flags & 4u) != 0;
     c->stage_used = 0;
+    const bool simple = s->plain_materials && P.ubo.mapping == RT_MAP_RENDER && P.ubo.debug == 0u;
     const FrameBuffers fb = c->fb; const DScene DS = s->ds;
     for (uint32_t smp = 0; smp < S; ++smp) {
         P.sample = smp;
@@ -470,7 +472,8 @@ static int render_frame(rt_context* c, rt_scene* s, const FrameParams& P0, const
             launch_extend<ALPHA, COUNT>(c, DS, P, qin, qcount + idx, fetch_e + idx, n_local, st);
             stage_end(ev, st);
             ev = stage_begin(c, timing, 2, st);
-            launch_shade<COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, b, st);
+            if (simple) launch_shade<true, COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, b, st);
+            else launch_shade<false, COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, b, st);
             stage_end(ev, st);
             if (s->has_nee) {
                 ev = stage_begin(c, timing, 3, st);
@@ -620,6 +623,14 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
     e |= dev_upload(&s->d_images, dimg.data(), dimg.size(), st); e |= dev_upload(&s->d_textures, dtex.data(), dtex.size(), st); e |= dev_upload(&s->d_lut, lut, 256, st);
     if (e) return bail("rt_scene_create: texture table upload failed");
     s->ds.n_textures = d->n_textures;
+    s->plain_materials = true;
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const rt_material& mt = d->materials[m];
+        const rt_texture_info* tis[] = {&mt.base_color_texture, &mt.metallic_roughness_texture, &mt.normal_texture, &mt.emissive_texture, &mt.transmission_texture,
+                                         &mt.specular_texture, &mt.specular_color_texture, &mt.sg_diffuse_texture, &mt.sg_specular_glossiness_texture};
+        for (const rt_texture_info* ti : tis) if (ti->index >= 0) s->plain_materials = false;
+        if (mt.workflow == 1u) s->plain_materials = false;
+    }
     if (d->skybox_faces[0] && d->skybox_width && upload_sky(s, d->skybox_faces, d->skybox_width, d->skybox_height, d->skybox_srgb)) return bail(g_err);
 
     // ---- geometry records, baking classification and BVH storage ----

@@ -67,7 +67,7 @@ RT_D void extend_item(const DScene& S, const FrameParams& P, const DQueue& q, co
 // returns true when the path continues; slot allocation is done by the caller (warp-aggregated on the GPU)
 struct ShadeResult { bool alive; PathState next; bool has_shadow; ShadowRay shadow; };
 
-template <bool COUNT>
+template <bool SIMPLE, bool COUNT>
 RT_D ShadeResult shade_item(const DScene& S, const FrameParams& P, const FrameBuffers& fb, const DQueue& q, const DHits& hits,
                             uint32_t i, uint32_t bounce, RtCounters* cnt) {
     PathState st = load_path(q, i);
@@ -75,7 +75,7 @@ RT_D ShadeResult shade_item(const DScene& S, const FrameParams& P, const FrameBu
     RtHit h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.prim = rt_float_as_uint(hv.w); h.inst = hits.inst[i];
     ShadeOut so;
     if (h.t < 0.0f) shade_miss(S, P, st.dir, bounce == 0, so, cnt);
-    else shade_hit(S, P, h, st, so, cnt);
+    else shade_hit<SIMPLE>(S, P, h, st, so, cnt);
 
     ShadeResult r; r.alive = false; r.has_shadow = so.has_shadow;
     if (so.has_shadow) { r.shadow = so.shadow; r.shadow.contrib = so.shadow.contrib * st.throughput; }
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) shado
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 4
 #endif
-template <bool COUNT>
+template <bool SIMPLE, bool COUNT>
 __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
                                                     const uint32_t* count_ptr, uint32_t* out_count, uint32_t* shadow_count, uint32_t bounce, RtCounters* cnt) {
     const uint32_t count = *count_ptr;
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
         const uint32_t i = base + lane;
         ShadeResult r; r.alive = false; r.has_shadow = false;
-        if (i < count) r = shade_item<COUNT>(S, P, fb, qin, hits, i, bounce, cnt);
+        if (i < count) r = shade_item<SIMPLE, COUNT>(S, P, fb, qin, hits, i, bounce, cnt);
         const uint32_t alive_mask = __ballot_sync(0xFFFFFFFFu, r.alive);
         if (alive_mask) {
             uint32_t slot0 = 0;

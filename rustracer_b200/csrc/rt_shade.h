@@ -254,6 +254,10 @@ RT_D void shade_miss(const DScene& S, const FrameParams& P, f3 world_dir, bool p
 }
 
 // RayTracing.rchit:136-477.  `st` carries the payload fields that survive the stage (rng, volume_dis, lens seed).
+// SIMPLE: the scene has no textures and no specular-glossiness material and the frame uses mapping == RENDER with
+// debug == 0 (checked on the host per frame) — the same kind of specialisation as the reference's any-hit-free pipeline
+// for fully opaque scenes (pipeline_res.rs:155-166).  It removes the texture / debug code from the hot kernel.
+template <bool SIMPLE>
 RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, PathState& st, ShadeOut& o, RtCounters* cnt) {
     const rt_ubo& ubo = P.ubo;
     const float4* wp = S.inst_w2o + (size_t)hit.inst * RT_INST_F4;
@@ -279,9 +283,9 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     f3 origin = mk3(m0.x * pos.x + m0.y * pos.y + m0.z * pos.z + m0.w, m1.x * pos.x + m1.y * pos.y + m1.z * pos.z + m1.w, m2.x * pos.x + m2.y * pos.y + m2.z * pos.z + m2.w);
 
     f4 color4 = vcolor * ld_f4(mat.base_color);
-    if (mat.base_color_texture.index >= 0) color4 *= texture2d(S, mat.base_color_texture.index, get_uv(uv, mat.base_color_texture.coord));
+    if (!SIMPLE && mat.base_color_texture.index >= 0) color4 *= texture2d(S, mat.base_color_texture.index, get_uv(uv, mat.base_color_texture.coord));
     f3 color = xyz(color4);
-    if (mat.normal_texture.index >= 0) {
+    if (!SIMPLE && mat.normal_texture.index >= 0) {
         const f3 nt = normalize(xyz(texture2d(S, mat.normal_texture.index, get_uv(uv, mat.normal_texture.coord))) * 2.0f - 1.0f);
         const f3 tm = xyz(tangent);                                         // getNormal :124-129
         const f3 tg = normalize(tm - dot(tm, normal) * normal);
@@ -297,14 +301,14 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     const f3 N = dot(geo_normal, normal) < 0.0f ? -normal : normal;
 
     f3 emissive = mk3(mat.emissive_factor[0], mat.emissive_factor[1], mat.emissive_factor[2]);
-    if (mat.emissive_texture.index >= 0) emissive *= xyz(texture2d(S, mat.emissive_texture.index, get_uv(uv, mat.emissive_texture.coord)));
+    if (!SIMPLE && mat.emissive_texture.index >= 0) emissive *= xyz(texture2d(S, mat.emissive_texture.index, get_uv(uv, mat.emissive_texture.coord)));
     float metallic = mat.metallic_factor, roughness = mat.roughness_factor;
-    if (mat.metallic_roughness_texture.index >= 0) {
+    if (!SIMPLE && mat.metallic_roughness_texture.index >= 0) {
         const f4 mr = texture2d(S, mat.metallic_roughness_texture.index, get_uv(uv, mat.metallic_roughness_texture.coord));
         roughness *= mr.y; metallic *= mr.z;
     }
     f3 spec_wf = mk3(1.0f);
-    const bool sg = mat.workflow == 1u;
+    const bool sg = !SIMPLE && mat.workflow == 1u;
     if (sg) {
         f4 diffuse_factor = ld_f4(mat.sg_diffuse_factor), sgf = ld_f4(mat.sg_specular_glossiness_factor);
         if (mat.sg_diffuse_texture.index >= 0) diffuse_factor *= texture2d(S, mat.sg_diffuse_texture.index, get_uv(uv, mat.sg_diffuse_texture.coord));
@@ -317,12 +321,12 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     float transmission = 0.0f;
     if (mat.transmission_exist) {
         transmission = mat.transmission_factor;
-        if (mat.transmission_texture.index >= 0) transmission *= texture2d(S, mat.transmission_texture.index, get_uv(uv, mat.transmission_texture.coord)).x;
+        if (!SIMPLE && mat.transmission_texture.index >= 0) transmission *= texture2d(S, mat.transmission_texture.index, get_uv(uv, mat.transmission_texture.coord)).x;
     }
 
     o.t = hit.t; o.need_scatter = false; o.has_shadow = false; o.hit_value = mk3(0.0f);
     o.next_origin = pos; o.next_dir = mk3(0.0f);
-    uint32_t mapping = ubo.mapping;
+    uint32_t mapping = SIMPLE ? (uint32_t)RT_MAP_RENDER : ubo.mapping;
     if (mat.unlit) mapping = RT_MAP_ALBEDO;
     switch (mapping) {   // :258-286 debug channels return through Ray.emittance
         case RT_MAP_ALBEDO: o.emittance = color; return;
@@ -340,8 +344,8 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
 
     float spec_factor = mat.specular_factor;
     f3 spec_color = mk3(mat.specular_color_factor[0], mat.specular_color_factor[1], mat.specular_color_factor[2]);
-    if (mat.specular_texture.index >= 0) spec_factor *= texture2d(S, mat.specular_texture.index, get_uv(uv, mat.specular_texture.coord)).w;
-    if (mat.specular_color_texture.index >= 0) spec_color *= xyz(texture2d(S, mat.specular_color_texture.index, get_uv(uv, mat.specular_color_texture.coord)));
+    if (!SIMPLE && mat.specular_texture.index >= 0) spec_factor *= texture2d(S, mat.specular_texture.index, get_uv(uv, mat.specular_texture.coord)).w;
+    if (!SIMPLE && mat.specular_color_texture.index >= 0) spec_color *= xyz(texture2d(S, mat.specular_color_texture.index, get_uv(uv, mat.specular_color_texture.coord)));
 
     o.emittance = emissive * ubo.exposure;
     Surface m;
@@ -412,7 +416,7 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     thr *= weight;
     o.next_origin = origin; o.next_dir = ndir; o.hit_value = thr;
 
-    if (ubo.debug == 1u) {   // :437-474 legacy path on the LCG stream
+    if (!SIMPLE && ubo.debug == 1u) {   // :437-474 legacy path on the LCG stream
         uint32_t seed = st.lens_seed;
         const f3 wd = st.dir;
         if (m.transmission > 0.0f) {
