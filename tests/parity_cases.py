@@ -219,3 +219,35 @@ def case_skinned_character(api, n_tris=20000, joints=64, size=48, frames=3):
         acc_g, out_g = ctx.readback()
         # vertices differ by rounding (FMA contraction in the skinning kernel) -> silhouettes may move by a pixel
         assert util.mean_rel_err(acc_g, acc, 2) < 0.02 and util.psnr(out_g[..., :3], out[..., :3]) >= 35.0
+
+
+def case_frame_options(api, cornell_desc, cornell_oracle, size=48):
+    """UBO variants of RayTracing.rgen / Tonemapping.glsl / rchit debug path: thin lens (LCG stream), orthographic
+    camera, every tone-map mode, DISTANCE and HEAT mappings, debug == 1, no anti-aliasing, spp > 1, bounce limits."""
+    variants = [
+        dict(aperture=0.6, focus_distance=12.0), dict(orthographic_fov_dis=4.0), dict(selected_tone_map_mode=1), dict(selected_tone_map_mode=2),
+        dict(selected_tone_map_mode=3), dict(selected_tone_map_mode=7), dict(mapping=4, map_scale=25.0), dict(mapping=1, map_scale=1.0),
+        dict(debug=1), dict(antialiasing=0), dict(number_of_samples=5), dict(number_of_bounces=1), dict(number_of_bounces=2), dict(exposure=0.5, scale=2.0),
+        dict(mapping=6), dict(mapping=7), dict(mapping=9), dict(mapping=10), dict(mapping=11),
+    ]
+    dl, pl = bright_lights()
+    ctx, sc = make(api, cornell_desc, size, size)
+    cornell_oracle.update_lights(dl, pl); sc.update_lights(dl, pl)
+    try:
+        cam = host.Camera(size, size).set(position=(0.5, 0.3, 13.0), direction=(-0.05, -0.02, -1))
+        for kw in variants:
+            base = dict(number_of_samples=2, number_of_bounces=5)
+            base.update(kw)
+            gui = host.Gui(**base)
+            d1, d2 = host.FrameDriver(cam, gui, False), host.FrameDriver(cam, gui, False)
+            ctx.resize(size, size)
+            acc = None
+            for _ in range(2):
+                ctx.render(sc, d1.next_ubo()); acc, out, st = cornell_oracle.render(d2.next_ubo(), size, size, acc)
+            acc_g, out_g = ctx.readback()
+            mre, ps = util.mean_rel_err(acc_g, acc, max(1, d1.total.value)), util.psnr(out_g[..., :3], out[..., :3])
+            assert mre < MRE_TOL and ps >= PSNR_TOL, (kw, mre, ps)
+    finally:
+        d0 = np.frombuffer(util._arr(cornell_desc.dlights, cornell_desc.n_dlights, F.rt_light), F.LIGHT_DTYPE)
+        p0 = np.frombuffer(util._arr(cornell_desc.plights, cornell_desc.n_plights, F.rt_light), F.LIGHT_DTYPE)
+        cornell_oracle.update_lights(d0, p0)

@@ -43,3 +43,7 @@ def test_emu_glass_volume():
 
 def test_emu_skinned_character():
     pc.case_skinned_character(emu_api(), n_tris=4000, joints=32, size=32, frames=2)
+
+
+def test_emu_frame_options(cornell_desc, cornell_oracle):
+    pc.case_frame_options(emu_api(), cornell_desc, cornell_oracle, size=32)

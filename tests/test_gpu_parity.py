@@ -111,3 +111,8 @@ def test_glass_volume_scene(api):
 def test_skinned_character_per_frame(api):
     """Config-4 shape: skinning kernel + BLAS refit + TLAS rebuild + render every frame."""
     pc.case_skinned_character(api, n_tris=200000, joints=256, size=96, frames=3)
+
+
+def test_frame_options(api, cornell_desc, cornell_oracle):
+    """Lens, orthographic camera, all tone-map modes, DISTANCE / HEAT / debug mappings, debug == 1, spp > 1."""
+    pc.case_frame_options(api, cornell_desc, cornell_oracle, size=96)
