@@ -2,6 +2,7 @@
 // peer-memory reduce.  Compiled for sm_100a only (see Makefile); no CPU path exists in this library.
 #include "rt_core.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 int g_rt_sm_count = 148;
 unsigned long long g_rt_launch_count = 0;
@@ -31,6 +32,20 @@ int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32
     g_rt_launch_count += 4;
     if (rt_d2d(keys, keys_tmp, n * 8, s)) return 1;
     return rt_d2d(vals, vals_tmp, n * 4, s);
+}
+
+int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, rt_stream_t s) {
+    size_t need = 0;
+    if (chk(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, s))) return 1;
+    if (need > g_sort_tmp_bytes) {
+        if (g_sort_tmp) { cudaStreamSynchronize(s); cudaFree(g_sort_tmp); }
+        g_sort_tmp_bytes = need + need / 4 + 256;
+        if (chk(cudaMalloc(&g_sort_tmp, g_sort_tmp_bytes))) { g_sort_tmp = nullptr; g_sort_tmp_bytes = 0; return 1; }
+    }
+    size_t bytes = g_sort_tmp_bytes;
+    if (chk(cub::DeviceScan::ExclusiveSum(g_sort_tmp, bytes, in, out, (int)n, s))) return 1;
+    g_rt_launch_count += 1;
+    return 0;
 }
 
 // ---- multi-GPU: peer access to the accumulation image across processes ----------------

@@ -83,6 +83,12 @@ inline int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
     return 0;
 }
 
+inline int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, rt_stream_t) {
+    uint32_t acc = 0;
+    for (size_t i = 0; i < n; ++i) { const uint32_t v = in[i]; out[i] = acc; acc += v; }
+    return 0;
+}
+
 struct rt_timer { void create() {} void destroy() {} void record(rt_stream_t) {} };
 inline float rt_timer_ms(rt_timer&, rt_timer&) { return 0.0f; }
 
@@ -135,6 +141,7 @@ int rt_d2d(void* d, const void* s_, size_t n, rt_stream_t s);
 int rt_memset(void* d, int v, size_t n, rt_stream_t s);
 int rt_stream_sync(rt_stream_t s);
 int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, size_t n, rt_stream_t s);
+int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, rt_stream_t s);
 
 // generic element-wise launch: grid-stride, 256 threads, grid capped at a multiple of the SM count
 template <class F> __global__ void __launch_bounds__(256) rt_foreach_kernel(size_t n, F f) {
