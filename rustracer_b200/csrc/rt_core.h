@@ -757,7 +757,7 @@ int RT_API(rt_scene_set_skybox)(rt_scene* s, const uint8_t* const faces[6], uint
 
 int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_render_opts* opts, void* stream) {
     if (!c || !s || !ubo) return fail("rt_render: null argument");
-    if (s->ctx != c) return fail("rt_render: scene belongs to another context");
+    if (s->ctx->device != c->device) return fail("rt_render: scene lives on another device");   // contexts of one device may share a scene (read-only here)
     if (ubo->total_number_of_samples == 0) return fail("rt_render: total_number_of_samples must be > 0");
 #ifndef RT_EMU
     cudaSetDevice(c->device);
