@@ -187,7 +187,7 @@ RT_D void baked_triangle(const rt_vertex* verts, const uint32_t* indices, const 
                          uint2 src, f3& w0, f3& w1, f3& w2) {
     const uint32_t geo = rt_float_as_uint(inst_w2o[(size_t)src.x * RT_INST_F4 + 3].y);
     const rt_prim_info pi = prims[geo];
-    const float4 m0 = inst_o2w[(size_t)src.x * 3], m1 = inst_o2w[(size_t)src.x * 3 + 1], m2 = inst_o2w[(size_t)src.x * 3 + 2];
+    const float4 m0 = inst_o2w[(size_t)src.x * RT_O2W_F4], m1 = inst_o2w[(size_t)src.x * RT_O2W_F4 + 1], m2 = inst_o2w[(size_t)src.x * RT_O2W_F4 + 2];
     const uint32_t io = pi.i_offset + 3 * src.y;
     const float* p0 = verts[pi.v_offset + indices[io]].position; const float* p1 = verts[pi.v_offset + indices[io + 1]].position; const float* p2 = verts[pi.v_offset + indices[io + 2]].position;
     w0 = xform_point_exact(m0, m1, m2, mk3(p0[0], p0[1], p0[2]));
@@ -278,7 +278,7 @@ static void refit_merged(rt_scene* s) { pack_merged(s); refit_nodes(s, s->merged
 static int upload_instance_records(rt_scene* s) {
     rt_stream_t st = s->ctx->stream;
     const uint32_t n = (uint32_t)s->instances.size();
-    std::vector<float> w2o((size_t)(n + 1) * 16), o2w((size_t)(n ? n : 1) * 12);
+    std::vector<float> w2o((size_t)(n + 1) * 16), o2w((size_t)(n ? n : 1) * 4 * RT_O2W_F4);
     for (uint32_t i = 0; i < n; ++i) {
         const rt_instance& in = s->instances[i];
         float inv[12]; invert_3x4(in.transform, inv);
@@ -286,14 +286,18 @@ static int upload_instance_records(rt_scene* s) {
         const GeoRecord& gr = s->geo[in.geo_id];
         uint32_t meta[4] = {gr.node_off, in.geo_id, s->geometries[in.geo_id].opaque ? RT_INST_OPAQUE : 0u, gr.tri_off};
         memcpy(&w2o[(size_t)i * 16 + 12], meta, 16);
-        memcpy(&o2w[(size_t)i * 12], in.transform, 48);
+        memcpy(&o2w[(size_t)i * 4 * RT_O2W_F4], in.transform, 48);
+        // 4th row: the geometry's PrimInfo, so that shading resolves indices and material without the geo -> PrimInfo hop
+        const rt_prim_info& pi = s->prim_infos[in.geo_id];
+        const uint32_t shade_meta[4] = {pi.v_offset, pi.i_offset, pi.material_id, in.geo_id};
+        memcpy(&o2w[(size_t)i * 4 * RT_O2W_F4 + 12], shade_meta, 16);
     }
     const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     memcpy(&w2o[(size_t)n * 16], ident, 48);
     uint32_t meta[4] = {s->merged.node_off, 0u, RT_INST_IDENTITY | RT_INST_MERGED, s->merged.tri_off};
     memcpy(&w2o[(size_t)n * 16 + 12], meta, 16);
     RT_CHECK(rt_h2d(s->d_inst_w2o, w2o.data(), w2o.size() * 4, st), "upload instances");
-    if (n) RT_CHECK(rt_h2d(s->d_inst_o2w, o2w.data(), (size_t)n * 48, st), "upload instances");
+    if (n) RT_CHECK(rt_h2d(s->d_inst_o2w, o2w.data(), (size_t)n * 16 * RT_O2W_F4, st), "upload instances");
     return 0;
 }
 
@@ -316,7 +320,7 @@ static int build_tlas(rt_scene* s) {
         DAabb w;
         if (rec == n) { w = b; }      // merged BLAS: already world space
         else {
-            const float4 m0 = o2wd[(size_t)rec * 3], m1 = o2wd[(size_t)rec * 3 + 1], m2 = o2wd[(size_t)rec * 3 + 2];
+            const float4 m0 = o2wd[(size_t)rec * RT_O2W_F4], m1 = o2wd[(size_t)rec * RT_O2W_F4 + 1], m2 = o2wd[(size_t)rec * RT_O2W_F4 + 2];
             for (int c = 0; c < 8; ++c) {
                 const float x = (c & 1) ? b.hi[0] : b.lo[0], y = (c & 2) ? b.hi[1] : b.lo[1], z = (c & 4) ? b.hi[2] : b.lo[2];
                 const float p[3] = {m0.x * x + m0.y * y + m0.z * z + m0.w, m1.x * x + m1.y * y + m1.z * z + m1.w, m2.x * x + m2.y * y + m2.z * z + m2.w};
@@ -670,7 +674,7 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
     e |= dev_upload(&s->d_bake_src, bake_src.data(), bake_src.size(), st);
     e |= dev_alloc(&s->d_tlas_nodes, (size_t)(ninst + 1) * RT_NODE_F4); e |= dev_alloc(&s->d_tlas_prims, ninst + 1);
     e |= dev_alloc(&s->d_tlas_box, ninst + 1); e |= dev_alloc(&s->d_tlas_parent, ninst + 1); e |= dev_alloc(&s->d_inst_boxes, ninst + 1);
-    e |= dev_alloc(&s->d_inst_w2o, (size_t)(ninst + 1) * RT_INST_F4); e |= dev_alloc(&s->d_inst_o2w, (size_t)(ninst ? ninst : 1) * 3);
+    e |= dev_alloc(&s->d_inst_w2o, (size_t)(ninst + 1) * RT_INST_F4); e |= dev_alloc(&s->d_inst_o2w, (size_t)(ninst ? ninst : 1) * RT_O2W_F4);
     e |= dev_alloc(&s->d_inst_root, ninst + 1); e |= dev_alloc(&s->d_entry_rec, ninst + 1);
     if (e) return bail(std::string("rt_scene_create: BVH allocation failed: ") + rt_platform_error());
 

@@ -442,6 +442,14 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) shado
         });
 }
 
+#ifndef RT_SHADE_PREFETCH
+#define RT_SHADE_PREFETCH 1   // 1 = L2, 2 = L1
+#endif
+#if RT_SHADE_PREFETCH == 2
+RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 4
 #endif
@@ -454,6 +462,15 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
     // all lanes of a warp iterate together so the ballots below are convergent
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
         const uint32_t i = base + lane;
+#if RT_SHADE_PREFETCH
+        {   // stream the next iteration's path state and hit record towards the SM while this one is shaded
+            const uint32_t nx = i + stride;
+            if (nx < count) {
+                rt_prefetch(qin.o_tmin + nx); rt_prefetch(qin.d_tmax + nx); rt_prefetch(qin.thr_pix + nx); rt_prefetch(qin.rng + nx);
+                rt_prefetch(hits.tuvp + nx); rt_prefetch(hits.inst + nx);
+            }
+        }
+#endif
         ShadeResult r; r.alive = false; r.has_shadow = false;
         if (i < count) r = shade_item<SIMPLE, COUNT>(S, P, fb, qin, hits, i, bounce, cnt);
         const uint32_t alive_mask = __ballot_sync(0xFFFFFFFFu, r.alive);

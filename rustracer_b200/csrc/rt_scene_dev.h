@@ -12,7 +12,10 @@
 // meta[i]: 0 = empty; inner: 0b001_xxxxx with xxxxx = 24 + slot; leaf: top 3 bits = unary count (1 -> 001,
 // 2 -> 011, 3 -> 111), low 5 bits = first primitive offset (0..23) relative to prim_base.
 #define RT_NODE_F4 5
+#define RT_O2W_F4 4
+#ifndef RT_LEAF_MAX
 #define RT_LEAF_MAX 3
+#endif
 #define RT_STACK_SIZE 48
 
 // BLAS primitive record, 48 bytes = 3 x float4: v0.xyz | primitive_id ; v1.xyz | instance_id (merged BLAS only) ; v2.xyz | 0
@@ -39,7 +42,7 @@ struct DScene {
     const float4* blas_nodes;      // all BLASes, child indices absolute
     const float4* tris;            // RT_TRI_F4 float4 per triangle, leaf order
     const float4* inst_w2o;        // RT_INST_F4 float4 per instance
-    const float4* inst_o2w;        // 3 float4 per instance: object->world rows
+    const float4* inst_o2w;        // RT_O2W_F4 float4 per instance: object->world rows | v_offset, i_offset, material_id, geo_id
     uint32_t n_instances;
     // when the TLAS holds nothing but the merged world-space BLAS, rays start inside it (no TLAS visit, no instance entry)
     uint32_t single_merged, merged_node_off, merged_tri_off;

@@ -260,11 +260,11 @@ RT_D void shade_miss(const DScene& S, const FrameParams& P, f3 world_dir, bool p
 template <bool SIMPLE>
 RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, PathState& st, ShadeOut& o, RtCounters* cnt) {
     const rt_ubo& ubo = P.ubo;
-    const float4* wp = S.inst_w2o + (size_t)hit.inst * RT_INST_F4;
-    const uint32_t geo_id = rt_float_as_uint(rt_ld(wp + 3).y);
-    const float4* op = S.inst_o2w + (size_t)hit.inst * 3;
-    const float4 m0 = rt_ld(op), m1 = rt_ld(op + 1), m2 = rt_ld(op + 2);
-    const rt_prim_info pinfo = S.prim_infos[geo_id];
+    const float4* op = S.inst_o2w + (size_t)hit.inst * RT_O2W_F4;
+    const float4 m0 = rt_ld(op), m1 = rt_ld(op + 1), m2 = rt_ld(op + 2), m3 = rt_ld(op + 3);
+    rt_prim_info pinfo;     // copy of prim_infos[geo_id] kept in the instance record (one dependent load less)
+    pinfo.v_offset = rt_float_as_uint(m3.x); pinfo.i_offset = rt_float_as_uint(m3.y); pinfo.material_id = rt_float_as_uint(m3.z);
+    const uint32_t geo_id = rt_float_as_uint(m3.w);
     const rt_material& mat = S.materials[pinfo.material_id];
     const TriIndices ti = fetch_indices(S, pinfo, hit.prim);
     const rt_vertex& v0 = S.vertices[ti.i0]; const rt_vertex& v1 = S.vertices[ti.i1]; const rt_vertex& v2 = S.vertices[ti.i2];
