@@ -3,6 +3,7 @@
 // reference functions each entry point mirrors.  CPU only; produces rt_scene_desc / rt_ubo.
 #include "../include/gltf_host.h"
 
+#include <dirent.h>
 #include <zlib.h>
 #include <cmath>
 #include <cstdio>
@@ -248,6 +249,343 @@ bool decode_png(const uint8_t* d, size_t n, DecodedImage& out, std::string& err)
         }
     }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// JPEG (ITU-T T.81: baseline and progressive Huffman, 8 bit, 1 or 3 components)
+// The reference decodes through the `image` 0.24.6 crate -> `jpeg-decoder` 0.3.0 (Cargo.lock; not under
+// /root/reference).  T.81 leaves IDCT precision, chroma upsampling and colour conversion to the decoder; this one
+// uses the LL&M 13-bit integer IDCT, triangle-filter ("fancy") upsampling for 2x1 / 2x2 chroma and the JFIF
+// fixed-point YCbCr->RGB conversion, i.e. libjpeg's defaults, so it can be checked bit-for-bit against
+// libjpeg-turbo (tests/test_host.py); against jpeg-decoder a few texels may differ by 1-2 LSB.
+// ---------------------------------------------------------------------------------------------------
+namespace jpg {
+static const uint8_t ZZ[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                               35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+struct Huff {
+    bool present = false;
+    uint8_t vals[256]; int maxcode[18], valptr[17], mincode[17];
+    uint16_t fast[512];   // 9-bit prefix -> (length << 8 | symbol), 0 = longer code
+    void build(const uint8_t* counts, const uint8_t* symbols) {
+        present = true; memset(fast, 0, sizeof fast);
+        int code = 0, k = 0;
+        for (int len = 1; len <= 16; ++len) {
+            valptr[len] = k; mincode[len] = code;
+            for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+                vals[k] = symbols[k];
+                if (len <= 9) { const int lo = code << (9 - len); for (int f = 0; f < (1 << (9 - len)); ++f) fast[lo + f] = (uint16_t)(len << 8 | symbols[k]); }
+            }
+            maxcode[len] = counts[len - 1] ? code - 1 : -1;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7FFFFFFF;
+    }
+};
+struct Comp { int id = 0, h = 1, v = 1, tq = 0, bw = 0, bh = 0, pw = 0, ph = 0, dc_pred = 0, td = 0, ta = 0; std::vector<int16_t> coef; std::vector<uint8_t> plane; };
+struct Bits {
+    const uint8_t* d; size_t n, p; uint32_t acc = 0; int cnt = 0; bool hit_marker = false;
+    void fill() {
+        while (cnt <= 24) {
+            uint32_t b = 0;
+            if (!hit_marker && p < n) {
+                b = d[p];
+                if (b == 0xFF) {
+                    const uint8_t nx = p + 1 < n ? d[p + 1] : 0xD9;
+                    if (nx == 0) p += 2; else { hit_marker = true; b = 0; }
+                } else ++p;
+            }
+            acc |= b << (24 - cnt); cnt += 8;
+        }
+    }
+    int peek(int k) { if (cnt < k) fill(); return (int)(acc >> (32 - k)); }
+    void skip(int k) { acc <<= k; cnt -= k; }
+    int get(int k) { if (!k) return 0; const int v = peek(k); skip(k); return v; }
+    void reset() { acc = 0; cnt = 0; hit_marker = false; }
+};
+static inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+static int decode_sym(Bits& b, const Huff& h) {
+    const int look = b.peek(9); const uint16_t f = h.fast[look];
+    if (f) { b.skip(f >> 8); return f & 0xFF; }
+    int code = b.peek(16), len = 10;
+    for (; len <= 16; ++len) { const int c = code >> (16 - len); if (c <= h.maxcode[len] && h.maxcode[len] >= 0) { b.skip(len); return h.vals[h.valptr[len] + c - h.mincode[len]]; } }
+    b.skip(16); return 0;
+}
+// LL&M integer inverse DCT (13-bit constants, two passes), the "slow-but-accurate" variant
+static void idct(const int16_t* in, const uint16_t* q, uint8_t* out, int stride) {
+    const int CB = 13, P1 = 2;
+    const long F0298 = 2446, F0390 = 3196, F0541 = 4433, F0765 = 6270, F0899 = 7373, F1175 = 9633, F1501 = 12299, F1847 = 15137, F1961 = 16069, F2053 = 16819, F2562 = 20995, F3072 = 25172;
+    long ws[64];
+    for (int c = 0; c < 8; ++c) {
+        const int16_t* ip = in + c; const uint16_t* qp = q + c; long* wp = ws + c;
+        if (!ip[8] && !ip[16] && !ip[24] && !ip[32] && !ip[40] && !ip[48] && !ip[56]) {
+            const long dc = (long)ip[0] * qp[0] * (1 << P1);
+            for (int r = 0; r < 8; ++r) wp[8 * r] = dc;
+            continue;
+        }
+        long z2 = (long)ip[16] * qp[16], z3 = (long)ip[48] * qp[48];
+        long z1 = (z2 + z3) * F0541, tmp2 = z1 - z3 * F1847, tmp3 = z1 + z2 * F0765;
+        z2 = (long)ip[0] * qp[0]; z3 = (long)ip[32] * qp[32];
+        long tmp0 = (z2 + z3) * (1L << CB), tmp1 = (z2 - z3) * (1L << CB);
+        const long t10 = tmp0 + tmp3, t13 = tmp0 - tmp3, t11 = tmp1 + tmp2, t12 = tmp1 - tmp2;
+        tmp0 = (long)ip[56] * qp[56]; tmp1 = (long)ip[40] * qp[40]; tmp2 = (long)ip[24] * qp[24]; tmp3 = (long)ip[8] * qp[8];
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; long z4 = tmp1 + tmp3; const long z5 = (z3 + z4) * F1175;
+        tmp0 *= F0298; tmp1 *= F2053; tmp2 *= F3072; tmp3 *= F1501;
+        z1 *= -F0899; z2 *= -F2562; z3 *= -F1961; z4 *= -F0390; z3 += z5; z4 += z5;
+        tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+        const int sh = CB - P1; const long rnd = 1L << (sh - 1);
+        wp[0] = (t10 + tmp3 + rnd) >> sh; wp[56] = (t10 - tmp3 + rnd) >> sh; wp[8] = (t11 + tmp2 + rnd) >> sh; wp[48] = (t11 - tmp2 + rnd) >> sh;
+        wp[16] = (t12 + tmp1 + rnd) >> sh; wp[40] = (t12 - tmp1 + rnd) >> sh; wp[24] = (t13 + tmp0 + rnd) >> sh; wp[32] = (t13 - tmp0 + rnd) >> sh;
+    }
+    for (int r = 0; r < 8; ++r) {
+        const long* wp = ws + 8 * r; uint8_t* op = out + (size_t)r * stride;
+        long z2 = wp[2], z3 = wp[6];
+        long z1 = (z2 + z3) * F0541, tmp2 = z1 - z3 * F1847, tmp3 = z1 + z2 * F0765;
+        long tmp0 = (wp[0] + wp[4]) * (1L << CB), tmp1 = (wp[0] - wp[4]) * (1L << CB);
+        const long t10 = tmp0 + tmp3, t13 = tmp0 - tmp3, t11 = tmp1 + tmp2, t12 = tmp1 - tmp2;
+        tmp0 = wp[7]; tmp1 = wp[5]; tmp2 = wp[3]; tmp3 = wp[1];
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; long z4 = tmp1 + tmp3; const long z5 = (z3 + z4) * F1175;
+        tmp0 *= F0298; tmp1 *= F2053; tmp2 *= F3072; tmp3 *= F1501;
+        z1 *= -F0899; z2 *= -F2562; z3 *= -F1961; z4 *= -F0390; z3 += z5; z4 += z5;
+        tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+        const int sh = CB + P1 + 3; const long rnd = 1L << (sh - 1);
+        auto px = [&](long v) { v = ((v + rnd) >> sh) + 128; return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); };
+        op[0] = px(t10 + tmp3); op[7] = px(t10 - tmp3); op[1] = px(t11 + tmp2); op[6] = px(t11 - tmp2);
+        op[2] = px(t12 + tmp1); op[5] = px(t12 - tmp1); op[3] = px(t13 + tmp0); op[4] = px(t13 - tmp0);
+    }
+}
+}  // namespace jpg
+
+bool decode_jpeg(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) {
+    using namespace jpg;
+    if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) { err = "not a JPEG"; return false; }
+    uint16_t qt[4][64]; bool qt_ok[4] = {false, false, false, false};
+    Huff hdc[4], hac[4];
+    std::vector<Comp> comps; int W = 0, H = 0, hmax = 1, vmax = 1, restart = 0; bool progressive = false, have_sof = false;
+    int adobe_transform = -1;
+    size_t p = 2;
+    auto be16 = [&](size_t o) { return (int)d[o] << 8 | d[o + 1]; };
+    while (p + 4 <= n) {
+        if (d[p] != 0xFF) { ++p; continue; }
+        const uint8_t m = d[p + 1];
+        if (m == 0xFF) { ++p; continue; }
+        if (m == 0xD9) break;
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { p += 2; continue; }
+        const size_t len = (size_t)be16(p + 2);
+        if (len < 2 || p + 2 + len > n) { err = "truncated JPEG"; return false; }
+        const uint8_t* b = d + p + 4; const size_t bl = len - 2;
+        if (m == 0xDB) {
+            for (size_t o = 0; o < bl;) {
+                const int pq = b[o] >> 4, tq = b[o] & 15; ++o;
+                if (tq > 3 || o + (pq ? 128u : 64u) > bl) { err = "bad JPEG DQT"; return false; }
+                for (int i = 0; i < 64; ++i) { qt[tq][ZZ[i]] = (uint16_t)(pq ? (b[o] << 8 | b[o + 1]) : b[o]); o += pq ? 2 : 1; }
+                qt_ok[tq] = true;
+            }
+        } else if (m == 0xC4) {
+            for (size_t o = 0; o + 17 <= bl;) {
+                const int tc = b[o] >> 4, th = b[o] & 15; int total = 0;
+                for (int i = 0; i < 16; ++i) total += b[o + 1 + i];
+                if (th > 3 || tc > 1 || total > 256 || o + 17 + total > bl) { err = "bad JPEG DHT"; return false; }
+                (tc ? hac[th] : hdc[th]).build(b + o + 1, b + o + 17);
+                o += 17 + total;
+            }
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+            if (bl < 6 || b[0] != 8) { err = "JPEG sample precision unsupported"; return false; }
+            progressive = m == 0xC2; H = be16(p + 5); W = be16(p + 7);
+            const int nc = b[5];
+            if ((nc != 1 && nc != 3) || bl < (size_t)(6 + 3 * nc) || !W || !H) { err = "JPEG component count unsupported"; return false; }
+            comps.resize(nc);
+            for (int i = 0; i < nc; ++i) { comps[i].id = b[6 + 3 * i]; comps[i].h = b[7 + 3 * i] >> 4; comps[i].v = b[7 + 3 * i] & 15; comps[i].tq = b[8 + 3 * i] & 3;
+                                           if (comps[i].h < 1 || comps[i].h > 4 || comps[i].v < 1 || comps[i].v > 4) { err = "bad JPEG sampling"; return false; }
+                                           hmax = std::max(hmax, comps[i].h); vmax = std::max(vmax, comps[i].v); }
+            const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+            for (auto& c : comps) {
+                c.bw = ((W * c.h + hmax - 1) / hmax + 7) / 8; c.bh = ((H * c.v + vmax - 1) / vmax + 7) / 8;   // blocks covering the component
+                c.pw = mcux * c.h; c.ph = mcuy * c.v;                                                          // padded to whole MCUs
+                c.coef.assign((size_t)c.pw * c.ph * 64, 0);
+            }
+            have_sof = true;
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            err = "JPEG coding process unsupported (lossless / arithmetic / hierarchical)"; return false;
+        } else if (m == 0xDD) {
+            restart = be16(p + 4);
+        } else if (m == 0xEE && bl >= 12 && !memcmp(b, "Adobe", 5)) {
+            adobe_transform = b[11];
+        } else if (m == 0xDA) {
+            if (!have_sof) { err = "JPEG SOS before SOF"; return false; }
+            const int ns = b[0];
+            if (ns < 1 || ns > (int)comps.size() || bl < (size_t)(4 + 2 * ns)) { err = "bad JPEG SOS"; return false; }
+            Comp* sc[4];
+            for (int i = 0; i < ns; ++i) {
+                sc[i] = nullptr;
+                for (auto& c : comps) if (c.id == b[1 + 2 * i]) sc[i] = &c;
+                if (!sc[i]) { err = "bad JPEG SOS component"; return false; }
+                sc[i]->td = b[2 + 2 * i] >> 4; sc[i]->ta = b[2 + 2 * i] & 15;
+                if (sc[i]->td > 3 || sc[i]->ta > 3) { err = "bad JPEG SOS table"; return false; }
+            }
+            int Ss = b[1 + 2 * ns], Se = b[2 + 2 * ns]; const int Ah = b[3 + 2 * ns] >> 4, Al = b[3 + 2 * ns] & 15;
+            if (!progressive) { Ss = 0; Se = 63; }
+            if (Ss > Se || Se > 63 || (progressive && Ss == 0 && Se != 0) || (progressive && Ss > 0 && ns != 1)) { err = "bad JPEG spectral selection"; return false; }
+            Bits br{d, n, p + 2 + len};
+            int eobrun = 0, todo = restart;
+            for (auto& c : comps) c.dc_pred = 0;
+            auto block = [&](Comp& c, int bx, int by) -> bool {
+                int16_t* blk = &c.coef[((size_t)by * c.pw + bx) * 64];
+                if (!progressive) {
+                    const Huff &hd = hdc[c.td], &ha = hac[c.ta];
+                    if (!hd.present || !ha.present) return false;
+                    const int s = decode_sym(br, hd);
+                    c.dc_pred += s ? extend(br.get(s), s) : 0;
+                    blk[0] = (int16_t)c.dc_pred;
+                    for (int k = 1; k < 64;) {
+                        const int rs = decode_sym(br, ha), r = rs >> 4, sz = rs & 15;
+                        if (!sz) { if (r != 15) break; k += 16; continue; }
+                        k += r; if (k > 63) break;
+                        blk[ZZ[k++]] = (int16_t)extend(br.get(sz), sz);
+                    }
+                    return true;
+                }
+                if (Ss == 0) {                                   // DC scan
+                    if (Ah == 0) {
+                        const Huff& hd = hdc[c.td]; if (!hd.present) return false;
+                        const int s = decode_sym(br, hd);
+                        c.dc_pred += s ? extend(br.get(s), s) : 0;
+                        blk[0] = (int16_t)(c.dc_pred * (1 << Al));
+                    } else if (br.get(1)) blk[0] |= (int16_t)(1 << Al);
+                    return true;
+                }
+                const Huff& ha = hac[c.ta]; if (!ha.present) return false;
+                if (Ah == 0) {                                   // AC first pass
+                    if (eobrun > 0) { --eobrun; return true; }
+                    for (int k = Ss; k <= Se; ++k) {
+                        const int rs = decode_sym(br, ha), r = rs >> 4, sz = rs & 15;
+                        if (sz) { k += r; if (k > 63) break; blk[ZZ[k]] = (int16_t)(extend(br.get(sz), sz) * (1 << Al)); }
+                        else if (r == 15) k += 15;
+                        else { eobrun = (1 << r) + (r ? br.get(r) : 0) - 1; break; }
+                    }
+                    return true;
+                }
+                // AC refinement (T.81 G.1.2.3)
+                const int p1 = 1 << Al, m1 = -(1 << Al);
+                int k = Ss;
+                auto refine = [&](int16_t& cf) { if (br.get(1) && !(cf & p1)) cf = (int16_t)(cf + (cf >= 0 ? p1 : m1)); };
+                if (eobrun == 0) {
+                    for (; k <= Se; ++k) {
+                        const int rs = decode_sym(br, ha); int r = rs >> 4; int s = rs & 15;
+                        if (s) s = br.get(1) ? p1 : m1;
+                        else if (r != 15) { eobrun = (1 << r) + (r ? br.get(r) : 0); break; }
+                        for (; k <= Se; ++k) {
+                            int16_t& cf = blk[ZZ[k]];
+                            if (cf) refine(cf); else if (--r < 0) break;
+                        }
+                        if (s && k <= Se) blk[ZZ[k]] = (int16_t)s;
+                    }
+                }
+                if (eobrun > 0) {
+                    for (; k <= Se; ++k) { int16_t& cf = blk[ZZ[k]]; if (cf) refine(cf); }
+                    --eobrun;
+                }
+                return true;
+            };
+            auto restart_check = [&]() -> bool {
+                if (!restart) return true;
+                if (--todo > 0) return true;
+                // byte-align, expect RSTn
+                br.reset();
+                while (br.p + 1 < n && !(d[br.p] == 0xFF && d[br.p + 1] >= 0xD0 && d[br.p + 1] <= 0xD7)) {
+                    if (d[br.p] == 0xFF && d[br.p + 1] != 0 && d[br.p + 1] != 0xFF) return true;   // some other marker: let the outer parser see it
+                    ++br.p;
+                }
+                if (br.p + 1 < n) br.p += 2;
+                todo = restart; eobrun = 0;
+                for (auto& c : comps) c.dc_pred = 0;
+                return true;
+            };
+            bool ok = true;
+            if (ns == 1) {
+                Comp& c = *sc[0];
+                for (int by = 0; by < c.bh && ok; ++by) for (int bx = 0; bx < c.bw && ok; ++bx) { ok = block(c, bx, by); restart_check(); }
+            } else {
+                const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+                for (int my = 0; my < mcuy && ok; ++my) for (int mx = 0; mx < mcux && ok; ++mx) {
+                    for (int i = 0; i < ns && ok; ++i) for (int v = 0; v < sc[i]->v && ok; ++v) for (int h = 0; h < sc[i]->h && ok; ++h)
+                        ok = block(*sc[i], mx * sc[i]->h + h, my * sc[i]->v + v);
+                    restart_check();
+                }
+            }
+            if (!ok) { err = "JPEG scan references a missing Huffman table"; return false; }
+            // continue after the entropy-coded segment: next marker that is not RSTn / stuffing
+            size_t q = br.p < p + 2 + len ? p + 2 + len : br.p;          // the bit reader never steps over a marker
+            while (q + 1 < n && !(d[q] == 0xFF && d[q + 1] != 0 && d[q + 1] != 0xFF && !(d[q + 1] >= 0xD0 && d[q + 1] <= 0xD7))) ++q;
+            p = q; continue;
+        }
+        p += 2 + len;
+    }
+    if (!have_sof) { err = "JPEG without frame header"; return false; }
+    for (auto& c : comps) {
+        if (!qt_ok[c.tq]) { err = "JPEG quantisation table missing"; return false; }
+        const int pw = c.pw * 8;
+        c.plane.assign((size_t)pw * c.ph * 8, 0);
+        for (int by = 0; by < c.ph; ++by) for (int bx = 0; bx < c.pw; ++bx)
+            idct(&c.coef[((size_t)by * c.pw + bx) * 64], qt[c.tq], &c.plane[(size_t)by * 8 * pw + bx * 8], pw);
+        c.coef.clear(); c.coef.shrink_to_fit();
+    }
+    // chroma upsampling to full resolution
+    std::vector<std::vector<uint8_t>> full(comps.size());
+    for (size_t ci = 0; ci < comps.size(); ++ci) {
+        Comp& c = comps[ci]; const int pw = c.pw * 8;
+        const int cw = (W * c.h + hmax - 1) / hmax, chh = (H * c.v + vmax - 1) / vmax;     // real component size
+        const int fx = hmax / c.h, fy = vmax / c.v;
+        std::vector<uint8_t>& o = full[ci]; o.resize((size_t)W * H);
+        auto at = [&](int x, int y) -> int { return c.plane[(size_t)std::min(std::max(y, 0), chh - 1) * pw + std::min(std::max(x, 0), cw - 1)]; };
+        if (fx == 1 && fy == 1 && hmax % c.h == 0 && vmax % c.v == 0) {
+            for (int y = 0; y < H; ++y) memcpy(&o[(size_t)y * W], &c.plane[(size_t)y * pw], W);
+        } else if (fx == 2 && fy == 1 && hmax == 2 * c.h && vmax == c.v && cw > 2) {
+            for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+                const int i = x >> 1, cur = at(i, y);
+                int v;
+                if (x & 1) v = (i == cw - 1) ? cur : (3 * cur + at(i + 1, y) + 2) >> 2;
+                else v = (i == 0) ? cur : (3 * cur + at(i - 1, y) + 1) >> 2;
+                o[(size_t)y * W + x] = (uint8_t)v;
+            }
+        } else if (fx == 2 && fy == 2 && hmax == 2 * c.h && vmax == 2 * c.v && cw > 2) {
+            for (int y = 0; y < H; ++y) {
+                const int iy = y >> 1, oy = (y & 1) ? iy + 1 : iy - 1;     // nearer row iy (weight 3), farther row oy (weight 1)
+                for (int x = 0; x < W; ++x) {
+                    const int i = x >> 1;
+                    const int cur = 3 * at(i, iy) + at(i, oy);
+                    int v;
+                    if (x & 1) v = (i == cw - 1) ? (cur * 4 + 7) >> 4 : (cur * 3 + 3 * at(i + 1, iy) + at(i + 1, oy) + 7) >> 4;
+                    else v = (i == 0) ? (cur * 4 + 8) >> 4 : (cur * 3 + 3 * at(i - 1, iy) + at(i - 1, oy) + 8) >> 4;
+                    o[(size_t)y * W + x] = (uint8_t)v;
+                }
+            }
+        } else {
+            for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) o[(size_t)y * W + x] = (uint8_t)at(x * c.h / hmax, y * c.v / vmax);
+        }
+        c.plane.clear(); c.plane.shrink_to_fit();
+    }
+    out.w = (uint32_t)W; out.h = (uint32_t)H; out.rgba.resize((size_t)W * H * 4);
+    const bool ycc = comps.size() == 3 && adobe_transform != 0;
+    for (size_t i = 0; i < (size_t)W * H; ++i) {
+        uint8_t* o = &out.rgba[i * 4];
+        if (comps.size() == 1) { o[0] = o[1] = o[2] = full[0][i]; }
+        else if (!ycc) { o[0] = full[0][i]; o[1] = full[1][i]; o[2] = full[2][i]; }
+        else {
+            const int y = full[0][i], cb = full[1][i] - 128, cr = full[2][i] - 128;
+            auto cl = [](int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); };
+            const int r = y + ((91881 * cr + 32768) >> 16);
+            const int g = y + ((-22554 * cb - 46802 * cr + 32768) >> 16);
+            const int bl = y + ((116130 * cb + 32768) >> 16);
+            o[0] = cl(r); o[1] = cl(g); o[2] = cl(bl);
+        }
+        o[3] = 255;
+    }
+    return true;
+}
+
+bool decode_image(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) {
+    if (n >= 2 && d[0] == 0xFF && d[1] == 0xD8) return decode_jpeg(d, n, out, err);
+    return decode_png(d, n, out, err);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -611,7 +949,7 @@ struct Loader {
                 bytes.assign(buf.begin() + off, buf.begin() + off + len);
             }
             DecodedImage di; std::string err;
-            if (!decode_png(bytes.data(), bytes.size(), di, err)) die("image " + std::to_string(i) + ": " + err + " (only 8-bit PNG is decoded by the C++ host; pass other formats pre-decoded)");
+            if (!decode_image(bytes.data(), bytes.size(), di, err)) die("image " + std::to_string(i) + ": " + err + " (the C++ host decodes 8-bit PNG and baseline/progressive JPEG; pass other formats pre-decoded)");
             doc.images.push_back(std::move(di)); doc.image_srgb.push_back(linear[i] ? 0 : 1);
         }
         // samplers: slot 0 default (texture.rs:31-41)
@@ -927,6 +1265,47 @@ void gv_build_ubo(const gv_camera* cam, const gv_gui* gui, uint32_t* total, uint
 int gv_decode_png(const uint8_t* data, size_t size, uint8_t** rgba, uint32_t* w, uint32_t* h) {
     DecodedImage d; std::string err;
     if (!decode_png(data, size, d, err)) return fail(err);
+    *rgba = (uint8_t*)malloc(d.rgba.size()); memcpy(*rgba, d.rgba.data(), d.rgba.size()); *w = d.w; *h = d.h; return 0;
+}
+// SkyBox::new (cubumap.rs:86-106) + resource_manager::load_cubemap: the six *.png / *.jpg files of a directory, ordered
+// by Face::get_index (cubumap.rs:29-50): posx,negx,posy,negy,posz,negz or right,left,top,bottom,front,back.
+int gv_load_skybox_dir(const char* dir, uint8_t* faces[6], uint32_t* w, uint32_t* h) {
+    static const char* names[6][2] = {{"posx", "right"}, {"negx", "left"}, {"posy", "top"}, {"negy", "bottom"}, {"posz", "front"}, {"negz", "back"}};
+    for (int f = 0; f < 6; ++f) faces[f] = nullptr;
+    DIR* dp = opendir(dir);
+    if (!dp) return fail(std::string("cannot open skybox directory ") + dir);
+    std::string found[6]; int count = 0;
+    while (dirent* e = readdir(dp)) {
+        const std::string fn = e->d_name;
+        if (fn.size() < 5) continue;
+        const std::string ext = fn.substr(fn.size() - 4);
+        if (ext != ".png" && ext != ".jpg") continue;
+        ++count;
+        const std::string stem = fn.substr(0, fn.find('.'));
+        for (int f = 0; f < 6; ++f) if (stem == names[f][0] || stem == names[f][1]) found[f] = std::string(dir) + "/" + fn;
+    }
+    closedir(dp);
+    if (count != 6) return fail("skybox directory must hold exactly 6 .png/.jpg files (resource_manager::load_cubemap)");
+    uint32_t fw = 0, fh = 0;
+    for (int f = 0; f < 6; ++f) {
+        if (found[f].empty()) { for (int g = 0; g < f; ++g) { free(faces[g]); faces[g] = nullptr; } return fail(std::string("skybox face missing: ") + names[f][0]); }
+        std::vector<uint8_t> bytes;
+        try { bytes = read_file(found[f]); } catch (const std::exception& ex) { for (int g = 0; g < f; ++g) { free(faces[g]); faces[g] = nullptr; } return fail(ex.what()); }
+        DecodedImage d; std::string err;
+        if (!decode_image(bytes.data(), bytes.size(), d, err) || (f && (d.w != fw || d.h != fh))) {
+            for (int g = 0; g < f; ++g) { free(faces[g]); faces[g] = nullptr; }
+            return fail(found[f] + ": " + (err.empty() ? "face size differs" : err));
+        }
+        fw = d.w; fh = d.h;
+        faces[f] = (uint8_t*)malloc(d.rgba.size()); memcpy(faces[f], d.rgba.data(), d.rgba.size());
+    }
+    *w = fw; *h = fh;
+    return 0;
+}
+
+int gv_decode_image(const uint8_t* data, size_t size, uint8_t** rgba, uint32_t* w, uint32_t* h) {
+    DecodedImage d; std::string err;
+    if (!decode_image(data, size, d, err)) return fail(err);
     *rgba = (uint8_t*)malloc(d.rgba.size()); memcpy(*rgba, d.rgba.data(), d.rgba.size()); *w = d.w; *h = d.h; return 0;
 }
 void gv_free(void* p) { free(p); }

@@ -68,6 +68,11 @@ void gv_build_ubo(const gv_camera* cam, const gv_gui* gui, uint32_t* total_numbe
 
 /* PNG decoder used for embedded glTF images (8-bit, non-interlaced): returns RGBA8 via malloc */
 int  gv_decode_png(const uint8_t* data, size_t size, uint8_t** rgba, uint32_t* w, uint32_t* h);
+/* PNG (8 bit) or JPEG (baseline / progressive, 8 bit) -> RGBA8; replaces image::ImageReader::decode (image.rs:60-83) */
+int  gv_decode_image(const uint8_t* data, size_t size, uint8_t** rgba, uint32_t* w, uint32_t* h);
+/* SkyBox::new (asset_loader/src/cubumap.rs:86-106): six faces of a directory in +x,-x,+y,-y,+z,-z order, RGBA8 (sRGB).
+   Each faces[f] is malloc'd: release with gv_free. */
+int  gv_load_skybox_dir(const char* dir, uint8_t* faces[6], uint32_t* w, uint32_t* h);
 void gv_free(void* p);
 
 #ifdef __cplusplus

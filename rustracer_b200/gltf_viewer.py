@@ -16,22 +16,6 @@ import numpy as np
 
 from . import core, host
 
-FACES = ("posx", "negx", "posy", "negy", "posz", "negz")          # cubumap.rs:20-27
-ALIASES = {"right": "posx", "left": "negx", "top": "posy", "bottom": "negy", "front": "posz", "back": "negz"}   # :36-43
-
-
-def load_skybox(path: str):
-    """asset_loader::cubumap::SkyBox::new: six .png/.jpg faces named posx.. or right/left/top/bottom/front/back."""
-    from PIL import Image
-    files = {}
-    for p in Path(path).iterdir():
-        if p.suffix.lower() in (".png", ".jpg"):
-            files[ALIASES.get(p.stem, p.stem)] = p
-    if sorted(files) != sorted(FACES):
-        raise SystemExit(f"skybox directory must hold exactly the six faces {FACES}")
-    return [np.asarray(Image.open(files[f]).convert("RGBA")) for f in FACES]
-
-
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="gltf_viewer")
     ap.add_argument("-f", "--file", required=True, help="Path of the glTF file")
@@ -52,7 +36,7 @@ def main(argv=None):
     doc = host.load_file(a.file)
     sky = False
     if a.skybox:
-        doc.set_skybox(load_skybox(a.skybox))
+        doc.set_skybox(host.load_skybox_dir(a.skybox))     # SkyBox::new, cubumap.rs:86-106
         sky = True
     desc = doc.scene_desc()
     ctx = core.Context(a.width, a.height, device=a.device)

@@ -78,6 +78,32 @@ class Doc:
             raise HostError(self._lib.gv_last_error().decode())
 
 
+def decode_image(data: bytes) -> np.ndarray:
+    """PNG / JPEG bytes -> HxWx4 uint8 (asset_loader::image::Image::load_image, image.rs:60-83)."""
+    lib = F.load_host()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    out = F.c_u8p(); w = F.c_u32(); h = F.c_u32()
+    if lib.gv_decode_image(buf, len(data), C.byref(out), C.byref(w), C.byref(h)):
+        raise HostError(lib.gv_last_error().decode())
+    try:
+        return np.ctypeslib.as_array(out, shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib.gv_free(out)
+
+
+def load_skybox_dir(path: str) -> list:
+    """asset_loader::cubumap::SkyBox::new (cubumap.rs:86-106): six faces, +x,-x,+y,-y,+z,-z, each HxWx4 uint8."""
+    lib = F.load_host()
+    faces = (F.c_u8p * 6)(); w = F.c_u32(); h = F.c_u32()
+    if lib.gv_load_skybox_dir(str(path).encode(), faces, C.byref(w), C.byref(h)):
+        raise HostError(lib.gv_last_error().decode())
+    out = []
+    for f in range(6):
+        out.append(np.ctypeslib.as_array(faces[f], shape=(h.value, w.value, 4)).copy())
+        lib.gv_free(faces[f])
+    return out
+
+
 def load_file(path: str) -> Doc:
     lib = F.load_host()
     h = C.c_void_p()

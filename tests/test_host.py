@@ -163,3 +163,61 @@ def test_skinned_animated_glb_end_to_end():
     rays, _ = util.random_rays(3000, seed=2, extent=3.0)
     a, b = sc.trace_closest(rays, 1), o.trace_closest(rays, 1)
     assert util.hits_equal(a, b).all()
+
+
+def _test_image(w, h, seed=1):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    a = np.stack([(np.sin(x / 7.0) + np.cos(y / 5.0)) * 60 + 128, (x * 3 + y * 2) % 256, rng.integers(0, 255, (h, w)) * 0.3 + 100], -1)
+    return np.clip(a, 0, 255).astype(np.uint8)
+
+
+def test_jpeg_decoder_matches_libjpeg():
+    """Baseline + progressive, 4:4:4 / 4:2:2 / 4:2:0 / grey, odd sizes, restart markers: bit-identical to libjpeg-turbo
+    (same integer IDCT, triangle upsampling and YCbCr conversion).  The reference's decoder (jpeg-decoder 0.3.0) is not
+    available; T.81 allows decoders to differ by an LSB or two, see host/gltf_host.cpp."""
+    Image = pytest.importorskip("PIL.Image")
+    import io
+    cases = 0
+    for (w, h) in [(64, 48), (67, 35), (16, 16), (200, 133)]:
+        for sub in (0, 1, 2):
+            for prog in (False, True):
+                for grey in (False, True):
+                    im = Image.fromarray(_test_image(w, h))
+                    kw = dict(quality=85, progressive=prog, optimize=prog)
+                    if grey:
+                        im = im.convert("L")
+                    else:
+                        kw["subsampling"] = sub
+                    b = io.BytesIO(); im.save(b, "JPEG", **kw)
+                    ref = np.asarray(Image.open(io.BytesIO(b.getvalue())).convert("RGBA"))
+                    got = host.decode_image(b.getvalue())
+                    assert got.shape == ref.shape and np.array_equal(got, ref), (w, h, sub, prog, grey)
+                    cases += 1
+    b = io.BytesIO(); Image.fromarray(_test_image(128, 96)).save(b, "JPEG", quality=90, restart_marker_blocks=3)
+    assert np.array_equal(host.decode_image(b.getvalue()), np.asarray(Image.open(io.BytesIO(b.getvalue())).convert("RGBA")))
+    assert cases == 48
+    with pytest.raises(host.HostError):
+        host.decode_image(b.getvalue()[:200])          # truncated stream: error, not garbage
+
+
+def test_skybox_directory_loader(tmp_path):
+    """cubumap.rs:29-50,86-106: six .png/.jpg files, sorted by face name or alias; anything else is an error."""
+    Image = pytest.importorskip("PIL.Image")
+    names = ["right.png", "negx.jpg", "top.png", "negy.png", "posz.jpg", "back.png"]          # mixed aliases / formats
+    want = []
+    for i, n in enumerate(names):
+        a = _test_image(32, 32, seed=i)
+        Image.fromarray(a).save(tmp_path / n, quality=95)
+        want.append(np.asarray(Image.open(tmp_path / n).convert("RGBA")))
+    (tmp_path / "readme.txt").write_text("ignored")
+    faces = host.load_skybox_dir(tmp_path)
+    assert len(faces) == 6 and all(np.array_equal(f, w) for f, w in zip(faces, want))
+    (tmp_path / "extra.png").write_bytes((tmp_path / "top.png").read_bytes())
+    with pytest.raises(host.HostError):
+        host.load_skybox_dir(tmp_path)                  # 7 images: resource_manager::load_cubemap asserts len == 6
+    ref_dir = Path("/root/reference/assets/skyboxs/Yokohama")
+    if ref_dir.is_dir():                                # the reference's own skybox (absent on the GPU box)
+        faces = host.load_skybox_dir(ref_dir)
+        for f, n in zip(faces, ("posx", "negx", "posy", "negy", "posz", "negz")):
+            assert np.array_equal(f, np.asarray(Image.open(ref_dir / f"{n}.jpg").convert("RGBA"))), n
