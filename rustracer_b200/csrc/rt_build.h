@@ -179,6 +179,19 @@ RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, c
         const int2 c = bin_children[ch[best]];
         ch[best] = (uint32_t)c.x; ch[nch++] = (uint32_t)c.y;
     }
+    // spare slots are free to test (the node test always does 8 boxes): split multi-primitive leaf slots further,
+    // largest first, so that each primitive sits in the tightest box the node can give it
+    while (nch < 8) {
+        int best = -1; float best_area = -1.0f;
+        for (int i = 0; i < nch; ++i) {
+            if (ch[i] >= (uint32_t)(n - 1) || count_of(ch[i]) > RT_LEAF_MAX) continue;   // single primitive / inner child
+            const float a = aabb_half_area(bin_box[ch[i]]);
+            if (a > best_area) { best_area = a; best = i; }
+        }
+        if (best < 0) break;
+        const int2 c = bin_children[ch[best]];
+        ch[best] = (uint32_t)c.x; ch[nch++] = (uint32_t)c.y;
+    }
     const DAabb box = (n == 1) ? bin_box[0] : bin_box[bin];
     // slot assignment: slot s is visited first by rays travelling in the negative direction of the axes whose bit
     // is set in s, so it should hold the child lying furthest towards +axis on those axes (greedy max-cost matching)
