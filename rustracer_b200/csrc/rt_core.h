@@ -175,7 +175,7 @@ static void pack_tris(rt_scene* s, uint32_t g) {
         const float* p0 = verts[pi.v_offset + indices[io]].position; const float* p1 = verts[pi.v_offset + indices[io + 1]].position; const float* p2 = verts[pi.v_offset + indices[io + 2]].position;
         tris[k * RT_TRI_F4 + 0] = make_float4(p0[0], p0[1], p0[2], rt_uint_as_float(prim));
         tris[k * RT_TRI_F4 + 1] = make_float4(p1[0], p1[1], p1[2], 0.0f);
-        tris[k * RT_TRI_F4 + 2] = make_float4(p2[0], p2[1], p2[2], 0.0f);
+        tris[k * RT_TRI_F4 + 2] = make_float4(p2[0], p2[1], p2[2], rt_uint_as_float(prim));      // .w: tie-break rank inside this BLAS
         DAabb b;
         for (int a = 0; a < 3; ++a) { b.lo[a] = fminf(p0[a], fminf(p1[a], p2[a])); b.hi[a] = fmaxf(p0[a], fmaxf(p1[a], p2[a])); }
         lb[k] = b;
@@ -205,7 +205,7 @@ static void pack_merged(rt_scene* s) {
         f3 a, b, c; baked_triangle(verts, indices, prims, w2o, o2w, sp, a, b, c);
         tris[k * RT_TRI_F4 + 0] = make_float4(a.x, a.y, a.z, rt_uint_as_float(sp.y));
         tris[k * RT_TRI_F4 + 1] = make_float4(b.x, b.y, b.z, rt_uint_as_float(sp.x));
-        tris[k * RT_TRI_F4 + 2] = make_float4(c.x, c.y, c.z, 0.0f);
+        tris[k * RT_TRI_F4 + 2] = make_float4(c.x, c.y, c.z, rt_uint_as_float(order[k]));   // .w: rank of (instance, primitive): bake_src is sorted by it
         DAabb bb;
         bb.lo[0] = fminf(a.x, fminf(b.x, c.x)); bb.lo[1] = fminf(a.y, fminf(b.y, c.y)); bb.lo[2] = fminf(a.z, fminf(b.z, c.z));
         bb.hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)); bb.hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)); bb.hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));

@@ -208,6 +208,9 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 #define RT_REFILL_BELOW 22     // refill when fewer than this many lanes still hold a ray
 #endif
 #define RT_WARPS_PER_BLOCK (RT_EXTEND_THREADS / 32)
+#ifndef RT_TQ_ATOMIC_TAIL
+#define RT_TQ_ATOMIC_TAIL 1
+#endif
 #ifndef RT_TQ_PUSH_MAX
 #define RT_TQ_PUSH_MAX 7        // triangles a lane may queue per iteration (the rest stay parked in its tgroup)
 #endif
@@ -216,10 +219,12 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 
 struct CoopShared {            // one per warp; SoA over the 32 owner lanes
     float ox[32], oy[32], oz[32], Sx[32], Sy[32], Sz[32], tmin[32], tmax[32], cur_t[32], u[32], v[32];
-    unsigned long long best_ip[32];          // (instance << 32 | primitive) of the best candidate: lexicographic tie-break
-    uint32_t kxyz[32], best_t[32], done[32];
+    unsigned long long best_ip[32];          // (ordered t << 32 | rank) of the best candidate of this round
+    unsigned long long win_ip[32];           // its (instance << 32 | primitive)
+    uint32_t kxyz[32], done[32];
     uint32_t inst[32], geo[32], alpha[32], rng[4][32];   // inst: 0xFFFFFFFF = merged BLAS (instance id in the triangle record)
     uint32_t items[RT_TQ_CAP];
+    uint32_t tail;                           // total items ever appended (RT_TQ_ATOMIC_TAIL)
 };
 
 template <bool ALPHA>
@@ -240,9 +245,11 @@ RT_D void coop_publish_ray(const Trav& tv, CoopShared& sh, uint32_t lane) {
 template <int MODE, bool ALPHA, bool COUNT>
 RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, uint32_t n, uint32_t lane, uint32_t& outstanding, bool usable, bool& terminated,
                      unsigned long long* c4) {
-    sh.best_t[lane] = 0xFFFFFFFFu; sh.best_ip[lane] = ~0ull; sh.done[lane] = 0u;
+    // winner per owner = lexicographic minimum of (t, instance, primitive).  One 64-bit shared-memory atomicMin on
+    // (ordered t << 32 | rank) decides it: rank (triangle record .w) orders the triangles of a BLAS by (instance, primitive)
+    sh.best_ip[lane] = ~0ull; sh.done[lane] = 0u;
     __syncwarp();
-    bool hit = false; float tt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t owner = 0, key = 0; unsigned long long ip = 0;
+    bool hit = false; float tt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t owner = 0; unsigned long long key = 0, ip = 0;
     if (lane < n) {
         const uint32_t item = sh.items[(head + lane) & (RT_TQ_CAP - 1u)];
         owner = item >> RT_TQ_TRI_BITS;
@@ -267,20 +274,18 @@ RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, u
                 if (anyhit_ignore(S, inst, prim, geo, bu, bv, rng)) hit = false;
             }
         }
-        if (hit) { key = float_to_ordered(tt); atomicMin(&sh.best_t[owner], key); }
+        if (hit) { key = ((unsigned long long)float_to_ordered(tt) << 32) | rt_float_as_uint(c.w); atomicMin(&sh.best_ip[owner], key); }
         atomicAdd(&sh.done[owner], 1u);
     }
     __syncwarp();
-    if (hit && key == sh.best_t[owner]) atomicMin(&sh.best_ip[owner], ip);
-    __syncwarp();
-    if (hit && key == sh.best_t[owner] && ip == sh.best_ip[owner]) { sh.u[owner] = bu; sh.v[owner] = bv; }
+    if (hit && key == sh.best_ip[owner]) { sh.u[owner] = bu; sh.v[owner] = bv; sh.win_ip[owner] = ip; }
     __syncwarp();
     const uint32_t d = sh.done[lane];
     if (d) {
         outstanding -= d;
-        if (usable && sh.best_t[lane] != 0xFFFFFFFFu) {
-            const float ct = ordered_to_float(sh.best_t[lane]);
-            const uint32_t ci = (uint32_t)(sh.best_ip[lane] >> 32), cp = (uint32_t)sh.best_ip[lane];
+        if (usable && sh.best_ip[lane] != ~0ull) {
+            const float ct = ordered_to_float((uint32_t)(sh.best_ip[lane] >> 32));
+            const uint32_t ci = (uint32_t)(sh.win_ip[lane] >> 32), cp = (uint32_t)sh.win_ip[lane];
             if (trav_candidate_wins(tv, ct, ci, cp)) {
                 trav_commit(tv, ct, sh.u[lane], sh.v[lane], ci, cp);
                 sh.cur_t[lane] = ct;
@@ -304,6 +309,8 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
     bool active = false, exhausted = false;
     uint32_t idx = 0, outstanding = 0;          // outstanding: this lane's items still in the queue
     uint32_t q_head = 0, q_count = 0;           // warp-uniform queue cursor
+    if (lane == 0) sh.tail = 0u;
+    __syncwarp();
     for (;;) {
         if (!exhausted) {
             const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && outstanding == 0u);
@@ -361,6 +368,22 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             }
             // append this iteration's leaf triangles to the warp queue
             const uint32_t k = (uint32_t)__popc(leaf_mask);
+#if RT_TQ_ATOMIC_TAIL
+            // queue positions from one shared-memory atomic per pushing lane (item order inside the queue is irrelevant:
+            // hit resolution is order-independent) instead of a 5-step shuffle scan
+            if (k) {
+                uint32_t pos = atomicAdd(&sh.tail, k);
+                outstanding += k;
+                while (leaf_mask) {
+                    const int bit = 31 - __clz((int)leaf_mask);
+                    leaf_mask &= ~(1u << bit);
+                    sh.items[pos & (RT_TQ_CAP - 1u)] = (lane << RT_TQ_TRI_BITS) | (leaf_base + (uint32_t)bit);
+                    ++pos;
+                }
+            }
+            __syncwarp();
+            q_count = sh.tail - q_head;
+#else
             uint32_t incl = k;
 #pragma unroll
             for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if ((int)lane >= dd) incl += nn; }
@@ -376,6 +399,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                 }
             }
             q_count += pushed;
+#endif
             const bool flush = __any_sync(0xFFFFFFFFu, want_flush);
             __syncwarp();
             while (q_count >= 32u || (flush && q_count)) {
