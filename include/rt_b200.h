@@ -250,6 +250,28 @@ void rt_context_destroy(rt_context* ctx);
 /* replaces BaseApp::recreate_swapchain (app/src/lib.rs:355-385): drops the accumulation */
 int rt_frame_resize(rt_context* ctx, uint32_t width, uint32_t height);
 
+/* replaces InFlightFrames (app/src/lib.rs:34 IN_FLIGHT_FRAMES = 2, :329, :400-401 per-frame fence) and the
+   per-swapchain-image storage images beside the single accumulation image (app/src/lib.rs:305-325).
+   n = 1 (default): rt_render runs in strict order on the stream it is given.
+   n = 2..4: every rt_render call gets its own slot (private stream, path-state / hit / shadow queues,
+   frame radiance and RGBA8 output image); the path tracing of up to n frames overlaps on the GPU (the thin
+   tails of one frame's late bounces fill with the next frame's rays) while the accumulate+tonemap steps
+   run in submission order on the one shared accumulation image, so the images are bit-identical to n = 1.
+   A frame starts after everything queued on rt_render's `stream` at the time of the call.  The library's
+   own consumers (rt_readback, rt_tonemap, rt_reduce_peers, rt_last_frame_stats, rt_synchronize, the
+   rt_scene_update_* calls, rt_frame_resize) wait for the frames in flight; work of your own on another
+   stream must call rt_join first.  Keeps the accumulation image; synchronises. */
+int rt_context_set_frames_in_flight(rt_context* ctx, uint32_t n);
+/* makes `stream` (NULL = the context's) wait, on the device, for every frame submitted so far */
+int rt_join(rt_context* ctx, void* stream);
+/* presentation of the frame submitted last (the storage image -> swapchain copy of app/src/lib.rs:563-611
+   recorded in the same command buffer as the frame): queues the RGBA8 image's device->host copy behind that
+   frame on its slot and returns the frame's ticket.  out_rgba8 should be pinned and must stay untouched until
+   rt_frame_wait(ticket) returned (the in-flight fence wait, app/src/lib.rs:401); frames in flight need
+   distinct host buffers. */
+int rt_readback_async(rt_context* ctx, uint8_t* out_rgba8, uint64_t* ticket);
+int rt_frame_wait(rt_context* ctx, uint64_t ticket);
+
 /* replaces create_global + Buffers::new (asset_loader/src/globals.rs:309,43), create_as
    (acceleration_structures.rs:79-129), create_pipeline + SBT (gltf_viewer/src/pipeline_res.rs:21),
    create_descriptor_sets (desc_sets.rs:21) and the initial ComputeUnit::dispatch (main.rs:85-91) */
@@ -270,7 +292,8 @@ int rt_scene_set_skybox(rt_scene* scene, const uint8_t* const faces[6], uint32_t
 
 /* replaces ubo_buffer.copy_data_to_buffer + bind_* + trace_rays (main.rs:239,254-267): one frame of
    ubo->number_of_samples spp at ubo->number_of_bounces depth, accumulated per RayTracing.rgen:132-166.
-   opts may be NULL.  stream is a cudaStream_t or NULL (context's own stream).  Asynchronous. */
+   opts may be NULL.  stream is a cudaStream_t or NULL (context's own stream).  Asynchronous.
+   With frames in flight (rt_context_set_frames_in_flight) the frame runs on its slot's stream. */
 int rt_render(rt_context* ctx, rt_scene* scene, const rt_ubo* ubo, const rt_render_opts* opts,
               void* stream);
 /* accumulate+tonemap only (RayTracing.rgen:132-166 tail) over the current accumulation image;

@@ -60,6 +60,24 @@ class Context:
         opts = F.rt_render_opts(flags, strip_rows, n_parts, part)
         self.api.check(self.api.rt_render(self._h, scene._h, C.byref(ubo), C.byref(opts), stream))
 
+    def set_frames_in_flight(self, n: int):
+        """InFlightFrames of the reference (app/src/lib.rs:34): up to n rt_render calls overlap on the GPU; the
+        accumulation stays in submission order, so images are bit-identical to n = 1."""
+        self.api.check(self.api.rt_context_set_frames_in_flight(self._h, n))
+
+    def join(self, stream=None):
+        self.api.check(self.api.rt_join(self._h, stream))
+
+    def readback_async(self, out_buf: np.ndarray) -> int:
+        """Queues the device->host copy of the last submitted frame's RGBA8 image; returns its ticket."""
+        assert out_buf.dtype == np.uint8 and out_buf.size == self.width * self.height * 4 and out_buf.flags.c_contiguous
+        t = C.c_uint64()
+        self.api.check(self.api.rt_readback_async(self._h, out_buf.ctypes.data_as(F.c_u8p), C.byref(t)))
+        return int(t.value)
+
+    def frame_wait(self, ticket: int):
+        self.api.check(self.api.rt_frame_wait(self._h, ticket))
+
     def tonemap(self, ubo: F.rt_ubo, stream=None):
         self.api.check(self.api.rt_tonemap(self._h, C.byref(ubo), stream))
 

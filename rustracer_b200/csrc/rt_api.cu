@@ -73,7 +73,7 @@ int rt_ipc_export(rt_context* c, void* handle64) {
     if (!c || !handle64) return fail("rt_ipc_export: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
     cudaIpcMemHandle_t h;
-    if (chk(cudaIpcGetMemHandle(&h, c->fb.acc))) return fail(std::string("rt_ipc_export: ") + rt_platform_error());
+    if (chk(cudaIpcGetMemHandle(&h, c->acc))) return fail(std::string("rt_ipc_export: ") + rt_platform_error());
     memcpy(handle64, &h, 64);
     return 0;
 }
@@ -103,8 +103,10 @@ int rt_reduce_peers(rt_context* c, void* const* peer_acc, uint32_t n_peers, cons
     if (end == begin) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     size_t blocks = (end - begin + 255) / 256; const size_t cap = (size_t)g_rt_sm_count * 8; if (blocks > cap) blocks = cap;
-    reduce_peers_kernel<<<(unsigned)blocks, 256, 0, st>>>(c->fb.acc, c->fb.out, pp, n_peers, *ubo, begin, end);
+    join_frames(c, st);          // frames still in flight on this context accumulate first
+    reduce_peers_kernel<<<(unsigned)blocks, 256, 0, st>>>(c->acc, c->slot[c->cur].fb.out, pp, n_peers, *ubo, begin, end);
     ++g_rt_launch_count;
+    c->last_stream = st; consumer_ran(c, st);
     if (cudaPeekAtLastError() != cudaSuccess) return fail(std::string("rt_reduce_peers: ") + rt_platform_error());
     return 0;
 }

@@ -60,22 +60,38 @@ struct StageEvent { int stage; rt_timer a, b; };
 }  // namespace rtcore
 using namespace rtcore;
 
-struct rt_context {
-    int device = 0;
-    rt_stream_t stream = nullptr;
-    rt_stream_t last_stream = nullptr;   // stream of the most recent rt_render / rt_tonemap (may be caller-provided)
-    uint32_t width = 0, height = 0;
-    FrameBuffers fb{};
+#define RT_MAX_FRAMES_IN_FLIGHT 4
+
+// One frame in flight: everything a frame writes except the shared accumulation image.  Mirrors the reference's
+// InFlightFrames (app/src/lib.rs:34,329,400-401: IN_FLIGHT_FRAMES = 2, one fence per frame) and its per-swapchain-image
+// storage images next to the single acc_images[0] (app/src/lib.rs:305-325).
+struct FrameSlot {
+    rt_stream_t stream = nullptr;        // private stream of the slot (unused while the context has a single slot)
+    FrameBuffers fb{};                   // fb.acc aliases rt_context::acc
     DQueue q[2]{};
     DHits hits{};
     DShadowQueue sq{};
     uint32_t* counters = nullptr; size_t counters_cap = 0;   // qcount | scount | fetch_extend | fetch_shadow
     RtCounters* dev_cnt = nullptr;
-    // last frame
+    // last frame rendered on this slot
     uint32_t last_S = 0, last_B = 0; uint64_t last_pixels = 0; bool last_counted = false; bool last_valid = false;
-    rt_timer ev_begin, ev_end; bool timers = false;
+    rt_timer ev_begin, ev_end;
     std::vector<StageEvent> stage_events; size_t stage_used = 0;
     unsigned long long launches_before = 0, launches_after = 0;
+    rt_event done; bool pending = false;   // recorded after the last operation queued for this slot
+};
+
+struct rt_context {
+    int device = 0;
+    rt_stream_t stream = nullptr;
+    rt_stream_t last_stream = nullptr;   // stream of the most recent rt_render / rt_tonemap (may be caller-provided)
+    uint32_t width = 0, height = 0;
+    float4* acc = nullptr;               // RGBA32F accumulation image shared by all slots (RayTracing.rgen:18)
+    FrameSlot slot[RT_MAX_FRAMES_IN_FLIGHT];
+    uint32_t n_slots = 1, cur = 0;       // cur: slot of the most recently submitted frame
+    uint64_t frame_seq = 0;              // frames submitted so far (ticket of the next frame)
+    rt_event ev_submit, ev_acc, ev_consumer; bool acc_pending = false, consumer_pending = false;
+    bool timers = false;
     std::vector<void*> ipc_opened;
 };
 
@@ -114,26 +130,44 @@ struct rt_scene {
 
 namespace rtcore {
 
-static void free_frame(rt_context* c) {
-    void* ptrs[] = {c->fb.acc, c->fb.out, c->fb.rad, c->fb.aux, c->fb.pixrng, c->hits.tuvp, c->hits.inst, c->sq.o_tmax, c->sq.d_pix, c->sq.contrib,
-                    c->q[0].o_tmin, c->q[0].d_tmax, c->q[0].thr_pix, c->q[0].rng, c->q[1].o_tmin, c->q[1].d_tmax, c->q[1].thr_pix, c->q[1].rng};
+static void free_slot(FrameSlot* f) {
+    void* ptrs[] = {f->fb.out, f->fb.rad, f->fb.aux, f->fb.pixrng, f->hits.tuvp, f->hits.inst, f->sq.o_tmax, f->sq.d_pix, f->sq.contrib,
+                    f->q[0].o_tmin, f->q[0].d_tmax, f->q[0].thr_pix, f->q[0].rng, f->q[1].o_tmin, f->q[1].d_tmax, f->q[1].thr_pix, f->q[1].rng};
     for (void* p : ptrs) if (p) rt_free(p);
-    c->fb = FrameBuffers{}; c->hits = DHits{}; c->sq = DShadowQueue{}; c->q[0] = DQueue{}; c->q[1] = DQueue{};
+    f->fb = FrameBuffers{}; f->hits = DHits{}; f->sq = DShadowQueue{}; f->q[0] = DQueue{}; f->q[1] = DQueue{};
+    f->last_valid = false; f->pending = false;
+}
+static void free_frame(rt_context* c) {
+    for (uint32_t k = 0; k < RT_MAX_FRAMES_IN_FLIGHT; ++k) free_slot(&c->slot[k]);
+    if (c->acc) rt_free(c->acc);
+    c->acc = nullptr;
 }
 
+static int alloc_slot(rt_context* c, FrameSlot* f, size_t n) {
+    int e = 0;
+    e |= dev_alloc(&f->fb.out, n); e |= dev_alloc(&f->fb.rad, n); e |= dev_alloc(&f->fb.aux, n); e |= dev_alloc(&f->fb.pixrng, n);
+    e |= dev_alloc(&f->hits.tuvp, n); e |= dev_alloc(&f->hits.inst, n);
+    e |= dev_alloc(&f->sq.o_tmax, n); e |= dev_alloc(&f->sq.d_pix, n); e |= dev_alloc(&f->sq.contrib, n);
+    for (int k = 0; k < 2; ++k) { e |= dev_alloc(&f->q[k].o_tmin, n); e |= dev_alloc(&f->q[k].d_tmax, n); e |= dev_alloc(&f->q[k].thr_pix, n); e |= dev_alloc(&f->q[k].rng, n); }
+    if (!f->dev_cnt) { e |= dev_alloc(&f->dev_cnt, 1); if (!e) rt_memset(f->dev_cnt, 0, sizeof(RtCounters), c->stream); }
+    if (e) return 1;
+    f->fb.acc = c->acc;
+    rt_memset(f->fb.out, 0, n * 4, c->stream);
+    rt_memset(f->fb.rad, 0, n * sizeof(float4), c->stream); rt_memset(f->fb.aux, 0, n * sizeof(float2), c->stream);
+    if (!f->stream && rt_stream_create(&f->stream)) return 1;
+    f->done.create(); f->ev_begin.create(); f->ev_end.create();
+    return 0;
+}
+
+// (re)allocates the accumulation image and n_slots frame slots; the caller has synchronised the context
 static int alloc_frame(rt_context* c, uint32_t w, uint32_t h) {
     free_frame(c);
     const size_t n = (size_t)w * h;
-    int e = 0;
-    e |= dev_alloc(&c->fb.acc, n); e |= dev_alloc(&c->fb.out, n); e |= dev_alloc(&c->fb.rad, n); e |= dev_alloc(&c->fb.aux, n); e |= dev_alloc(&c->fb.pixrng, n);
-    e |= dev_alloc(&c->hits.tuvp, n); e |= dev_alloc(&c->hits.inst, n);
-    e |= dev_alloc(&c->sq.o_tmax, n); e |= dev_alloc(&c->sq.d_pix, n); e |= dev_alloc(&c->sq.contrib, n);
-    for (int k = 0; k < 2; ++k) { e |= dev_alloc(&c->q[k].o_tmin, n); e |= dev_alloc(&c->q[k].d_tmax, n); e |= dev_alloc(&c->q[k].thr_pix, n); e |= dev_alloc(&c->q[k].rng, n); }
-    if (e) { free_frame(c); return 1; }
-    rt_memset(c->fb.acc, 0, n * sizeof(float4), c->stream); rt_memset(c->fb.out, 0, n * 4, c->stream);
-    rt_memset(c->fb.rad, 0, n * sizeof(float4), c->stream); rt_memset(c->fb.aux, 0, n * sizeof(float2), c->stream);
-    c->width = w; c->height = h; c->last_valid = false;
-    return 0;
+    if (dev_alloc(&c->acc, n)) return 1;
+    rt_memset(c->acc, 0, n * sizeof(float4), c->stream);
+    for (uint32_t k = 0; k < c->n_slots; ++k) if (alloc_slot(c, &c->slot[k], n)) { free_frame(c); return 1; }
+    c->width = w; c->height = h; c->cur = 0; c->acc_pending = false; c->consumer_pending = false;
+    return rt_stream_sync(c->stream);
 }
 
 static void update_ds(rt_scene* s) {
@@ -381,11 +415,22 @@ static uint32_t owned_rows(const TilePart& tp) {
 static int sync_all(rt_context* c) {
     int e = 0;
     if (c->last_stream && c->last_stream != c->stream) e |= rt_stream_sync(c->last_stream);
+    if (c->n_slots > 1) for (uint32_t k = 0; k < c->n_slots; ++k) if (c->slot[k].stream) e |= rt_stream_sync(c->slot[k].stream);
     e |= rt_stream_sync(c->stream);
     return e;
 }
+// device-side join: `st` waits for every frame submitted so far (no host block)
+static void join_frames(rt_context* c, rt_stream_t st) {
+    if (c->n_slots <= 1) return;
+    for (uint32_t k = 0; k < c->n_slots; ++k) if (c->slot[k].pending && c->slot[k].stream != st) c->slot[k].done.wait(st);
+}
+// a consumer of the accumulation image ran on `st`: later frames must not accumulate before it
+static void consumer_ran(rt_context* c, rt_stream_t st) {
+    if (c->n_slots <= 1) return;
+    c->ev_consumer.record(st); c->consumer_pending = true;
+}
 
-static StageEvent* stage_begin(rt_context* c, bool on, int stage, rt_stream_t st) {
+static StageEvent* stage_begin(FrameSlot* c, bool on, int stage, rt_stream_t st) {
     if (!on) return nullptr;
     if (c->stage_used == c->stage_events.size()) { StageEvent e; e.stage = stage; e.a.create(); e.b.create(); c->stage_events.push_back(e); }
     StageEvent* e = &c->stage_events[c->stage_used++];
@@ -396,32 +441,38 @@ static void stage_end(StageEvent* e, rt_stream_t st) { if (e) e->b.record(st); }
 
 #ifndef RT_EMU
 static inline unsigned persistent_grid(int blocks_per_sm) { return (unsigned)((g_rt_sm_count > 0 ? g_rt_sm_count : 148) * blocks_per_sm); }
+// traversal kernels: blocks per SM of the persistent grid (RT_B200_TRACE_BLOCKS overrides; experiments only)
+static inline unsigned trace_grid() {
+    static int bps = -1;
+    if (bps < 0) { const char* e = getenv("RT_B200_TRACE_BLOCKS"); bps = e ? atoi(e) : 8; if (bps < 1) bps = 1; }
+    return persistent_grid(bps);
+}
 #endif
 
 template <bool ALPHA, bool COUNT>
-static void launch_extend(rt_context* c, const DScene& S, const FrameParams& P, const DQueue& q, const uint32_t* count, uint32_t* fetch, uint32_t max_count, rt_stream_t st) {
+static void launch_extend(FrameSlot* c, const DScene& S, const FrameParams& P, const DQueue& q, const uint32_t* count, uint32_t* fetch, uint32_t max_count, rt_stream_t st) {
 #ifdef RT_EMU
     const uint32_t n = *count;
     for (uint32_t i = 0; i < n; ++i) extend_item<ALPHA, COUNT>(S, P, q, c->hits, i, c->dev_cnt);
     (void)fetch; (void)max_count; (void)st;
 #else
-    extend_kernel<ALPHA, COUNT><<<persistent_grid(8), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
+    extend_kernel<ALPHA, COUNT><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
     ++g_rt_launch_count; (void)max_count;
 #endif
 }
 template <bool ALPHA, bool COUNT>
-static void launch_shadow(rt_context* c, const DScene& S, const FrameParams& P, const uint32_t* count, uint32_t* fetch, rt_stream_t st) {
+static void launch_shadow(FrameSlot* c, const DScene& S, const FrameParams& P, const uint32_t* count, uint32_t* fetch, rt_stream_t st) {
 #ifdef RT_EMU
     const uint32_t n = *count;
     for (uint32_t i = 0; i < n; ++i) shadow_item<ALPHA, COUNT>(S, P, c->fb, c->sq, i, c->dev_cnt);
     (void)fetch; (void)st;
 #else
-    shadow_kernel<ALPHA, COUNT><<<persistent_grid(8), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
+    shadow_kernel<ALPHA, COUNT><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
     ++g_rt_launch_count;
 #endif
 }
 template <bool SIMPLE, bool COUNT>
-static void launch_shade(rt_context* c, const DScene& S, const FrameParams& P, const DQueue& qin, const DQueue& qout, const uint32_t* count, uint32_t* out_count,
+static void launch_shade(FrameSlot* c, const DScene& S, const FrameParams& P, const DQueue& qin, const DQueue& qout, const uint32_t* count, uint32_t* out_count,
                          uint32_t* shadow_count, uint32_t bounce, rt_stream_t st) {
 #ifdef RT_EMU
     const uint32_t n = *count;
@@ -443,7 +494,7 @@ static void launch_shade(rt_context* c, const DScene& S, const FrameParams& P, c
 }
 
 template <bool ALPHA, bool COUNT>
-static int render_frame(rt_context* c, rt_scene* s, const FrameParams& P0, const TilePart& tp, uint32_t flags, rt_stream_t st) {
+static int render_frame(rt_context* ctx, FrameSlot* c, rt_scene* s, const FrameParams& P0, const TilePart& tp, uint32_t flags, rt_stream_t st) {
     FrameParams P = P0;
     const uint32_t S = P.ubo.number_of_samples, B = P.ubo.number_of_bounces;
     const uint32_t n_local = owned_rows(tp) * tp.width;
@@ -488,12 +539,15 @@ static int render_frame(rt_context* c, rt_scene* s, const FrameParams& P0, const
     }
     {
         const FrameParams Pk = P; const bool no_trace = (S == 0);
+        // frames in flight trace concurrently but accumulate in submission order on the shared image
+        if (ctx->n_slots > 1 && ctx->acc_pending) ctx->ev_acc.wait(st);
         StageEvent* ev = stage_begin(c, timing, 4, st);
         rt_launch(n_local, st, RT_LAMBDA(size_t i) {
             if (no_trace) { const uint32_t pixel = local_to_pixel(tp, (uint32_t)i); fb.rad[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); fb.aux[pixel] = make_float2(0.0f, 0.0f); }
             accumulate_item(Pk, tp, fb, (uint32_t)i, false);
         });
         stage_end(ev, st);
+        if (ctx->n_slots > 1) { ctx->ev_acc.record(st); ctx->acc_pending = true; }
     }
     c->last_S = S; c->last_B = B; c->last_pixels = (uint64_t)n_local * S; c->last_counted = COUNT; c->last_valid = true;
     return 0;
@@ -515,6 +569,8 @@ const char* RT_API(rt_version)(void) {
 #endif
 }
 
+void RT_API(rt_context_destroy)(rt_context* c);
+
 int RT_API(rt_context_create)(int device, uint32_t width, uint32_t height, rt_context** out) {
     if (!out || !width || !height) return fail("rt_context_create: bad arguments");
     rt_context* c = new rt_context();
@@ -526,25 +582,28 @@ int RT_API(rt_context_create)(int device, uint32_t width, uint32_t height, rt_co
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail("rt_context_create: cudaSetDevice failed"); }
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); g_rt_sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("rt_context_create: stream creation failed"); }
-    c->ev_begin.create(); c->ev_end.create(); c->timers = true;
+    c->timers = true;
 #endif
-    if (dev_alloc(&c->dev_cnt, 1) || alloc_frame(c, width, height)) { delete c; return fail(std::string("rt_context_create: allocation failed: ") + rt_platform_error()); }
-    rt_memset(c->dev_cnt, 0, sizeof(RtCounters), c->stream);
-    rt_stream_sync(c->stream);
+    c->ev_submit.create(); c->ev_acc.create(); c->ev_consumer.create();
+    if (alloc_frame(c, width, height)) { RT_API(rt_context_destroy)(c); return fail(std::string("rt_context_create: allocation failed: ") + rt_platform_error()); }
     *out = c;
     return 0;
 }
 
 void RT_API(rt_context_destroy)(rt_context* c) {
     if (!c) return;
-    rt_stream_sync(c->stream);
+    sync_all(c);
     free_frame(c);
-    if (c->counters) rt_free(c->counters);
-    if (c->dev_cnt) rt_free(c->dev_cnt);
-    for (auto& e : c->stage_events) { e.a.destroy(); e.b.destroy(); }
+    for (FrameSlot& f : c->slot) {
+        if (f.counters) rt_free(f.counters);
+        if (f.dev_cnt) rt_free(f.dev_cnt);
+        for (auto& e : f.stage_events) { e.a.destroy(); e.b.destroy(); }
+        f.ev_begin.destroy(); f.ev_end.destroy(); f.done.destroy();
+        rt_stream_destroy(f.stream);
+    }
+    c->ev_submit.destroy(); c->ev_acc.destroy(); c->ev_consumer.destroy();
 #ifndef RT_EMU
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
-    c->ev_begin.destroy(); c->ev_end.destroy();
     if (c->stream) cudaStreamDestroy(c->stream);
 #endif
     delete c;
@@ -557,9 +616,31 @@ int RT_API(rt_frame_resize)(rt_context* c, uint32_t width, uint32_t height) {
     return 0;
 }
 
+int RT_API(rt_context_set_frames_in_flight)(rt_context* c, uint32_t n) {
+    if (!c) return fail("rt_context_set_frames_in_flight: null context");
+    if (n < 1 || n > RT_MAX_FRAMES_IN_FLIGHT) return fail("rt_context_set_frames_in_flight: n must be 1..4");
+    if (n == c->n_slots) return 0;
+#ifndef RT_EMU
+    cudaSetDevice(c->device);
+#endif
+    if (sync_all(c)) return fail(std::string("rt_context_set_frames_in_flight: ") + rt_platform_error());
+    // the accumulation image is kept; slots beyond the old count are allocated, surplus ones released
+    const size_t npx = (size_t)c->width * c->height;
+    if (c->cur >= n) {   // the image of the last frame must stay readable from the slot rt_readback looks at
+        rt_d2d(c->slot[0].fb.out, c->slot[c->cur].fb.out, npx * 4, c->stream);
+        rt_stream_sync(c->stream);
+        c->slot[0].last_valid = false; c->cur = 0;
+    }
+    for (uint32_t k = n; k < c->n_slots; ++k) free_slot(&c->slot[k]);
+    for (uint32_t k = c->n_slots; k < n; ++k)
+        if (alloc_slot(c, &c->slot[k], npx)) { for (uint32_t j = c->n_slots; j <= k; ++j) free_slot(&c->slot[j]); return fail(std::string("rt_context_set_frames_in_flight: allocation failed: ") + rt_platform_error()); }
+    c->n_slots = n;
+    return rt_stream_sync(c->stream) ? fail(std::string("rt_context_set_frames_in_flight: ") + rt_platform_error()) : 0;
+}
+
 void RT_API(rt_scene_destroy)(rt_scene* s) {
     if (!s) return;
-    rt_stream_sync(s->ctx->stream);
+    sync_all(s->ctx);
     void* ptrs[] = {s->d_vin, s->d_vout, s->d_indices, s->d_prim, s->d_mat, s->d_skins, s->d_dl, s->d_pl, s->d_images, s->d_textures, s->d_lut,
                     s->d_blas_nodes, s->d_tris, s->d_node_box, s->d_node_parent, s->d_prim_order, s->d_leaf_boxes, s->d_prim_boxes, s->d_pending,
                     s->d_tlas_nodes, s->d_tlas_prims, s->d_tlas_box, s->d_tlas_parent, s->d_inst_boxes, s->d_inst_w2o, s->d_inst_o2w, s->d_inst_root, s->d_entry_rec, s->d_bake_src};
@@ -704,6 +785,7 @@ int RT_API(rt_scene_update_instances)(rt_scene* s, const rt_instance* inst, uint
     for (uint32_t i = 0; i < n; ++i) if (inst[i].geo_id >= s->geo.size()) return fail("rt_scene_update_instances: geo_id out of range");
     for (uint32_t i = 0; i < n; ++i) if (inst[i].geo_id != s->instances[i].geo_id) return fail("rt_scene_update_instances: geo_id of an instance may not change");
     s->instances.assign(inst, inst + n);
+    sync_all(s->ctx);            // frames in flight (or on a caller's stream) still read the structures rebuilt below
     rt_timer t0, t1; t0.create(); t1.create(); t0.record(s->ctx->stream);
     if (upload_instance_records(s)) { t0.destroy(); t1.destroy(); return 1; }
     if (s->merged.n_tris) refit_merged(s);        // baked instances moved: re-bake their triangles, refit the merged BLAS
@@ -718,6 +800,7 @@ int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_ski
     if (!s || (!mats && n_skins)) return fail("rt_scene_update_skins: null argument");
     if (n_skins != s->n_skins) return fail("rt_scene_update_skins: skin count differs from the scene's");
     rt_stream_t st = s->ctx->stream;
+    sync_all(s->ctx);            // frames in flight (or on a caller's stream) still read the vertices / BVH rewritten below
     rt_timer t0, t1, t2, t3; t0.create(); t1.create(); t2.create(); t3.create();
     RT_CHECK(rt_h2d(s->d_skins, mats, (size_t)n_skins * RT_MAX_JOINTS * 16 * 4, st), "skin upload");
     t0.record(st);
@@ -742,7 +825,7 @@ int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_ski
 int RT_API(rt_scene_update_lights)(rt_scene* s, const rt_light* dl, uint32_t ndl, const rt_light* pl, uint32_t npl) {
     if (!s) return fail("rt_scene_update_lights: null scene");
     rt_stream_t st = s->ctx->stream;
-    rt_stream_sync(st);
+    sync_all(s->ctx);
     if (ndl > s->cap_dl) { rt_free(s->d_dl); s->d_dl = nullptr; RT_CHECK(dev_alloc(&s->d_dl, ndl), "light allocation"); s->cap_dl = ndl; }
     if (npl > s->cap_pl) { rt_free(s->d_pl); s->d_pl = nullptr; RT_CHECK(dev_alloc(&s->d_pl, npl), "light allocation"); s->cap_pl = npl; }
     if (ndl) RT_CHECK(rt_h2d(s->d_dl, dl, (size_t)ndl * sizeof(rt_light), st), "light upload");
@@ -755,7 +838,7 @@ int RT_API(rt_scene_update_lights)(rt_scene* s, const rt_light* dl, uint32_t ndl
 int RT_API(rt_scene_set_skybox)(rt_scene* s, const uint8_t* const faces[6], uint32_t w, uint32_t h, uint32_t srgb) {
     if (!s || !faces || !w || !h) return fail("rt_scene_set_skybox: bad arguments");
     for (int f = 0; f < 6; ++f) if (!faces[f]) return fail("rt_scene_set_skybox: null face");
-    rt_stream_sync(s->ctx->stream);
+    sync_all(s->ctx);
     return upload_sky(s, faces, w, h, srgb);
 }
 
@@ -779,17 +862,28 @@ int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_re
             tp.strip_rows = opts->strip_rows; tp.n_parts = opts->n_parts; tp.part = opts->part;
         }
     }
+    // frames in flight: the frame runs on its slot's stream, after everything queued on `st` so far and after the
+    // last consumer of the accumulation image; with a single slot it runs on `st` itself (strict stream order)
+    const uint32_t k = (uint32_t)(c->frame_seq % c->n_slots);
+    FrameSlot* f = &c->slot[k];
+    if (c->n_slots > 1) {
+        c->ev_submit.record(st); c->ev_submit.wait(f->stream);
+        if (c->consumer_pending) c->ev_consumer.wait(f->stream);
+        st = f->stream;
+    }
 #ifndef RT_EMU
-    c->launches_before = g_rt_launch_count;
+    f->launches_before = g_rt_launch_count;
 #endif
-    if (c->timers) c->ev_begin.record(st);
+    if (c->timers) f->ev_begin.record(st);
     const bool alpha = !ubo->fully_opaque, count = (flags & RT_RENDER_COUNTERS) != 0;
     int e;
-    if (alpha) e = count ? render_frame<true, true>(c, s, P, tp, flags, st) : render_frame<true, false>(c, s, P, tp, flags, st);
-    else e = count ? render_frame<false, true>(c, s, P, tp, flags, st) : render_frame<false, false>(c, s, P, tp, flags, st);
-    if (c->timers) c->ev_end.record(st);
+    if (alpha) e = count ? render_frame<true, true>(c, f, s, P, tp, flags, st) : render_frame<true, false>(c, f, s, P, tp, flags, st);
+    else e = count ? render_frame<false, true>(c, f, s, P, tp, flags, st) : render_frame<false, false>(c, f, s, P, tp, flags, st);
+    if (c->timers) f->ev_end.record(st);
+    f->done.record(st); f->pending = true;
+    c->cur = k; ++c->frame_seq;
 #ifndef RT_EMU
-    c->launches_after = g_rt_launch_count;
+    f->launches_after = g_rt_launch_count;
     if (!e && cudaPeekAtLastError() != cudaSuccess) return fail(std::string("rt_render: launch failed: ") + rt_platform_error());
 #endif
     return e;
@@ -799,10 +893,12 @@ int RT_API(rt_tonemap)(rt_context* c, const rt_ubo* ubo, void* stream) {
     if (!c || !ubo) return fail("rt_tonemap: null argument");
     rt_stream_t st = stream ? (rt_stream_t)stream : c->stream;
     c->last_stream = st;
+    join_frames(c, st);
     FrameParams P; P.ubo = *ubo; P.width = c->width; P.height = c->height; P.sample = 0; P.clk = 0;
     TilePart tp; tp.width = c->width; tp.height = c->height; tp.strip_rows = 1; tp.n_parts = 1; tp.part = 0;
-    const FrameBuffers fb = c->fb;
+    const FrameBuffers fb = c->slot[c->cur].fb;
     rt_launch((size_t)c->width * c->height, st, RT_LAMBDA(size_t i) { accumulate_item(P, tp, fb, (uint32_t)i, true); });
+    consumer_ran(c, st);
     return 0;
 }
 
@@ -816,48 +912,75 @@ int RT_API(rt_readback)(rt_context* c, float* acc, uint8_t* out) {
     if (!c) return fail("rt_readback: null context");
     const size_t n = (size_t)c->width * c->height;
     if (sync_all(c)) return fail(std::string("rt_readback: ") + rt_platform_error());
-    if (acc) RT_CHECK(rt_d2h(acc, c->fb.acc, n * 16, c->stream), "rt_readback");
-    if (out) RT_CHECK(rt_d2h(out, c->fb.out, n * 4, c->stream), "rt_readback");
+    if (acc) RT_CHECK(rt_d2h(acc, c->acc, n * 16, c->stream), "rt_readback");
+    if (out) RT_CHECK(rt_d2h(out, c->slot[c->cur].fb.out, n * 4, c->stream), "rt_readback");
     if (rt_stream_sync(c->stream)) return fail(std::string("rt_readback: ") + rt_platform_error());
     return 0;
 }
 
 int RT_API(rt_upload_accumulation)(rt_context* c, const float* acc) {
     if (!c || !acc) return fail("rt_upload_accumulation: null argument");
-    RT_CHECK(rt_h2d(c->fb.acc, acc, (size_t)c->width * c->height * 16, c->stream), "rt_upload_accumulation");
+    if (sync_all(c)) return fail(std::string("rt_upload_accumulation: ") + rt_platform_error());
+    RT_CHECK(rt_h2d(c->acc, acc, (size_t)c->width * c->height * 16, c->stream), "rt_upload_accumulation");
     rt_stream_sync(c->stream);
     return 0;
 }
 
 int RT_API(rt_device_ptrs)(rt_context* c, void** acc, void** out) {
     if (!c) return fail("rt_device_ptrs: null context");
-    if (acc) *acc = c->fb.acc;
-    if (out) *out = c->fb.out;
+    if (acc) *acc = c->acc;
+    if (out) *out = c->slot[c->cur].fb.out;
+    return 0;
+}
+
+int RT_API(rt_join)(rt_context* c, void* stream) {
+    if (!c) return fail("rt_join: null context");
+    join_frames(c, stream ? (rt_stream_t)stream : c->stream);
+    return 0;
+}
+
+int RT_API(rt_readback_async)(rt_context* c, uint8_t* out, uint64_t* ticket) {
+    if (!c || !out) return fail("rt_readback_async: null argument");
+    if (c->frame_seq == 0) return fail("rt_readback_async: no frame submitted yet");
+    FrameSlot* f = &c->slot[c->cur];
+    rt_stream_t st = c->n_slots > 1 ? f->stream : (c->last_stream ? c->last_stream : c->stream);
+    RT_CHECK(rt_d2h(out, f->fb.out, (size_t)c->width * c->height * 4, st), "rt_readback_async");
+    f->done.record(st); f->pending = true;
+    if (ticket) *ticket = c->frame_seq - 1;
+    return 0;
+}
+
+int RT_API(rt_frame_wait)(rt_context* c, uint64_t ticket) {
+    if (!c) return fail("rt_frame_wait: null context");
+    if (ticket >= c->frame_seq) return fail("rt_frame_wait: ticket of a frame that was never submitted");
+    FrameSlot* f = &c->slot[ticket % c->n_slots];
+    if (f->pending && f->done.sync()) return fail(std::string("rt_frame_wait: ") + rt_platform_error());
     return 0;
 }
 
 int RT_API(rt_last_frame_stats)(rt_context* c, rt_stats* o) {
     if (!c || !o) return fail("rt_last_frame_stats: null argument");
     memset(o, 0, sizeof *o);
-    if (!c->last_valid) return fail("rt_last_frame_stats: no frame rendered yet");
+    FrameSlot* f = &c->slot[c->cur];
+    if (!f->last_valid) return fail("rt_last_frame_stats: no frame rendered yet");
     if (sync_all(c)) return fail(std::string("rt_last_frame_stats: ") + rt_platform_error());
-    const size_t per = (size_t)(c->last_S ? c->last_S : 1) * (c->last_B + 1);
+    const size_t per = (size_t)(f->last_S ? f->last_S : 1) * (f->last_B + 1);
     std::vector<uint32_t> h(per * 2);
-    RT_CHECK(rt_d2h(h.data(), c->counters, per * 2 * 4, c->stream), "rt_last_frame_stats");
+    RT_CHECK(rt_d2h(h.data(), f->counters, per * 2 * 4, c->stream), "rt_last_frame_stats");
     rt_stream_sync(c->stream);
-    for (uint32_t smp = 0; smp < c->last_S; ++smp)
-        for (uint32_t b = 0; b < c->last_B; ++b) { o->rays_extend += h[(size_t)smp * (c->last_B + 1) + b]; o->rays_shadow += h[per + (size_t)smp * (c->last_B + 1) + b]; }
-    o->pixel_samples = c->last_pixels;
-    if (c->last_counted) {
-        RtCounters k; RT_CHECK(rt_d2h(&k, c->dev_cnt, sizeof k, c->stream), "rt_last_frame_stats"); rt_stream_sync(c->stream);
+    for (uint32_t smp = 0; smp < f->last_S; ++smp)
+        for (uint32_t b = 0; b < f->last_B; ++b) { o->rays_extend += h[(size_t)smp * (f->last_B + 1) + b]; o->rays_shadow += h[per + (size_t)smp * (f->last_B + 1) + b]; }
+    o->pixel_samples = f->last_pixels;
+    if (f->last_counted) {
+        RtCounters k; RT_CHECK(rt_d2h(&k, f->dev_cnt, sizeof k, c->stream), "rt_last_frame_stats"); rt_stream_sync(c->stream);
         o->nodes = k.nodes; o->tris = k.tris; o->insts = k.insts; o->anyhits = k.anyhits; o->tex_taps = k.tex_taps; o->light_cands = k.light_cands;
     }
-    if (c->timers) o->ms_total = rt_timer_ms(c->ev_begin, c->ev_end);
-    for (size_t i = 0; i < c->stage_used; ++i) {
-        StageEvent& e = c->stage_events[i]; const float ms = rt_timer_ms(e.a, e.b);
+    if (c->timers) o->ms_total = rt_timer_ms(f->ev_begin, f->ev_end);
+    for (size_t i = 0; i < f->stage_used; ++i) {
+        StageEvent& e = f->stage_events[i]; const float ms = rt_timer_ms(e.a, e.b);
         switch (e.stage) { case 0: o->ms_raygen += ms; break; case 1: o->ms_extend += ms; o->n_extend_launches++; break; case 2: o->ms_shade += ms; break; case 3: o->ms_shadow += ms; break; default: o->ms_accum += ms; }
     }
-    o->n_kernel_launches = (uint32_t)(c->launches_after - c->launches_before);
+    o->n_kernel_launches = (uint32_t)(f->launches_after - f->launches_before);
     // shaded hits = extend rays that hit something = rays_extend - misses; approximated by the next-queue inputs is wrong
     // (terminated paths also shade), so report the number of shade invocations
     o->shaded_hits = o->rays_extend;

@@ -91,6 +91,9 @@ inline int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, rt
 
 struct rt_timer { void create() {} void destroy() {} void record(rt_stream_t) {} };
 inline float rt_timer_ms(rt_timer&, rt_timer&) { return 0.0f; }
+struct rt_event { void create() {} void destroy() {} void record(rt_stream_t) {} void wait(rt_stream_t) {} int sync() { return 0; } };
+inline int rt_stream_create(rt_stream_t* s) { *s = nullptr; return 0; }
+inline void rt_stream_destroy(rt_stream_t) {}
 
 #else
 // ----------------------------------------------------------------------------------------------------
@@ -165,4 +168,15 @@ struct rt_timer {
     void record(rt_stream_t s) { cudaEventRecord(e, s); }
 };
 inline float rt_timer_ms(rt_timer& a, rt_timer& b) { float ms = 0; cudaEventElapsedTime(&ms, a.e, b.e); return ms; }
+// ordering-only event (no timing): cross-stream dependencies of the frames in flight
+struct rt_event {
+    cudaEvent_t e = nullptr;
+    void create() { if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+    void destroy() { if (e) cudaEventDestroy(e); e = nullptr; }
+    void record(rt_stream_t s) { cudaEventRecord(e, s); }
+    void wait(rt_stream_t s) { cudaStreamWaitEvent(s, e, 0); }
+    int sync() { return cudaEventSynchronize(e) == cudaSuccess ? 0 : 1; }
+};
+inline int rt_stream_create(rt_stream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1; }
+inline void rt_stream_destroy(rt_stream_t s) { if (s) cudaStreamDestroy(s); }
 #endif

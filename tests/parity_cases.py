@@ -57,6 +57,49 @@ def case_tile_partition(api, cornell_desc, golden):
     assert (acc_full == acc_p).all() and (out_full == out_p).all()
 
 
+def case_frames_in_flight(api, cornell_desc, golden, size=64, frames=7):
+    """InFlightFrames (app/src/lib.rs:34): n frames overlap on the GPU, accumulation stays in submission order, so the
+    accumulation image and every presented RGBA8 frame are bit-identical to the strictly ordered n = 1 run."""
+    ctx, sc = make(api, cornell_desc, size, size)
+    cam = host.Camera(size, size).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=6)
+    drv = host.FrameDriver(cam, gui, cornell_desc.fully_opaque)
+    ubos = [drv.next_ubo() for _ in range(frames)]
+    ref_out = []
+    for u in ubos:
+        ctx.render(sc, u)
+        ref_out.append(ctx.readback(want_acc=False)[1].copy())
+    ref_acc, _ = ctx.readback()
+    ref_stats = ctx.stats()
+    for n in (2, 3, 4):
+        ctx.set_frames_in_flight(n)
+        ctx.resize(size, size)
+        bufs = [np.zeros((size, size, 4), np.uint8) for _ in ubos]
+        tickets = []
+        for u, b in zip(ubos, bufs):
+            ctx.render(sc, u)
+            tickets.append(ctx.readback_async(b))
+        assert tickets == list(range(tickets[0], tickets[0] + len(ubos)))
+        for t in tickets:
+            ctx.frame_wait(t)
+        for f, (b, r) in enumerate(zip(bufs, ref_out)):
+            assert (b == r).all(), (n, f)
+        acc, out = ctx.readback()
+        assert (acc == ref_acc).all() and (out == ref_out[-1]).all(), n
+        st = ctx.stats()
+        assert st.rays_extend == ref_stats.rays_extend and st.rays_shadow == ref_stats.rays_shadow
+        # a consumer of the accumulation image joins the frames in flight: tonemap-only pass == last frame's image
+        ctx.tonemap(ubos[-1]); _, out2 = ctx.readback()
+        assert (out2 == ref_out[-1]).all()
+    ctx.set_frames_in_flight(1)
+    acc, out = ctx.readback()
+    assert (acc == ref_acc).all() and (out == ref_out[-1]).all()       # shrinking keeps the presented image
+    import pytest
+    with pytest.raises(core.RtError):
+        ctx.set_frames_in_flight(5)
+    with pytest.raises(core.RtError):
+        ctx.frame_wait(10 ** 9)
+
+
 def case_instancing(api):
     b = scenes.SceneBuilder()
     m = b.add_material(scenes.material((0.8, 0.3, 0.2, 1), metallic=0.0))

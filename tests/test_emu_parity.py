@@ -17,6 +17,10 @@ def test_emu_tile_partition_is_bit_identical(cornell_desc, golden):
     pc.case_tile_partition(emu_api(), cornell_desc, golden)
 
 
+def test_emu_frames_in_flight_bookkeeping(cornell_desc, golden):
+    pc.case_frames_in_flight(emu_api(), cornell_desc, golden, size=24, frames=4)
+
+
 def test_emu_instancing_and_tlas_update():
     pc.case_instancing(emu_api())
 

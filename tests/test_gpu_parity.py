@@ -31,6 +31,10 @@ def test_tile_partition_bit_identical(api, cornell_desc, golden):
     pc.case_tile_partition(api, cornell_desc, golden)
 
 
+def test_frames_in_flight_bit_identical(api, cornell_desc, golden):
+    pc.case_frames_in_flight(api, cornell_desc, golden)
+
+
 def test_instancing_and_tlas_update(api):
     pc.case_instancing(api)
 
