@@ -456,7 +456,8 @@ static void launch_extend(FrameSlot* c, const DScene& S, const FrameParams& P, c
     for (uint32_t i = 0; i < n; ++i) extend_item<ALPHA, COUNT>(S, P, q, c->hits, i, c->dev_cnt);
     (void)fetch; (void)max_count; (void)st;
 #else
-    extend_kernel<ALPHA, COUNT><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
+    if (S.single_merged) extend_kernel<ALPHA, COUNT, true><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
+    else extend_kernel<ALPHA, COUNT, false><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
     ++g_rt_launch_count; (void)max_count;
 #endif
 }
@@ -467,7 +468,8 @@ static void launch_shadow(FrameSlot* c, const DScene& S, const FrameParams& P, c
     for (uint32_t i = 0; i < n; ++i) shadow_item<ALPHA, COUNT>(S, P, c->fb, c->sq, i, c->dev_cnt);
     (void)fetch; (void)st;
 #else
-    shadow_kernel<ALPHA, COUNT><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
+    if (S.single_merged) shadow_kernel<ALPHA, COUNT, true><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
+    else shadow_kernel<ALPHA, COUNT, false><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
     ++g_rt_launch_count;
 #endif
 }

@@ -190,6 +190,9 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 6   // <= 85 registers: 24 warps per SM
 #endif
+#ifndef RT_EXTEND_MIN_BLOCKS_SINGLE
+#define RT_EXTEND_MIN_BLOCKS_SINGLE 8   // single-BLAS specialisation fits 64 registers without spills: 32 warps per SM
+#endif
 
 // Persistent traversal kernel body.
 //  * per-lane dynamic fetch (Aila & Laine 2009; Ylitie et al. 2017): every lane owns a resumable traversal state;
@@ -217,23 +220,25 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 #define RT_TQ_CAP 256u         // per-warp triangle queue capacity (power of two, >= 31 + 32 * RT_TQ_PUSH_MAX)
 #define RT_TQ_TRI_BITS 27      // item = owner lane << 27 | absolute triangle index
 
+template <bool ALPHA>
 struct CoopShared {            // one per warp; SoA over the 32 owner lanes
     float ox[32], oy[32], oz[32], Sx[32], Sy[32], Sz[32], tmin[32], tmax[32], cur_t[32], u[32], v[32];
     unsigned long long best_ip[32];          // (ordered t << 32 | rank) of the best candidate of this round
     unsigned long long win_ip[32];           // its (instance << 32 | primitive)
     uint32_t kxyz[32], done[32];
-    uint32_t inst[32], geo[32], alpha[32], rng[4][32];   // inst: 0xFFFFFFFF = merged BLAS (instance id in the triangle record)
+    uint32_t inst[32];                       // 0xFFFFFFFF = merged BLAS (instance id in the triangle record)
+    uint32_t geo[ALPHA ? 32 : 1], alpha[ALPHA ? 32 : 1], rng[4][ALPHA ? 32 : 1];   // any-hit context, only kept when alpha tests can run
     uint32_t items[RT_TQ_CAP];
     uint32_t tail;                           // total items ever appended (RT_TQ_ATOMIC_TAIL)
 };
 
-template <bool ALPHA>
-RT_D void coop_publish_ray(const Trav& tv, CoopShared& sh, uint32_t lane) {
+template <bool ALPHA, bool SINGLE>
+RT_D void coop_publish_ray(const Trav& tv, CoopShared<ALPHA>& sh, uint32_t lane) {
     sh.ox[lane] = tv.o.x; sh.oy[lane] = tv.o.y; sh.oz[lane] = tv.o.z;
     sh.Sx[lane] = tv.sh.Sx; sh.Sy[lane] = tv.sh.Sy; sh.Sz[lane] = tv.sh.Sz;
     sh.tmin[lane] = tv.tmin; sh.tmax[lane] = tv.tmax; sh.cur_t[lane] = tv.found ? tv.hit.t : tv.tmax;
     sh.kxyz[lane] = (uint32_t)tv.sh.kx | ((uint32_t)tv.sh.ky << 2) | ((uint32_t)tv.sh.kz << 4);
-    sh.inst[lane] = tv.merged ? 0xFFFFFFFFu : tv.cur_inst;
+    if (!SINGLE) sh.inst[lane] = tv.merged ? 0xFFFFFFFFu : tv.cur_inst;
     if (ALPHA) {
         sh.geo[lane] = tv.cur_geo; sh.alpha[lane] = tv.cur_alpha ? 1u : 0u;
         sh.rng[0][lane] = tv.rng.x; sh.rng[1][lane] = tv.rng.y; sh.rng[2][lane] = tv.rng.z; sh.rng[3][lane] = tv.rng.w;
@@ -242,8 +247,8 @@ RT_D void coop_publish_ray(const Trav& tv, CoopShared& sh, uint32_t lane) {
 
 // Tests up to 32 queued (owner, triangle) items, one per lane.  Returns through `outstanding` / tv the owner-side
 // bookkeeping.  `usable`: this lane's ray is still live (results of a retired any-hit ray are discarded).
-template <int MODE, bool ALPHA, bool COUNT>
-RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, uint32_t n, uint32_t lane, uint32_t& outstanding, bool usable, bool& terminated,
+template <int MODE, bool ALPHA, bool COUNT, bool SINGLE>
+RT_D void coop_round(Trav& tv, const DScene& S, CoopShared<ALPHA>& sh, uint32_t head, uint32_t n, uint32_t lane, uint32_t& outstanding, bool usable, bool& terminated,
                      unsigned long long* c4) {
     // winner per owner = lexicographic minimum of (t, instance, primitive).  One 64-bit shared-memory atomicMin on
     // (ordered t << 32 | rank) decides it: rank (triangle record .w) orders the triangles of a BLAS by (instance, primitive)
@@ -261,7 +266,7 @@ RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, u
         rs.Sx = sh.Sx[owner]; rs.Sy = sh.Sy[owner]; rs.Sz = sh.Sz[owner];
         hit = tri_test(rs, mk3(sh.ox[owner], sh.oy[owner], sh.oz[owner]), xyz(a), xyz(b), xyz(c), sh.tmin[owner], sh.tmax[owner], tt, bu, bv);
         const uint32_t prim = rt_float_as_uint(a.w);
-        const bool merged = sh.inst[owner] == 0xFFFFFFFFu;
+        const bool merged = SINGLE || sh.inst[owner] == 0xFFFFFFFFu;
         const uint32_t inst = merged ? rt_float_as_uint(b.w) : sh.inst[owner];
         ip = ((unsigned long long)inst << 32) | prim;
         if (hit && tt > sh.cur_t[owner]) hit = false;            // cannot beat the owner's committed hit
@@ -296,10 +301,12 @@ RT_D void coop_round(Trav& tv, const DScene& S, CoopShared& sh, uint32_t head, u
     __syncwarp();
 }
 
-template <int MODE, bool ALPHA, bool COUNT, class LoadRay, class StoreHit>
+// SINGLE: the scene is one merged world-space BLAS (DScene::single_merged) — no TLAS level, no instance entry / exit,
+// node and triangle bases come from the kernel parameters (uniform registers) instead of per-lane state.
+template <int MODE, bool ALPHA, bool COUNT, bool SINGLE, class LoadRay, class StoreHit>
 RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetch, RtCounters* cnt, LoadRay load_ray, StoreHit store_hit) {
-    __shared__ CoopShared coop_smem[RT_WARPS_PER_BLOCK];
-    CoopShared& sh = coop_smem[threadIdx.x >> 5];
+    __shared__ CoopShared<ALPHA> coop_smem[RT_WARPS_PER_BLOCK];
+    CoopShared<ALPHA>& sh = coop_smem[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint2 stack[RT_STACK_SIZE];
@@ -321,7 +328,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
                 if (!active && outstanding == 0u) {
                     idx = base + (uint32_t)__popc(need & lt_mask);
-                    if (idx < count) { load_ray(idx, tv); active = true; if (tv.blas_sp >= 0) coop_publish_ray<ALPHA>(tv, sh, lane); }
+                    if (idx < count) { load_ray(idx, tv); active = true; if (SINGLE || tv.blas_sp >= 0) coop_publish_ray<ALPHA, SINGLE>(tv, sh, lane); }
                 }
                 if (base + (uint32_t)__popc(need) >= count) exhausted = true;
             }
@@ -333,7 +340,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             if (active) {
                 // acquire the next node group: leave the BLAS / pop until ngroup holds an inner child or instances are parked
                 while (tv.ngroup.y <= 0x00FFFFFFu && tv.tgroup.y == 0u) {
-                    if (tv.blas_sp >= 0 && tv.sp == tv.blas_sp) {
+                    if (!SINGLE && tv.blas_sp >= 0 && tv.sp == tv.blas_sp) {
                         if (outstanding) { want_flush = true; break; }     // queued triangles refer to the object-space ray
                         trav_leave_blas(tv, S);
                     }
@@ -345,15 +352,15 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                     if (e.y > 0x00FFFFFFu) tv.ngroup = e; else { tv.tgroup = e; tv.ngroup = make_uint2(0u, 0u); }
                 }
                 if (active && !want_flush) {
-                    if (tv.tgroup.y != 0u && tv.blas_sp < 0) {
+                    if (!SINGLE && tv.tgroup.y != 0u && tv.blas_sp < 0) {
                         // TLAS level: parked instances
                         trav_enter_instance<ALPHA, COUNT>(tv, S, stack, c4);
-                        coop_publish_ray<ALPHA>(tv, sh, lane);
+                        coop_publish_ray<ALPHA, SINGLE>(tv, sh, lane);
                     } else {
                         // BLAS level with leftover leaf triangles parked: queue those first; else visit the next node
-                        if (tv.tgroup.y == 0u) trav_node_step<COUNT>(tv, S, stack, c4);
-                        if (tv.blas_sp >= 0 && tv.tgroup.y != 0u) {
-                            leaf_base = tv.tri_off + tv.tgroup.x;
+                        if (tv.tgroup.y == 0u) trav_node_step<COUNT, SINGLE>(tv, S, stack, c4);
+                        if ((SINGLE || tv.blas_sp >= 0) && tv.tgroup.y != 0u) {
+                            leaf_base = (SINGLE ? S.merged_tri_off : tv.tri_off) + tv.tgroup.x;
                             leaf_mask = tv.tgroup.y;
                             if (__popc(leaf_mask) > RT_TQ_PUSH_MAX) {     // keep the RT_TQ_PUSH_MAX highest bits, park the rest
                                 uint32_t keep = 0u, m = leaf_mask;
@@ -405,13 +412,13 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             while (q_count >= 32u || (flush && q_count)) {
                 const uint32_t n = q_count < 32u ? q_count : 32u;
                 bool terminated = false;
-                coop_round<MODE, ALPHA, COUNT>(tv, S, sh, q_head, n, lane, outstanding, active, terminated, c4);
+                coop_round<MODE, ALPHA, COUNT, SINGLE>(tv, S, sh, q_head, n, lane, outstanding, active, terminated, c4);
                 if (MODE == RT_MODE_ANY && terminated && active) { trav_finish(tv); store_hit(idx, tv); active = false; }
                 q_head += n; q_count -= n;
             }
             // a lane that only waited for its last triangles can retire now instead of spending another iteration
             if (want_flush && active && outstanding == 0u && tv.sp == 0 && tv.ngroup.y <= 0x00FFFFFFu && tv.tgroup.y == 0u &&
-                (tv.blas_sp <= 0)) {
+                (SINGLE || tv.blas_sp <= 0)) {
                 trav_finish(tv); store_hit(idx, tv); active = false;
             }
             holding = __ballot_sync(0xFFFFFFFFu, active);
@@ -421,7 +428,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             while (q_count) {
                 const uint32_t n = q_count < 32u ? q_count : 32u;
                 bool terminated = false;
-                coop_round<MODE, ALPHA, COUNT>(tv, S, sh, q_head, n, lane, outstanding, active, terminated, c4);
+                coop_round<MODE, ALPHA, COUNT, SINGLE>(tv, S, sh, q_head, n, lane, outstanding, active, terminated, c4);
                 if (MODE == RT_MODE_ANY && terminated && active) { trav_finish(tv); store_hit(idx, tv); active = false; }
                 q_head += n; q_count -= n;
             }
@@ -432,14 +439,14 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
     }
 }
 
-template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
-    persistent_trace<RT_MODE_CLOSEST, ALPHA, COUNT>(S, *count_ptr, fetch, cnt,
+template <bool ALPHA, bool COUNT, bool SINGLE>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOCKS_SINGLE : RT_EXTEND_MIN_BLOCKS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+    persistent_trace<RT_MODE_CLOSEST, ALPHA, COUNT, SINGLE>(S, *count_ptr, fetch, cnt,
         [&](uint32_t i, Trav& tv) {
             const float4 a = q.o_tmin[i], b = q.d_tmax[i];
             u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
             if (ALPHA) { const uint32_t pixel = rt_float_as_uint(q.thr_pix[i].w); rng = path_stream(P, pixel, q.rng[i].x); }
-            trav_init(tv, S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, rng);
+            trav_init<SINGLE>(tv, S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, rng);
         },
         [&](uint32_t i, const Trav& tv) {
             hits.tuvp[i] = make_float4(tv.hit.t, tv.hit.u, tv.hit.v, rt_uint_as_float(tv.hit.prim));
@@ -447,14 +454,14 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) exten
         });
 }
 
-template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
-    persistent_trace<RT_MODE_ANY, ALPHA, COUNT>(S, *count_ptr, fetch, cnt,
+template <bool ALPHA, bool COUNT, bool SINGLE>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOCKS_SINGLE : RT_EXTEND_MIN_BLOCKS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+    persistent_trace<RT_MODE_ANY, ALPHA, COUNT, SINGLE>(S, *count_ptr, fetch, cnt,
         [&](uint32_t i, Trav& tv) {
             const float4 a = sq.o_tmax[i], b = sq.d_pix[i];
             u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
             if (ALPHA) rng = path_stream(P, rt_float_as_uint(b.w), rt_float_as_uint(sq.contrib[i].w));
-            trav_init(tv, S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.1f, a.w, rng);   // tMin 0.1: RayTracing.rchit:43
+            trav_init<SINGLE>(tv, S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.1f, a.w, rng);   // tMin 0.1: RayTracing.rchit:43
         },
         [&](uint32_t i, const Trav& tv) {
             if (!tv.found) {   // unoccluded: add the light's contribution to the frame radiance of the pixel

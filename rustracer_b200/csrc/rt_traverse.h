@@ -111,7 +111,8 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, 
             const float tnz = fmaf(rt_byte_to_biased_float(nz, j), az, czn), tfz = fmaf(rt_byte_to_biased_float(fz, j), az, czf);
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (cmin <= cmax) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
+            // child_bits << bit_index: one PRMT for the byte, a wrapping shift that only looks at the low 5 bits of its amount
+            if (cmin <= cmax) hitmask |= rt_shl_wrap(rt_byte_of(child_bits4, j), bit_index4 >> (8 * j));
         }
     }
     return hitmask;
@@ -138,6 +139,7 @@ RT_D void trav_set_level_ray(Trav& t, f3 o, f3 d) {
     t.o = o; t.idir = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z)); t.octinv = octant_inv(d);
 }
 
+template <bool SINGLE = false>
 RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tmax, u4 rng) {
     t.ow = ow; t.dw = dw; t.tmin = tmin; t.tmax = tmax; t.rng = rng;
     trav_set_level_ray(t, ow, dw);
@@ -145,7 +147,7 @@ RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tm
     t.nodes = S.tlas_nodes; t.tri_off = 0; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false; t.merged = false; t.identity = false;
     t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u); t.sp = 0;
     t.hit.t = tmax; t.hit.u = 0.0f; t.hit.v = 0.0f; t.hit.inst = 0xFFFFFFFFu; t.hit.prim = 0xFFFFFFFFu; t.found = false;
-    if (S.single_merged) {
+    if (SINGLE || S.single_merged) {
         // the whole scene is the merged world-space BLAS: start inside it
         t.nodes = S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4; t.tri_off = S.merged_tri_off;
         t.blas_sp = 0; t.identity = true; t.merged = true; t.cur_inst = S.n_instances;
@@ -170,7 +172,7 @@ RT_D void trav_leave_blas(Trav& t, const DScene& S) {
 // phases execute with most lanes active instead of interleaving per lane.
 // MODE: closest / any (terminate on first accepted hit).  ALPHA: run the alpha test on non-opaque geometry
 // (false == gl_RayFlagsOpaqueEXT / the reference's `fully_opaque` pipeline without any-hit shaders).
-template <bool COUNT>
+template <bool COUNT, bool SINGLE = false>
 RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
     if (t.ngroup.y > 0x00FFFFFFu) {
         const uint32_t hits = t.ngroup.y, imask = t.ngroup.y;
@@ -180,7 +182,7 @@ RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
         if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
         const uint32_t slot = (uint32_t)(child_bit - 24) ^ (t.octinv & 7u);
         const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-        const float4* np = t.nodes + (size_t)(child_base + rel) * RT_NODE_F4;
+        const float4* np = (SINGLE ? S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4 : t.nodes) + (size_t)(child_base + rel) * RT_NODE_F4;
         const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4);
         if (COUNT) c4[0]++;
         const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, t.o, t.idir, t.octinv, t.tmin, t.hit.t);
