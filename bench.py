@@ -335,14 +335,19 @@ def run_ours(args):
     for s in range(Wm, Wm + K):
         pre_step(s)
         ctx.render(scene, ubos[s], stream=stream)
+    t_sub = time.perf_counter()
     if world > 1:
-        ctx.synchronize(); dist.barrier()      # all ranks must have finished rendering before peers are read
+        ctx.synchronize(); t_sync = time.perf_counter()
+        dist.barrier()                         # all ranks must have finished rendering before peers are read
+        t_bar = time.perf_counter()
         combine()
     ctx.join(stream)                           # the timing stream waits (on the device) for every frame in flight
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    if world > 1 and os.environ.get("BENCH_DEBUG"):
+        print(f"[rank {rank}] timed region {ms:.3f} ms; host: submit->sync {1e3 * (t_sync - t_sub):.3f} ms, barrier {1e3 * (t_bar - t_sync):.3f} ms", file=sys.stderr, flush=True)
     tmax = torch.tensor([ms], device="cuda")
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -482,7 +482,7 @@ RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" :
 RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 #ifndef RT_SHADE_MIN_BLOCKS
-#define RT_SHADE_MIN_BLOCKS 4
+#define RT_SHADE_MIN_BLOCKS 8
 #endif
 template <bool SIMPLE, bool COUNT>
 __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,

@@ -36,6 +36,7 @@ def main():
     ctx = core.Context(W, H, device=local); sc = core.Scene(ctx, d)
     cam = host.Camera(W, H).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=8)
     n_frames = K * world
+    ctx.set_frames_in_flight(3)     # the sharded passes overlap on each GPU; rt_reduce_peers joins them
     for g in sharding.frames_of_rank(n_frames, rank, world):
         ctx.render(sc, ubo_of(cam, gui, g, True))
     ctx.synchronize()
