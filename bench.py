@@ -440,7 +440,7 @@ def run_ours(args):
             try:
                 from oracle import orc
                 m, rays, secs = cpu_sample(desc, 1, (0, HEIGHT))
-                nfr = int(max(1, min(8, round(15.0 / max(secs, 1e-3)))))
+                nfr = int(max(1, min(64, round(15.0 / max(secs, 1e-3)))))   # ~15 s of CPU work
                 if nfr > 1:
                     m, rays, secs = cpu_sample(desc, nfr, (0, HEIGHT), warm=0)
                 cpu = {"value": m, "unit": "Mrays/s", "cores": int(orc.lib().orc_num_threads()), "kind": "port",

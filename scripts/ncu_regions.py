@@ -17,14 +17,14 @@ for s in sections:
     if s['file'] in seen: launches.append([]); seen = set()
     seen.add(s['file']); launches[-1].append(s)
 secs = launches[launch]
-REGIONS = [  # (file, first line, last line, region)
+REGIONS = [  # (file, first line, last line, region) — line numbers of the committed sources
     ('rt_traverse.h', 13, 29, 'ray setup (shear/init)'), ('rt_traverse.h', 30, 58, 'triangle test'), ('rt_traverse.h', 59, 69, 'instance xform'),
-    ('rt_traverse.h', 70, 123, 'node test'), ('rt_traverse.h', 137, 172, 'ray setup (shear/init)'), ('rt_traverse.h', 173, 199, 'node step (fetch, push, sort)'),
-    ('rt_traverse.h', 200, 230, 'instance enter'), ('rt_traverse.h', 231, 248, 'commit'),
-    ('rt_kernels.h', 225, 236, 'publish ray'), ('rt_kernels.h', 240, 252, 'coop round: setup/load'), ('rt_kernels.h', 253, 262, 'triangle test'),
-    ('rt_kernels.h', 263, 300, 'coop round: resolve'), ('rt_kernels.h', 303, 325, 'fetch rays'), ('rt_kernels.h', 326, 346, 'acquire/pop/retire'),
-    ('rt_kernels.h', 347, 362, 'leaf handling'), ('rt_kernels.h', 363, 380, 'queue append (scan)'), ('rt_kernels.h', 381, 396, 'flush control'),
-    ('rt_kernels.h', 397, 411, 'drain/tail'), ('rt_kernels.h', 412, 430, 'load/store ray+hit'),
+    ('rt_traverse.h', 70, 124, 'node test'), ('rt_traverse.h', 138, 174, 'ray setup (shear/init)'), ('rt_traverse.h', 175, 201, 'node step (fetch, stack push)'),
+    ('rt_traverse.h', 202, 232, 'instance enter'), ('rt_traverse.h', 233, 250, 'commit'),
+    ('rt_kernels.h', 235, 249, 'publish ray'), ('rt_kernels.h', 250, 261, 'coop round: setup/load'), ('rt_kernels.h', 262, 271, 'triangle test'),
+    ('rt_kernels.h', 272, 303, 'coop round: resolve'), ('rt_kernels.h', 307, 336, 'fetch rays'), ('rt_kernels.h', 337, 353, 'acquire/pop/retire'),
+    ('rt_kernels.h', 354, 375, 'leaf handling'), ('rt_kernels.h', 376, 409, 'queue append'), ('rt_kernels.h', 410, 418, 'flush control'),
+    ('rt_kernels.h', 419, 441, 'retire/drain/tail'), ('rt_kernels.h', 442, 470, 'load/store ray+hit'),
 ]
 def region_of(f, l):
     for rf, a, b, name in REGIONS:
@@ -42,9 +42,9 @@ for s in secs:
         insts.append([int(r[2], 16), region_of(s['file'], line), ie, te, sm, s['file'], line, r[3].strip()])
 # an inlined instruction is listed once per level of its inline stack: keep one row per address, classified by the
 # innermost (most specific) region
-PRIORITY = ['triangle test', 'node test', 'instance xform', 'ray setup (shear/init)', 'commit', 'node step (fetch, push, sort)', 'instance enter',
+PRIORITY = ['triangle test', 'node test', 'instance xform', 'ray setup (shear/init)', 'commit', 'node step (fetch, stack push)', 'instance enter',
             'publish ray', 'coop round: setup/load', 'coop round: resolve', 'load/store ray+hit', 'fetch rays', 'acquire/pop/retire', 'leaf handling',
-            'queue append (scan)', 'flush control', 'drain/tail']
+            'queue append', 'flush control', 'retire/drain/tail']
 by_addr = {}
 for x in insts:
     o = by_addr.get(x[0])
