@@ -172,6 +172,15 @@ class Scene:
         self.api.check(self.api.rt_scene_read_vertices(self._h, F.as_ptr(v, F.rt_vertex), n))
         return v
 
+    def read_nodes(self, geo: int = -1) -> np.ndarray:
+        """80-byte compressed nodes of one BLAS as (n, 20) uint32 (geo < 0: the merged world-space BLAS)."""
+        n = F.c_u32()
+        self.api.check(self.api.rt_scene_read_nodes(self._h, geo, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 20), np.float32)
+        if n.value:
+            self.api.check(self.api.rt_scene_read_nodes(self._h, geo, F.as_ptr(out, F.c_f), n.value, C.byref(n)))
+        return out.view(np.uint32)
+
     def bvh_info(self) -> F.rt_bvh_info:
         info = F.rt_bvh_info()
         self.api.check(self.api.rt_scene_bvh_info(self._h, C.byref(info)))

@@ -126,6 +126,11 @@ struct rt_scene {
     bool has_nee = false;
     bool plain_materials = false;            // no texture reference and no specular-glossiness material anywhere
     float build_ms = 0, refit_ms = 0, skin_ms = 0, tlas_ms = 0;
+    // TLAS refit state (rt_scene_update_skins keeps the TLAS topology): leaf k -> entry, boxes in leaf order, counters
+    uint32_t* d_tlas_leaf_entry = nullptr; DAabb* d_tlas_leaf_boxes = nullptr; uint32_t* d_tlas_pending = nullptr; uint32_t tlas_entries = 0;
+    // asynchronous skin updates: frames wait for ev_updated on the device; the stage timers are read lazily
+    rt_event ev_updated; bool update_pending = false;
+    rt_timer upd_t[4]; bool upd_timers_pending = false, upd_timers_created = false;
 };
 
 namespace rtcore {
@@ -290,6 +295,13 @@ static void refit_nodes(rt_scene* s, const GeoRecord& gr) {
     const uint32_t* parent = s->d_node_parent + gr.node_off; uint32_t* pending = s->d_pending + gr.node_off;
     const DAabb* lb = s->d_leaf_boxes + gr.tri_off;
     rt_launch(gr.n_nodes, st, RT_LAMBDA(size_t w) { pending[w] = (uint32_t)rt_popc(rt_float_as_uint(nodes[w * RT_NODE_F4].w) >> 24); });
+#ifndef RT_EMU
+    if (gr.n_nodes) {
+        refit_nodes_kernel<<<(unsigned)(((size_t)gr.n_nodes * 8 + 255) / 256), 256, 0, st>>>(nodes, nb, lb, parent, pending, gr.n_nodes);
+        ++g_rt_launch_count;
+    }
+    return;
+#endif
     rt_launch(gr.n_nodes, st, RT_LAMBDA(size_t w0) {
         uint32_t w = (uint32_t)w0;
         if ((rt_float_as_uint(nodes[(size_t)w * RT_NODE_F4].w) >> 24) != 0u) return;   // only nodes without inner children start
@@ -335,18 +347,10 @@ static int upload_instance_records(rt_scene* s) {
     return 0;
 }
 
-// TLAS over the non-baked instances plus (when it has triangles) the merged world-space BLAS
-static int build_tlas(rt_scene* s) {
+// world-space boxes of the TLAS entries (entry e -> instance record d_entry_rec[e], BLAS root d_inst_root[e])
+static void instance_boxes(rt_scene* s, uint32_t ne) {
     rt_stream_t st = s->ctx->stream;
     const uint32_t n = (uint32_t)s->instances.size();
-    std::vector<uint32_t> entry_rec, entry_root;
-    for (uint32_t i = 0; i < n; ++i) if (!s->baked[i]) { entry_rec.push_back(i); entry_root.push_back(s->geo[s->instances[i].geo_id].node_off); }
-    if (s->merged.n_tris) { entry_rec.push_back(n); entry_root.push_back(s->merged.node_off); }
-    const uint32_t ne = (uint32_t)entry_rec.size();
-    if (ne) {
-        RT_CHECK(rt_h2d(s->d_inst_root, entry_root.data(), (size_t)ne * 4, st), "upload TLAS entries");
-        RT_CHECK(rt_h2d(s->d_entry_rec, entry_rec.data(), (size_t)ne * 4, st), "upload TLAS entries");
-    }
     const float4* o2wd = s->d_inst_o2w; const uint32_t* rootd = s->d_inst_root; const uint32_t* recd = s->d_entry_rec; const DAabb* nb = s->d_node_box; DAabb* ib = s->d_inst_boxes;
     rt_launch(ne, st, RT_LAMBDA(size_t e) {
         const DAabb b = nb[rootd[e]];
@@ -368,13 +372,29 @@ static int build_tlas(rt_scene* s) {
         }
         ib[e] = w;
     });
+}
+
+// TLAS over the non-baked instances plus (when it has triangles) the merged world-space BLAS
+static int build_tlas(rt_scene* s) {
+    rt_stream_t st = s->ctx->stream;
+    const uint32_t n = (uint32_t)s->instances.size();
+    std::vector<uint32_t> entry_rec, entry_root;
+    for (uint32_t i = 0; i < n; ++i) if (!s->baked[i]) { entry_rec.push_back(i); entry_root.push_back(s->geo[s->instances[i].geo_id].node_off); }
+    if (s->merged.n_tris) { entry_rec.push_back(n); entry_root.push_back(s->merged.node_off); }
+    const uint32_t ne = (uint32_t)entry_rec.size();
+    if (ne) {
+        RT_CHECK(rt_h2d(s->d_inst_root, entry_root.data(), (size_t)ne * 4, st), "upload TLAS entries");
+        RT_CHECK(rt_h2d(s->d_entry_rec, entry_rec.data(), (size_t)ne * 4, st), "upload TLAS entries");
+    }
+    instance_boxes(s, ne);
+    const uint32_t* recd = s->d_entry_rec; DAabb* ib = s->d_inst_boxes;
     WideOut out; out.nodes = s->d_tlas_nodes; out.prim_order = s->d_tlas_prims; out.node_box = s->d_tlas_box; out.node_parent = s->d_tlas_parent; out.max_nodes = ne ? ne : 1u;
     WideBvhInfo info;
     const int e = build_wide_bvh(ib, ne, s->scratch, out, st, &info);
     if (e) return fail("TLAS build failed (code " + std::to_string(e) + ")");
-    uint32_t* tp = s->d_tlas_prims;
-    rt_launch(ne, st, RT_LAMBDA(size_t k) { tp[k] = recd[tp[k]]; });   // TLAS leaf -> instance record index
-    s->tlas_nodes = info.n_nodes; s->tlas_depth = info.depth;
+    uint32_t* tp = s->d_tlas_prims; uint32_t* le = s->d_tlas_leaf_entry;
+    rt_launch(ne, st, RT_LAMBDA(size_t k) { le[k] = tp[k]; tp[k] = recd[tp[k]]; });   // TLAS leaf -> entry (kept for refits) -> instance record index
+    s->tlas_nodes = info.n_nodes; s->tlas_depth = info.depth; s->tlas_entries = ne;
     s->ds.single_merged = (ne == 1 && s->merged.n_tris) ? 1u : 0u;
     s->ds.merged_node_off = s->merged.node_off; s->ds.merged_tri_off = s->merged.tri_off;
     uint32_t bd = s->merged.depth;
@@ -383,6 +403,25 @@ static int build_tlas(rt_scene* s) {
     if (s->tlas_depth + s->blas_depth + 6 > RT_STACK_SIZE)
         return fail("BVH too deep for the traversal stack: tlas " + std::to_string(s->tlas_depth) + " + blas " + std::to_string(s->blas_depth));
     return 0;
+}
+
+// keeps the TLAS topology, refreshes the entry boxes and refits its nodes (no host synchronisation)
+static int refit_tlas(rt_scene* s) {
+#ifdef RT_EMU
+    return build_tlas(s);
+#else
+    rt_stream_t st = s->ctx->stream;
+    const uint32_t ne = s->tlas_entries;
+    if (!ne || !s->tlas_nodes) return 0;
+    instance_boxes(s, ne);
+    const DAabb* ib = s->d_inst_boxes; DAabb* lbx = s->d_tlas_leaf_boxes; const uint32_t* le = s->d_tlas_leaf_entry;
+    float4* nodes = s->d_tlas_nodes; uint32_t* pending = s->d_tlas_pending;
+    rt_launch(ne, st, RT_LAMBDA(size_t k) { lbx[k] = ib[le[k]]; });
+    rt_launch(s->tlas_nodes, st, RT_LAMBDA(size_t w) { pending[w] = (uint32_t)rt_popc(rt_float_as_uint(nodes[w * RT_NODE_F4].w) >> 24); });
+    refit_nodes_kernel<<<(unsigned)(((size_t)s->tlas_nodes * 8 + 255) / 256), 256, 0, st>>>(nodes, s->d_tlas_box, lbx, s->d_tlas_parent, pending, s->tlas_nodes);
+    ++g_rt_launch_count;
+    return 0;
+#endif
 }
 
 static void compute_has_nee(rt_scene* s, const rt_light* pl, uint32_t n) {
@@ -421,8 +460,8 @@ static int sync_all(rt_context* c) {
 }
 // device-side join: `st` waits for every frame submitted so far (no host block)
 static void join_frames(rt_context* c, rt_stream_t st) {
-    if (c->n_slots <= 1) return;
-    for (uint32_t k = 0; k < c->n_slots; ++k) if (c->slot[k].pending && c->slot[k].stream != st) c->slot[k].done.wait(st);
+    // (with a single slot the frame ran on the caller's stream; its `done` event was recorded there)
+    for (uint32_t k = 0; k < c->n_slots; ++k) if (c->slot[k].pending && (c->n_slots == 1 || c->slot[k].stream != st)) c->slot[k].done.wait(st);
 }
 // a consumer of the accumulation image ran on `st`: later frames must not accumulate before it
 static void consumer_ran(rt_context* c, rt_stream_t st) {
@@ -645,11 +684,14 @@ void RT_API(rt_scene_destroy)(rt_scene* s) {
     sync_all(s->ctx);
     void* ptrs[] = {s->d_vin, s->d_vout, s->d_indices, s->d_prim, s->d_mat, s->d_skins, s->d_dl, s->d_pl, s->d_images, s->d_textures, s->d_lut,
                     s->d_blas_nodes, s->d_tris, s->d_node_box, s->d_node_parent, s->d_prim_order, s->d_leaf_boxes, s->d_prim_boxes, s->d_pending,
-                    s->d_tlas_nodes, s->d_tlas_prims, s->d_tlas_box, s->d_tlas_parent, s->d_inst_boxes, s->d_inst_w2o, s->d_inst_o2w, s->d_inst_root, s->d_entry_rec, s->d_bake_src};
+                    s->d_tlas_nodes, s->d_tlas_prims, s->d_tlas_box, s->d_tlas_parent, s->d_inst_boxes, s->d_inst_w2o, s->d_inst_o2w, s->d_inst_root, s->d_entry_rec, s->d_bake_src,
+                    s->d_tlas_leaf_entry, s->d_tlas_leaf_boxes, s->d_tlas_pending};
     for (void* p : ptrs) if (p) rt_free(p);
     for (uint8_t* p : s->d_image_px) if (p) rt_free(p);
     for (int f = 0; f < 6; ++f) if (s->d_sky[f]) rt_free(s->d_sky[f]);
     scratch_free(s->scratch);
+    s->ev_updated.destroy();
+    if (s->upd_timers_created) for (auto& t : s->upd_t) t.destroy();
     delete s;
 }
 
@@ -757,6 +799,7 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
     e |= dev_upload(&s->d_bake_src, bake_src.data(), bake_src.size(), st);
     e |= dev_alloc(&s->d_tlas_nodes, (size_t)(ninst + 1) * RT_NODE_F4); e |= dev_alloc(&s->d_tlas_prims, ninst + 1);
     e |= dev_alloc(&s->d_tlas_box, ninst + 1); e |= dev_alloc(&s->d_tlas_parent, ninst + 1); e |= dev_alloc(&s->d_inst_boxes, ninst + 1);
+    e |= dev_alloc(&s->d_tlas_leaf_entry, ninst + 1); e |= dev_alloc(&s->d_tlas_leaf_boxes, ninst + 1); e |= dev_alloc(&s->d_tlas_pending, ninst + 1);
     e |= dev_alloc(&s->d_inst_w2o, (size_t)(ninst + 1) * RT_INST_F4); e |= dev_alloc(&s->d_inst_o2w, (size_t)(ninst ? ninst : 1) * RT_O2W_F4);
     e |= dev_alloc(&s->d_inst_root, ninst + 1); e |= dev_alloc(&s->d_entry_rec, ninst + 1);
     if (e) return bail(std::string("rt_scene_create: BVH allocation failed: ") + rt_platform_error());
@@ -798,28 +841,44 @@ int RT_API(rt_scene_update_instances)(rt_scene* s, const rt_instance* inst, uint
     return 0;
 }
 
+// stage timers of the last skin update are read on demand (rt_scene_bvh_info): the update itself never blocks the host
+static void collect_update_timers(rt_scene* s) {
+    if (!s->upd_timers_pending) return;
+    rt_stream_sync(s->ctx->stream);
+    s->skin_ms = rt_timer_ms(s->upd_t[0], s->upd_t[1]); s->refit_ms = rt_timer_ms(s->upd_t[1], s->upd_t[2]); s->tlas_ms = rt_timer_ms(s->upd_t[2], s->upd_t[3]);
+    s->upd_timers_pending = false;
+}
+
 int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_skins, int rebuild) {
     if (!s || (!mats && n_skins)) return fail("rt_scene_update_skins: null argument");
     if (n_skins != s->n_skins) return fail("rt_scene_update_skins: skin count differs from the scene's");
     rt_stream_t st = s->ctx->stream;
-    sync_all(s->ctx);            // frames in flight (or on a caller's stream) still read the vertices / BVH rewritten below
-    rt_timer t0, t1, t2, t3; t0.create(); t1.create(); t2.create(); t3.create();
+#ifndef RT_EMU
+    cudaSetDevice(s->ctx->device);
+#endif
+    // Frames in flight (or on a caller's stream) still read the vertices / BVH rewritten below: the scene's stream
+    // waits for them on the device.  A refit never blocks the host: skinning, BLAS refit and TLAS refit are queued,
+    // later frames wait for ev_updated.  A rebuild reads builder counters back level by level and is synchronous.
+    join_frames(s->ctx, st);
+    if (rebuild) sync_all(s->ctx);
+    if (!s->upd_timers_created) { for (auto& t : s->upd_t) t.create(); s->ev_updated.create(); s->upd_timers_created = true; }
+    collect_update_timers(s);     // (the events are about to be re-recorded)
     RT_CHECK(rt_h2d(s->d_skins, mats, (size_t)n_skins * RT_MAX_JOINTS * 16 * 4, st), "skin upload");
-    t0.record(st);
+    s->upd_t[0].record(st);
     run_skinning(s);
-    t1.record(st);
+    s->upd_t[1].record(st);
     for (uint32_t g = 0; g < s->geo.size(); ++g) {
         if (!s->geo[g].skinned || !s->geo[g].needed) continue;
         if (rebuild) { if (build_blas(s, g)) return 1; } else refit_blas(s, g);
     }
     if (s->merged_skinned && s->merged.n_tris) { if (rebuild) { if (build_merged(s)) return 1; } else refit_merged(s); }
-    t2.record(st);
-    const int e = build_tlas(s);
-    t3.record(st);
-    rt_stream_sync(st);
-    s->skin_ms = rt_timer_ms(t0, t1); s->refit_ms = rt_timer_ms(t1, t2); s->tlas_ms = rt_timer_ms(t2, t3);
-    t0.destroy(); t1.destroy(); t2.destroy(); t3.destroy();
+    s->upd_t[2].record(st);
+    const int e = rebuild ? build_tlas(s) : refit_tlas(s);
+    s->upd_t[3].record(st);
+    s->upd_timers_pending = true;
+    s->ev_updated.record(st); s->update_pending = true;
     if (e) return 1;
+    if (rebuild) { if (rt_stream_sync(st)) return fail(std::string("rt_scene_update_skins: ") + rt_platform_error()); }
     update_ds(s);
     return 0;
 }
@@ -873,6 +932,7 @@ int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_re
         if (c->consumer_pending) c->ev_consumer.wait(f->stream);
         st = f->stream;
     }
+    if (s->update_pending) s->ev_updated.wait(st);     // asynchronous skin update queued on the scene's stream
 #ifndef RT_EMU
     f->launches_before = g_rt_launch_count;
 #endif
@@ -1047,9 +1107,23 @@ int RT_API(rt_scene_read_vertices)(rt_scene* s, rt_vertex* out, uint32_t n) {
     return 0;
 }
 
+int RT_API(rt_scene_read_nodes)(rt_scene* s, int geo, float* out, uint32_t max_nodes, uint32_t* n_nodes) {
+    if (!s || !n_nodes) return fail("rt_scene_read_nodes: null argument");
+    if (geo >= (int)s->geo.size()) return fail("rt_scene_read_nodes: geometry index out of range");
+    const GeoRecord& gr = geo < 0 ? s->merged : s->geo[geo];
+    *n_nodes = gr.needed ? gr.n_nodes : 0u;
+    if (!out || !*n_nodes) return 0;
+    if (max_nodes < *n_nodes) return fail("rt_scene_read_nodes: buffer too small");
+    sync_all(s->ctx);
+    RT_CHECK(rt_d2h(out, s->d_blas_nodes + (size_t)gr.node_off * RT_NODE_F4, (size_t)gr.n_nodes * RT_NODE_F4 * sizeof(float4), s->ctx->stream), "rt_scene_read_nodes");
+    rt_stream_sync(s->ctx->stream);
+    return 0;
+}
+
 int RT_API(rt_scene_bvh_info)(rt_scene* s, rt_bvh_info* o) {
     if (!s || !o) return fail("rt_scene_bvh_info: null argument");
     memset(o, 0, sizeof *o);
+    collect_update_timers(s);
     for (auto& g : s->geo) if (g.needed) o->blas_nodes += g.n_nodes;
     o->blas_nodes += s->merged.n_nodes;
     o->blas_tris = s->total_tris; o->tlas_nodes = s->tlas_nodes;

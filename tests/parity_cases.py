@@ -185,6 +185,20 @@ def case_skinning(api):
     ctx, sc = make(api, d, 32, 32)
     rays, _ = util.random_rays(3000, seed=21, extent=3.0)
     n = d.n_vertices
+    # refit is idempotent: refitting with the pose the BVH was built from reproduces the built nodes byte for byte
+    # (child boxes are exact min / max unions either way), and so does a rebuild (deterministic builder)
+    built = sc.read_nodes(-1)
+    assert built.shape[0] >= 2 and built.shape[1] == 20
+    sc.update_skins(pose(0.0), rebuild=False)
+    assert (sc.read_nodes(-1) == built).all()
+    # a rebuild allocates child / primitive ranges with atomics, so nodes may be numbered differently from run to run:
+    # compare the nodes as a multiset, ignoring the two base-index words
+    def canon(nodes):
+        k = np.delete(nodes, [4, 5], axis=1)
+        return k[np.lexsort(k.T[::-1])]
+    sc.update_skins(pose(0.0), rebuild=True)
+    rebuilt = sc.read_nodes(-1)
+    assert rebuilt.shape == built.shape and (canon(rebuilt) == canon(built)).all()
     for k, phase in enumerate((0.0, 0.9, 2.3)):
         if k:
             mats = pose(phase)

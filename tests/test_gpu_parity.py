@@ -91,6 +91,36 @@ def test_full_size_properties(api):
     assert st.pixel_samples == 16 * 8 * W and st.rays_extend >= st.pixel_samples   # last render: part 7 of 8 owns 16 of the 135 strips
 
 
+def test_full_size_frames_in_flight(api):
+    """1920x1080 depth 8: 4 frames in flight (the bench's mode) leave the accumulation and the presented images
+    bit-identical to strictly ordered rendering; the async presentation copies land in the right host buffers."""
+    d = scenes.cornell_box(lucy=True, lucy_rows=200, lucy_cols=201)
+    W, H, K = 1920, 1080, 9
+    ctx = core.Context(W, H, api=api); sc = core.Scene(ctx, d)
+    cam = host.Camera(W, H).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=8)
+    drv = host.FrameDriver(cam, gui, True)
+    ubos = [drv.next_ubo() for _ in range(K)]
+    outs = []
+    for u in ubos:
+        ctx.render(sc, u)
+        outs.append(ctx.readback(want_acc=False)[1].copy())
+    acc1, _ = ctx.readback()
+    ctx.set_frames_in_flight(4); ctx.resize(W, H)
+    bufs = [np.zeros((H, W, 4), np.uint8) for _ in range(4)]
+    tickets = []
+    for f, u in enumerate(ubos):
+        if len(tickets) >= 4:
+            ctx.frame_wait(tickets[-4])
+            assert (bufs[f % 4] == outs[f - 4]).all(), f       # the frame presented 4 submissions ago
+        ctx.render(sc, u)
+        tickets.append(ctx.readback_async(bufs[f % 4]))
+    ctx.synchronize()
+    for f in range(K - 4, K):
+        assert (bufs[f % 4] == outs[f]).all(), f
+    acc4, out4 = ctx.readback()
+    assert (acc4 == acc1).all() and (out4 == outs[-1]).all()
+
+
 def test_errors_are_reported_not_swallowed(api, cornell_desc):
     ctx = core.Context(32, 32, api=api); sc = core.Scene(ctx, cornell_desc)
     u = F.rt_ubo()   # total_number_of_samples == 0
