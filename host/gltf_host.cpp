@@ -2,6 +2,7 @@
 // animation sampling, skin matrices, camera and per-frame UBO fill.  See include/gltf_host.h for the
 // reference functions each entry point mirrors.  CPU only; produces rt_scene_desc / rt_ubo.
 #include "../include/gltf_host.h"
+#include "mikktspace_gen.h"
 
 #include <dirent.h>
 #include <zlib.h>
@@ -872,8 +873,7 @@ struct Loader {
         if (at.has("TEXCOORD_1")) { View v = view(at.integer("TEXCOORD_1", -1)); for (size_t i = 0; i < nv && i < v.count; ++i) { verts[i].uv1[0] = comp_f32(v, i, 0, true); verts[i].uv1[1] = comp_f32(v, i, 1, true); } }
         if (at.has("TANGENT")) { View v = view(at.integer("TANGENT", -1)); for (size_t i = 0; i < nv && i < v.count; ++i) for (int c = 0; c < 4; ++c) verts[i].tangent[c] = comp_f32(v, i, c, true); }
         else {
-            // geometry.rs:192-212: default (1,0,0,0); the reference runs MikkTSpace when the material has a normal map.
-            // MikkTSpace is row 8f-4 ("next"); until then a per-triangle UV-derivative tangent is generated (documented).
+            // geometry.rs:192-212: default (1,0,0,0); MikkTSpace when the material has a normal map
             for (size_t i = 0; i < nv; ++i) { verts[i].tangent[0] = 1.0f; verts[i].tangent[1] = verts[i].tangent[2] = verts[i].tangent[3] = 0.0f; }
             if (doc.materials[material_index].normal_texture.index >= 0) generate_tangents(verts, idx);
         }
@@ -898,24 +898,12 @@ struct Loader {
         return p;
     }
 
+    // geometry.rs:192-212: mikktspace::generate_tangents over the indexed triangles (restated in mikktspace_gen.h)
     static void generate_tangents(std::vector<rt_vertex>& v, const std::vector<uint32_t>& idx) {
-        for (size_t t = 0; t + 2 < idx.size(); t += 3) {
-            rt_vertex &a = v[idx[t]], &b = v[idx[t + 1]], &c = v[idx[t + 2]];
-            float e1[3], e2[3]; for (int k = 0; k < 3; ++k) { e1[k] = b.position[k] - a.position[k]; e2[k] = c.position[k] - a.position[k]; }
-            float du1 = b.uv0[0] - a.uv0[0], dv1 = b.uv0[1] - a.uv0[1], du2 = c.uv0[0] - a.uv0[0], dv2 = c.uv0[1] - a.uv0[1];
-            float det = du1 * dv2 - du2 * dv1; if (det == 0.0f) continue;
-            float r = 1.0f / det, tg[3], bt[3];
-            for (int k = 0; k < 3; ++k) { tg[k] = (e1[k] * dv2 - e2[k] * dv1) * r; bt[k] = (e2[k] * du1 - e1[k] * du2) * r; }
-            for (rt_vertex* p : {&a, &b, &c}) {
-                float n[3] = {p->normal[0], p->normal[1], p->normal[2]};
-                float d = n[0] * tg[0] + n[1] * tg[1] + n[2] * tg[2];
-                float o[3] = {tg[0] - n[0] * d, tg[1] - n[1] * d, tg[2] - n[2] * d};
-                float l = std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]); if (!(l > 0)) continue;
-                float cx[3] = {n[1] * o[2] - n[2] * o[1], n[2] * o[0] - n[0] * o[2], n[0] * o[1] - n[1] * o[0]};
-                float w = (cx[0] * bt[0] + cx[1] * bt[1] + cx[2] * bt[2]) < 0 ? -1.0f : 1.0f;
-                p->tangent[0] = o[0] / l; p->tangent[1] = o[1] / l; p->tangent[2] = o[2] / l; p->tangent[3] = w;
-            }
-        }
+        if (v.empty() || idx.size() < 3) return;
+        const size_t stride = sizeof(rt_vertex) / sizeof(float);
+        mikk::Mesh m{v[0].position, v[0].normal, v[0].uv0, stride};
+        mikk::generate(m, v.size(), idx.data(), idx.size(), v[0].tangent, stride);
     }
 
     void load_textures() {
@@ -1301,6 +1289,13 @@ int gv_load_skybox_dir(const char* dir, uint8_t* faces[6], uint32_t* w, uint32_t
     }
     *w = fw; *h = fh;
     return 0;
+}
+
+void gv_generate_tangents(rt_vertex* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices) {
+    if (!vertices || !indices || !n_vertices || n_indices < 3) return;
+    const size_t stride = sizeof(rt_vertex) / sizeof(float);
+    mikk::Mesh m{vertices[0].position, vertices[0].normal, vertices[0].uv0, stride};
+    mikk::generate(m, n_vertices, indices, n_indices, vertices[0].tangent, stride);
 }
 
 int gv_decode_image(const uint8_t* data, size_t size, uint8_t** rgba, uint32_t* w, uint32_t* h) {

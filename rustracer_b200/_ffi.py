@@ -179,7 +179,7 @@ GV_EXPORTS = [
     "gv_doc_static_scene", "gv_doc_need_compute", "gv_doc_aabb_trans", "gv_doc_animate", "gv_doc_get_skins",
     "gv_doc_get_instances", "gv_doc_set_skybox", "gv_camera_default", "gv_camera_view_matrix",
     "gv_camera_projection_matrix", "gv_mat4_inverse", "gv_gui_default", "gv_build_ubo", "gv_decode_png", "gv_decode_image",
-    "gv_load_skybox_dir", "gv_free",
+    "gv_load_skybox_dir", "gv_free", "gv_generate_tangents",
 ]
 
 _rt = None
@@ -220,6 +220,8 @@ def load_host() -> C.CDLL:
         lib.gv_decode_png.argtypes = [c_u8p, C.c_size_t, C.POINTER(c_u8p), C.POINTER(c_u32), C.POINTER(c_u32)]
         lib.gv_decode_image.argtypes = [c_u8p, C.c_size_t, C.POINTER(c_u8p), C.POINTER(c_u32), C.POINTER(c_u32)]
         lib.gv_load_skybox_dir.argtypes = [C.c_char_p, c_u8p * 6, C.POINTER(c_u32), C.POINTER(c_u32)]
+        lib.gv_generate_tangents.argtypes = [C.POINTER(rt_vertex), c_u32, C.POINTER(c_u32), c_u32]
+        lib.gv_generate_tangents.restype = None
         lib.gv_free.argtypes = [C.c_void_p]
         lib.gv_free.restype = None
         _host = lib

@@ -221,3 +221,79 @@ def test_skybox_directory_loader(tmp_path):
         faces = host.load_skybox_dir(ref_dir)
         for f, n in zip(faces, ("posx", "negx", "posy", "negy", "posz", "negz")):
             assert np.array_equal(f, np.asarray(Image.open(ref_dir / f"{n}.jpg").convert("RGBA"))), n
+
+
+# ---- MikkTSpace restatement (host/mikktspace_gen.h; geometry.rs:192-212,296-350) ---------------------------------
+def _gen_tangents(pos, nrm, uv, idx):
+    v = np.zeros(len(pos), F.VERTEX_DTYPE)
+    v["position"][:, :3] = pos; v["normal"][:, :3] = nrm; v["uv0"] = uv
+    v["tangent"] = [1, 0, 0, 0]                                     # the reference's pre-fill (geometry.rs:195)
+    idx = np.ascontiguousarray(idx, np.uint32).reshape(-1)
+    F.load_host().gv_generate_tangents(F.as_ptr(v, F.rt_vertex), len(v), F.as_ptr(idx, F.c_u32), len(idx))
+    return v["tangent"].copy()
+
+
+def _grid(n, fn):
+    """(n+1)^2 vertices over (u, v) in [0,1]^2, two CCW triangles per cell; fn(u, v) -> position, normal."""
+    us, vs = np.meshgrid(np.linspace(0, 1, n + 1), np.linspace(0, 1, n + 1), indexing="xy")
+    uv = np.stack([us.ravel(), vs.ravel()], 1).astype(np.float32)
+    pos, nrm = fn(uv[:, 0].astype(np.float64), uv[:, 1].astype(np.float64))
+    idx = []
+    for j in range(n):
+        for i in range(n):
+            a = j * (n + 1) + i; b = a + 1; c = a + n + 1; d = c + 1
+            idx += [a, b, d, a, d, c]
+    return pos.astype(np.float32), nrm.astype(np.float32), uv, np.array(idx, np.uint32)
+
+
+def test_mikktspace_plane_and_mirrored_uv():
+    plane = lambda u, v: (np.stack([2 * u, 3 * v, 0 * u], 1), np.tile([0.0, 0.0, 1.0], (len(u), 1)))
+    pos, nrm, uv, idx = _grid(6, plane)
+    t = _gen_tangents(pos, nrm, uv, idx)
+    # tangent = d(position)/du direction, unit length; UV orientation preserved -> w = -1 (the reference's inverted sign)
+    np.testing.assert_allclose(t[:, :3], np.tile([1, 0, 0], (len(t), 1)), atol=1e-6)
+    assert (t[:, 3] == -1).all()
+    # mirror the u coordinate: dP/du flips and the orientation flag with it
+    t2 = _gen_tangents(pos, nrm, np.stack([1 - uv[:, 0], uv[:, 1]], 1), idx)
+    np.testing.assert_allclose(t2[:, :3], np.tile([-1, 0, 0], (len(t), 1)), atol=1e-6)
+    assert (t2[:, 3] == 1).all()
+    # a constant UV mapping has no tangent: such triangles cannot found a group, vertices keep the default frame
+    t3 = _gen_tangents(pos, nrm, np.zeros_like(uv), idx)
+    assert (t3 == [1, 0, 0, 1]).all()
+
+
+def test_mikktspace_sphere_matches_analytic_tangent():
+    def sphere(u, v):
+        th, ph = 2 * np.pi * u, np.pi * (0.1 + 0.8 * v)              # stay away from the poles
+        p = np.stack([np.sin(ph) * np.cos(th), np.cos(ph), np.sin(ph) * np.sin(th)], 1)
+        return p, p
+    pos, nrm, uv, idx = _grid(48, sphere)
+    t = _gen_tangents(pos, nrm, uv, idx)
+    th = 2 * np.pi * uv[:, 0].astype(np.float64)
+    analytic = np.stack([-np.sin(th), 0 * th, np.cos(th)], 1)        # dP/du, normalised
+    inner = np.ones(len(t), bool)
+    inner[(uv[:, 0] == 0) | (uv[:, 0] == 1) | (uv[:, 1] == 0) | (uv[:, 1] == 1)] = False   # one-sided at the borders
+    assert np.abs(np.linalg.norm(t[:, :3], axis=1) - 1).max() < 1e-5
+    assert np.abs((t[:, :3] * nrm).sum(1)).max() < 1e-5              # in the tangent plane of the vertex normal
+    assert (t[inner, :3] * analytic[inner]).sum(1).min() > 0.999
+    assert len(set(t[:, 3])) == 1                                    # one orientation over the whole surface
+
+
+def test_mikktspace_degenerate_and_duplicate_vertices():
+    plane = lambda u, v: (np.stack([u, v, 0 * u], 1), np.tile([0.0, 0.0, 1.0], (len(u), 1)))
+    pos, nrm, uv, idx = _grid(3, plane)
+    base = _gen_tangents(pos, nrm, uv, idx)
+    # un-index the mesh: every corner its own vertex; welding must give the same per-vertex result
+    pos2, nrm2, uv2 = pos[idx], nrm[idx], uv[idx]
+    t2 = _gen_tangents(pos2, nrm2, uv2, np.arange(len(idx), dtype=np.uint32))
+    np.testing.assert_allclose(t2, base[idx], atol=1e-6)
+    # a degenerate triangle (two equal positions) that shares vertex 5 with good triangles copies their frame;
+    # one built from otherwise unused vertices keeps the default frame with w = +1
+    extra_p = np.array([[9, 9, 0], [9, 9, 0], [8, 9, 0]], np.float32)
+    pos3 = np.concatenate([pos, extra_p]); nrm3 = np.concatenate([nrm, np.tile([0, 0, 1], (3, 1)).astype(np.float32)])
+    uv3 = np.concatenate([uv, np.array([[0, 0], [1, 0], [0, 1]], np.float32)])
+    n0 = len(pos)
+    idx3 = np.concatenate([idx, np.array([5, 5, 6, n0, n0 + 1, n0 + 2], np.uint32)])
+    t3 = _gen_tangents(pos3, nrm3, uv3, idx3)
+    np.testing.assert_allclose(t3[:n0], base, atol=1e-6)
+    assert (t3[n0:] == [1, 0, 0, 1]).all()
