@@ -102,16 +102,28 @@ class ClockSampler:
                 break
             time.sleep(0.005)
 
-    def start(self):
+    def prepare(self):
+        """NVML initialisation takes milliseconds and varies from process to process: do it before the barrier that
+        precedes the timed region, so that the ranks enter the region together."""
         try:
             self.handle = self._nvml_handle()
             self.max_sm = self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            self.source = "nvml"
-            return
+            self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
         except Exception:
             self.nvml = None
+        return self
+
+    def start(self):
+        if self.nvml is None and self.handle is None:
+            self.prepare()
+        if self.nvml is not None:
+            try:
+                self.t = threading.Thread(target=self._poll, daemon=True)
+                self.t.start()
+                self.source = "nvml"
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.dev)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -330,14 +342,17 @@ def run_ours(args):
     ctx.resize(WIDTH, HEIGHT)
     frames(0, Wm)
     ctx.synchronize()
-    barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local).prepare()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
     e0.record()
+    t_loop0 = time.perf_counter()
     for s in range(Wm, Wm + K):
         pre_step(s)
         ctx.render(scene, ubos[s], stream=stream)
     t_sub = time.perf_counter()
+    t_enq = t_sub - t_loop0
     if world > 1:
         ctx.synchronize(); t_sync = time.perf_counter()
         dist.barrier()                         # all ranks must have finished rendering before peers are read
@@ -349,7 +364,7 @@ def run_ours(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     if world > 1 and os.environ.get("BENCH_DEBUG"):
-        print(f"[rank {rank}] timed region {ms:.3f} ms; host: submit->sync {1e3 * (t_sync - t_sub):.3f} ms, barrier {1e3 * (t_bar - t_sync):.3f} ms", file=sys.stderr, flush=True)
+        print(f"[rank {rank}] timed region {ms:.3f} ms; host: enqueue {1e3 * t_enq:.3f} ms, submit->sync {1e3 * (t_sync - t_sub):.3f} ms, barrier {1e3 * (t_bar - t_sync):.3f} ms; clocks {clocks}", file=sys.stderr, flush=True)
     tmax = torch.tensor([ms], device="cuda")
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
