@@ -339,6 +339,8 @@ def run_ours(args):
     # overlaps on the GPU, the accumulation stays in submission order (bit-identical images, tests/parity_cases.py)
     NF = max(1, min(4, args.frames_in_flight))
     ctx.set_frames_in_flight(NF)
+    if POSE is not None:
+        scene.set_versions(max(2, min(4, args.scene_versions)))   # skin updates write the next copy while frames read the previous ones
     ctx.resize(WIDTH, HEIGHT)
     frames(0, Wm)
     ctx.synchronize()
@@ -487,6 +489,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene-versions", type=int, default=3, help="config 4: copies of the buffers a skin update rewrites (2..4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="frames whose path tracing may overlap on one GPU (1..4; reference: IN_FLIGHT_FRAMES = 2)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (default 2 = the headline workload)")

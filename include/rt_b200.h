@@ -281,8 +281,14 @@ void rt_scene_destroy(rt_scene* scene);
 /* replaces create_top_as + update_tlas (acceleration_structures.rs:136 ; main.rs:397-409,424-436) */
 int rt_scene_update_instances(rt_scene* scene, const rt_instance* instances, uint32_t n);
 /* replaces skin.copy_data_to_buffer + ComputeUnit::dispatch + create_as (main.rs:384-395,
-   compute_unit.rs:30-68): skinning kernel, BLAS refit (rebuild != 0: full rebuild), TLAS rebuild */
+   compute_unit.rs:30-68): skinning kernel, BLAS refit + TLAS refit (asynchronous: queued on the scene's stream,
+   later frames wait for it on the device) or, with rebuild != 0, full BLAS + TLAS rebuild (synchronous) */
 int rt_scene_update_skins(rt_scene* scene, const float* skin_mats, uint32_t n_skins, int rebuild);
+/* Skinned scenes keep n (1..4, default 2 when the scene has skins, else 1) copies of what a skin update rewrites
+   (skinned vertices, packed triangles, BLAS / TLAS nodes).  A refit writes the next copy and only waits, on the
+   device, for the frames that still read it, so the update of frame f+1 overlaps the frames in flight; the host
+   never blocks (rebuild != 0 and rt_scene_update_instances stay synchronous).  Synchronises. */
+int rt_scene_set_versions(rt_scene* scene, uint32_t n);
 /* replaces dlights_buffer / plights_buffer.copy_data_to_buffer (main.rs:353-374) */
 int rt_scene_update_lights(rt_scene* scene, const rt_light* dlights, uint32_t n_dlights,
                            const rt_light* plights, uint32_t n_plights);

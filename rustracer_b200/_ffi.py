@@ -172,7 +172,7 @@ RT_EXPORTS = [
     "rt_readback", "rt_upload_accumulation", "rt_device_ptrs", "rt_last_frame_stats", "rt_trace_closest",
     "rt_trace_any", "rt_scene_read_vertices", "rt_scene_bvh_info", "rt_ipc_export", "rt_ipc_open",
     "rt_ipc_close", "rt_reduce_peers", "rt_context_set_frames_in_flight", "rt_join", "rt_readback_async",
-    "rt_frame_wait", "rt_scene_read_nodes",
+    "rt_frame_wait", "rt_scene_read_nodes", "rt_scene_set_versions",
 ]
 GV_EXPORTS = [
     "gv_last_error", "gv_load_file", "gv_doc_free", "gv_doc_scene_desc", "gv_doc_fully_opaque",
@@ -261,6 +261,7 @@ def bind_rt(lib: C.CDLL, rename=lambda n: n, optional=()) -> C.CDLL:
         "rt_join": ([vp, vp], C.c_int),
         "rt_readback_async": ([vp, c_u8p, C.POINTER(C.c_uint64)], C.c_int),
         "rt_frame_wait": ([vp, C.c_uint64], C.c_int),
+        "rt_scene_set_versions": ([vp, c_u32], C.c_int),
         "rt_scene_read_nodes": ([vp, C.c_int, C.POINTER(c_f), c_u32, C.POINTER(c_u32)], C.c_int),
     }
     assert set(sigs) == set(RT_EXPORTS)

@@ -135,6 +135,10 @@ class Scene:
         mats = np.ascontiguousarray(mats, np.float32)
         self.api.check(self.api.rt_scene_update_skins(self._h, F.as_ptr(mats, F.c_f), mats.size // 4096, int(rebuild)))
 
+    def set_versions(self, n: int):
+        """Copies of the buffers a skin update rewrites (default 2 for skinned scenes): updates overlap frames in flight."""
+        self.api.check(self.api.rt_scene_set_versions(self._h, n))
+
     def update_lights(self, dlights: np.ndarray, plights: np.ndarray):
         d = np.ascontiguousarray(dlights, F.LIGHT_DTYPE)
         p = np.ascontiguousarray(plights, F.LIGHT_DTYPE)

@@ -61,6 +61,7 @@ struct StageEvent { int stage; rt_timer a, b; };
 using namespace rtcore;
 
 #define RT_MAX_FRAMES_IN_FLIGHT 4
+#define RT_MAX_SCENE_VERSIONS 4
 
 // One frame in flight: everything a frame writes except the shared accumulation image.  Mirrors the reference's
 // InFlightFrames (app/src/lib.rs:34,329,400-401: IN_FLIGHT_FRAMES = 2, one fence per frame) and its per-swapchain-image
@@ -79,6 +80,7 @@ struct FrameSlot {
     std::vector<StageEvent> stage_events; size_t stage_used = 0;
     unsigned long long launches_before = 0, launches_after = 0;
     rt_event done; bool pending = false;   // recorded after the last operation queued for this slot
+    const void* scene = nullptr; uint32_t scene_version = 0;   // what the slot's last frame reads (animated scenes are multi-buffered)
 };
 
 struct rt_context {
@@ -126,6 +128,13 @@ struct rt_scene {
     bool has_nee = false;
     bool plain_materials = false;            // no texture reference and no specular-glossiness material anywhere
     float build_ms = 0, refit_ms = 0, skin_ms = 0, tlas_ms = 0;
+    // Buffers a skin update rewrites while frames may still read them: skinned vertices, packed triangles, BLAS and
+    // TLAS nodes.  A skinned scene keeps n_versions copies; d_vout / d_tris / d_blas_nodes / d_tlas_nodes alias the
+    // current one, a refit switches to the next and only waits for the frames that still read THAT copy, so the
+    // update of frame f+1 overlaps the rendering of frame f (the reference rebuilds in place behind three fence waits,
+    // gltf_viewer/src/main.rs:384-395).
+    struct Version { rt_vertex* vout = nullptr; float4 *tris = nullptr, *blas_nodes = nullptr, *tlas_nodes = nullptr; };
+    Version ver[RT_MAX_SCENE_VERSIONS]; uint32_t n_versions = 1, cur_ver = 0;
     // TLAS refit state (rt_scene_update_skins keeps the TLAS topology): leaf k -> entry, boxes in leaf order, counters
     uint32_t* d_tlas_leaf_entry = nullptr; DAabb* d_tlas_leaf_boxes = nullptr; uint32_t* d_tlas_pending = nullptr; uint32_t tlas_entries = 0;
     // asynchronous skin updates: frames wait for ev_updated on the device; the stage timers are read lazily
@@ -182,6 +191,34 @@ static void update_ds(rt_scene* s) {
     d.vertices = s->d_vout; d.indices = s->d_indices; d.prim_infos = s->d_prim; d.materials = s->d_mat;
     d.textures = s->d_textures; d.images = s->d_images; d.srgb_lut = s->d_lut;
     d.dlights = s->d_dl; d.plights = s->d_pl;
+}
+
+// ---- multi-buffered animated scenes ---------------------------------------------------------------------
+static size_t ver_bytes_vout(const rt_scene* s) { return (size_t)(s->n_vertices ? s->n_vertices : 1) * sizeof(rt_vertex); }
+static size_t ver_bytes_tris(const rt_scene* s) { return (size_t)(s->total_tris ? s->total_tris : 1) * RT_TRI_F4 * sizeof(float4); }
+static size_t ver_bytes_blas(const rt_scene* s) { return (size_t)(s->total_nodes ? s->total_nodes : 1) * RT_NODE_F4 * sizeof(float4); }
+static size_t ver_bytes_tlas(const rt_scene* s) { return (size_t)(s->instances.size() + 1) * RT_NODE_F4 * sizeof(float4); }
+static void use_version(rt_scene* s, uint32_t v) {
+    s->cur_ver = v;
+    s->d_vout = s->ver[v].vout; s->d_tris = s->ver[v].tris; s->d_blas_nodes = s->ver[v].blas_nodes; s->d_tlas_nodes = s->ver[v].tlas_nodes;
+}
+// after a (synchronous) build every copy must hold the new topology: replicate the current version
+static int replicate_versions(rt_scene* s) {
+    rt_stream_t st = s->ctx->stream; const uint32_t c = s->cur_ver; int e = 0;
+    for (uint32_t v = 0; v < s->n_versions; ++v) {
+        if (v == c) continue;
+        e |= rt_d2d(s->ver[v].vout, s->ver[c].vout, ver_bytes_vout(s), st); e |= rt_d2d(s->ver[v].tris, s->ver[c].tris, ver_bytes_tris(s), st);
+        e |= rt_d2d(s->ver[v].blas_nodes, s->ver[c].blas_nodes, ver_bytes_blas(s), st); e |= rt_d2d(s->ver[v].tlas_nodes, s->ver[c].tlas_nodes, ver_bytes_tlas(s), st);
+    }
+    return e;
+}
+static int alloc_versions(rt_scene* s, uint32_t n) {
+    for (uint32_t v = s->n_versions; v < n; ++v) {
+        int e = rt_malloc((void**)&s->ver[v].vout, ver_bytes_vout(s)); e |= rt_malloc((void**)&s->ver[v].tris, ver_bytes_tris(s));
+        e |= rt_malloc((void**)&s->ver[v].blas_nodes, ver_bytes_blas(s)); e |= rt_malloc((void**)&s->ver[v].tlas_nodes, ver_bytes_tlas(s));
+        if (e) return 1;
+    }
+    return 0;
 }
 
 static int run_skinning(rt_scene* s) {
@@ -687,6 +724,10 @@ void RT_API(rt_scene_destroy)(rt_scene* s) {
                     s->d_tlas_nodes, s->d_tlas_prims, s->d_tlas_box, s->d_tlas_parent, s->d_inst_boxes, s->d_inst_w2o, s->d_inst_o2w, s->d_inst_root, s->d_entry_rec, s->d_bake_src,
                     s->d_tlas_leaf_entry, s->d_tlas_leaf_boxes, s->d_tlas_pending};
     for (void* p : ptrs) if (p) rt_free(p);
+    for (uint32_t v = 0; v < s->n_versions; ++v) {      // (the current version's buffers were freed through their aliases above)
+        if (v == s->cur_ver) continue;
+        rt_free(s->ver[v].vout); rt_free(s->ver[v].tris); rt_free(s->ver[v].blas_nodes); rt_free(s->ver[v].tlas_nodes);
+    }
     for (uint8_t* p : s->d_image_px) if (p) rt_free(p);
     for (int f = 0; f < 6; ++f) if (s->d_sky[f]) rt_free(s->d_sky[f]);
     scratch_free(s->scratch);
@@ -819,6 +860,14 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
     if (rt_stream_sync(st)) { t0.destroy(); t1.destroy(); t2.destroy(); return bail(std::string("rt_scene_create: device error: ") + rt_platform_error()); }
     s->build_ms = rt_timer_ms(t0, t1); s->tlas_ms = rt_timer_ms(t1, t2);
     t0.destroy(); t1.destroy(); t2.destroy();
+    // skinned scenes are double-buffered so that a skin update overlaps the frames still reading the previous pose
+    s->ver[0].vout = s->d_vout; s->ver[0].tris = s->d_tris; s->ver[0].blas_nodes = s->d_blas_nodes; s->ver[0].tlas_nodes = s->d_tlas_nodes;
+    s->n_versions = 1; s->cur_ver = 0;
+    if (d->n_skins) {
+        if (alloc_versions(s, 2)) return bail(std::string("rt_scene_create: allocation failed: ") + rt_platform_error());
+        s->n_versions = 2;
+        if (replicate_versions(s) || rt_stream_sync(st)) return bail(std::string("rt_scene_create: device error: ") + rt_platform_error());
+    }
     update_ds(s);
     *out = s;
     return 0;
@@ -834,7 +883,8 @@ int RT_API(rt_scene_update_instances)(rt_scene* s, const rt_instance* inst, uint
     rt_timer t0, t1; t0.create(); t1.create(); t0.record(s->ctx->stream);
     if (upload_instance_records(s)) { t0.destroy(); t1.destroy(); return 1; }
     if (s->merged.n_tris) refit_merged(s);        // baked instances moved: re-bake their triangles, refit the merged BLAS
-    const int e = build_tlas(s);
+    int e = build_tlas(s);
+    if (!e) e = replicate_versions(s);
     t1.record(s->ctx->stream); rt_stream_sync(s->ctx->stream); s->tlas_ms = rt_timer_ms(t0, t1); t0.destroy(); t1.destroy();
     if (e) return 1;
     update_ds(s);
@@ -859,8 +909,16 @@ int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_ski
     // Frames in flight (or on a caller's stream) still read the vertices / BVH rewritten below: the scene's stream
     // waits for them on the device.  A refit never blocks the host: skinning, BLAS refit and TLAS refit are queued,
     // later frames wait for ev_updated.  A rebuild reads builder counters back level by level and is synchronous.
-    join_frames(s->ctx, st);
+    if (rebuild || s->n_versions == 1) join_frames(s->ctx, st);
     if (rebuild) sync_all(s->ctx);
+    if (!rebuild && s->n_versions > 1) {
+        // write the next copy; only the frames that still read that copy have to finish first
+        const uint32_t next = (s->cur_ver + 1) % s->n_versions;
+        rt_context* c = s->ctx;
+        for (uint32_t k = 0; k < c->n_slots; ++k)
+            if (c->slot[k].pending && c->slot[k].scene == (const void*)s && c->slot[k].scene_version == next) c->slot[k].done.wait(st);
+        use_version(s, next);
+    }
     if (!s->upd_timers_created) { for (auto& t : s->upd_t) t.create(); s->ev_updated.create(); s->upd_timers_created = true; }
     collect_update_timers(s);     // (the events are about to be re-recorded)
     RT_CHECK(rt_h2d(s->d_skins, mats, (size_t)n_skins * RT_MAX_JOINTS * 16 * 4, st), "skin upload");
@@ -878,7 +936,33 @@ int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_ski
     s->upd_timers_pending = true;
     s->ev_updated.record(st); s->update_pending = true;
     if (e) return 1;
-    if (rebuild) { if (rt_stream_sync(st)) return fail(std::string("rt_scene_update_skins: ") + rt_platform_error()); }
+    if (rebuild) {
+        if (replicate_versions(s) || rt_stream_sync(st)) return fail(std::string("rt_scene_update_skins: ") + rt_platform_error());
+    }
+    update_ds(s);
+    return 0;
+}
+
+int RT_API(rt_scene_set_versions)(rt_scene* s, uint32_t n) {
+    if (!s) return fail("rt_scene_set_versions: null scene");
+    if (n < 1 || n > RT_MAX_SCENE_VERSIONS) return fail("rt_scene_set_versions: n must be 1..4");
+    if (n == s->n_versions) return 0;
+    if (sync_all(s->ctx)) return fail(std::string("rt_scene_set_versions: ") + rt_platform_error());
+    if (n < s->n_versions) {
+        // keep the current copy as version 0
+        if (s->cur_ver != 0) { std::swap(s->ver[0], s->ver[s->cur_ver]); use_version(s, 0); }
+        for (uint32_t v = n; v < s->n_versions; ++v) { rt_free(s->ver[v].vout); rt_free(s->ver[v].tris); rt_free(s->ver[v].blas_nodes); rt_free(s->ver[v].tlas_nodes); s->ver[v] = rt_scene::Version{}; }
+        s->n_versions = n;
+    } else {
+        const uint32_t old_n = s->n_versions;
+        if (alloc_versions(s, n)) {
+            for (uint32_t v = old_n; v < n; ++v) { rt_free(s->ver[v].vout); rt_free(s->ver[v].tris); rt_free(s->ver[v].blas_nodes); rt_free(s->ver[v].tlas_nodes); s->ver[v] = rt_scene::Version{}; }
+            return fail(std::string("rt_scene_set_versions: allocation failed: ") + rt_platform_error());
+        }
+        s->n_versions = n;
+        if (replicate_versions(s) || rt_stream_sync(s->ctx->stream)) return fail(std::string("rt_scene_set_versions: ") + rt_platform_error());
+    }
+    for (uint32_t k = 0; k < RT_MAX_FRAMES_IN_FLIGHT; ++k) if (s->ctx->slot[k].scene == (const void*)s) s->ctx->slot[k].scene_version = s->cur_ver;
     update_ds(s);
     return 0;
 }
@@ -943,6 +1027,7 @@ int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_re
     else e = count ? render_frame<false, true>(c, f, s, P, tp, flags, st) : render_frame<false, false>(c, f, s, P, tp, flags, st);
     if (c->timers) f->ev_end.record(st);
     f->done.record(st); f->pending = true;
+    f->scene = s; f->scene_version = s->cur_ver;
     c->cur = k; ++c->frame_seq;
 #ifndef RT_EMU
     f->launches_after = g_rt_launch_count;

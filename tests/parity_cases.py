@@ -278,6 +278,42 @@ def case_skinned_character(api, n_tris=20000, joints=64, size=48, frames=3):
         assert util.mean_rel_err(acc_g, acc, 2) < 0.02 and util.psnr(out_g[..., :3], out[..., :3]) >= 35.0
 
 
+def case_skinned_in_flight(api, n_tris=20000, joints=64, size=48, frames=7):
+    """Animated scene with frames in flight: the skin update of frame f+1 is queued while earlier frames still render
+    (multi-buffered skinned vertices / triangles / BVH nodes).  Every presented frame must be bit-identical to the
+    strictly serial run (1 scene copy, 1 frame in flight)."""
+    d, pose = scenes.skinned_character(n_tris=n_tris, joints=joints)
+    ctx, sc = make(api, d, size, size)
+    cam = host.Camera(size, size).set(position=(0, 0, 9.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=5, animation=1)
+    drv = host.FrameDriver(cam, gui, True)
+    ubos = [drv.next_ubo() for _ in range(frames)]
+    poses = [pose(3 + 5 * f) for f in range(frames)]
+    sc.set_versions(1)
+    ref = []
+    for u, m in zip(ubos, poses):
+        sc.update_skins(m); ctx.render(sc, u)
+        ref.append(ctx.readback(want_acc=False)[1].copy())
+    assert any((ref[0] != r).any() for r in ref[1:])                 # the animation does move pixels
+    for n_ver, nf in ((2, 2), (3, 4), (2, 4), (4, 3)):
+        sc.set_versions(n_ver); ctx.set_frames_in_flight(nf); ctx.resize(size, size)
+        bufs = [np.zeros((size, size, 4), np.uint8) for _ in range(frames)]
+        tickets = []
+        for u, m, b in zip(ubos, poses, bufs):
+            sc.update_skins(m); ctx.render(sc, u)
+            tickets.append(ctx.readback_async(b))
+        for t in tickets:
+            ctx.frame_wait(t)
+        for f, (b, r) in enumerate(zip(bufs, ref)):
+            assert (b == r).all(), (n_ver, nf, f)
+    # a rebuild is synchronous and replicates the new topology into every copy
+    sc.update_skins(poses[0], rebuild=True); ctx.render(sc, ubos[0])
+    first = ctx.readback(want_acc=False)[1].copy()
+    sc.update_skins(poses[1]); ctx.render(sc, ubos[1]); sc.update_skins(poses[0]); ctx.render(sc, ubos[0])
+    assert (ctx.readback(want_acc=False)[1] == first).all()
+    with __import__("pytest").raises(core.RtError):
+        sc.set_versions(5)
+
+
 def case_frame_options(api, cornell_desc, cornell_oracle, size=48):
     """UBO variants of RayTracing.rgen / Tonemapping.glsl / rchit debug path: thin lens (LCG stream), orthographic
     camera, every tone-map mode, DISTANCE and HEAT mappings, debug == 1, no anti-aliasing, spp > 1, bounce limits."""

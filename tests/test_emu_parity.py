@@ -51,3 +51,7 @@ def test_emu_skinned_character():
 
 def test_emu_frame_options(cornell_desc, cornell_oracle):
     pc.case_frame_options(emu_api(), cornell_desc, cornell_oracle, size=32)
+
+
+def test_emu_skinned_in_flight_bookkeeping():
+    pc.case_skinned_in_flight(emu_api(), n_tris=1500, joints=16, size=20, frames=4)

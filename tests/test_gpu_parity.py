@@ -147,6 +147,11 @@ def test_skinned_character_per_frame(api):
     pc.case_skinned_character(api, n_tris=200000, joints=256, size=96, frames=3)
 
 
+def test_skinned_animation_with_frames_in_flight(api):
+    """Skin updates overlap the frames in flight (multi-buffered scene): every frame bit-identical to the serial run."""
+    pc.case_skinned_in_flight(api, n_tris=200000, joints=256, size=160, frames=9)
+
+
 def test_frame_options(api, cornell_desc, cornell_oracle):
     """Lens, orthographic camera, all tone-map modes, DISTANCE / HEAT / debug mappings, debug == 1, spp > 1."""
     pc.case_frame_options(api, cornell_desc, cornell_oracle, size=96)
