@@ -69,6 +69,12 @@ __global__ void __launch_bounds__(256) reduce_peers_kernel(float4* acc, uint32_t
 
 extern "C" {
 
+#ifdef RT_PROBE
+int rt_debug_probe(unsigned long long* out, uint32_t n_warps) {
+    cudaDeviceSynchronize();
+    return chk(cudaMemcpyFromSymbol(out, g_probe, (size_t)n_warps * 6 * sizeof(unsigned long long)));
+}
+#endif
 int rt_ipc_export(rt_context* c, void* handle64) {
     if (!c || !handle64) return fail("rt_ipc_export: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");

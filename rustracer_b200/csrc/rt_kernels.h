@@ -220,6 +220,11 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 #define RT_TQ_CAP 256u         // per-warp triangle queue capacity (power of two, >= 31 + 32 * RT_TQ_PUSH_MAX)
 #define RT_TQ_TRI_BITS 27      // item = owner lane << 27 | absolute triangle index
 
+#ifdef RT_PROBE
+// developer probe (variant builds only, scripts/gpu_probe.py): per-warp start / queue-exhausted / exit times, rays, iterations
+__device__ unsigned long long g_probe[8192 * 6];
+RT_D unsigned long long rt_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
 template <bool ALPHA>
 struct CoopShared {            // one per warp; SoA over the 32 owner lanes
     float ox[32], oy[32], oz[32], Sx[32], Sy[32], Sz[32], tmin[32], tmax[32], cur_t[32], u[32], v[32];
@@ -318,6 +323,9 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
     uint32_t q_head = 0, q_count = 0;           // warp-uniform queue cursor
     if (lane == 0) sh.tail = 0u;
     __syncwarp();
+#ifdef RT_PROBE
+    const unsigned long long probe_t0 = rt_globaltimer(); unsigned long long probe_tx = 0; uint32_t probe_rays = 0, probe_iters = 0;
+#endif
     for (;;) {
         if (!exhausted) {
             const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && outstanding == 0u);
@@ -331,6 +339,10 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                     if (idx < count) { load_ray(idx, tv); active = true; if (SINGLE || tv.blas_sp >= 0) coop_publish_ray<ALPHA, SINGLE>(tv, sh, lane); }
                 }
                 if (base + (uint32_t)__popc(need) >= count) exhausted = true;
+#ifdef RT_PROBE
+                probe_rays += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, active && idx >= base && idx < count && idx - base < 32u));
+                if (exhausted) probe_tx = rt_globaltimer();
+#endif
             }
         }
         if (!__ballot_sync(0xFFFFFFFFu, active || outstanding != 0u)) break;
@@ -422,6 +434,9 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                 trav_finish(tv); store_hit(idx, tv); active = false;
             }
             holding = __ballot_sync(0xFFFFFFFFu, active);
+#ifdef RT_PROBE
+            ++probe_iters;
+#endif
         } while (holding && (exhausted || __popc(holding) >= RT_REFILL_BELOW));
         // lanes whose any-hit ray retired early may still own queued items: drain so they can be refilled
         if (__any_sync(0xFFFFFFFFu, !active && outstanding != 0u)) {
@@ -434,6 +449,16 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             }
         }
     }
+#ifdef RT_PROBE
+    if (lane == 0) {
+        const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (wid < 8192u) {
+            unsigned long long* p = g_probe + (size_t)wid * 6;
+            p[0] = probe_t0; p[1] = probe_tx; p[2] = rt_globaltimer(); p[3] = probe_rays; p[4] = probe_iters;
+            uint32_t smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid)); p[5] = smid;
+        }
+    }
+#endif
     if (COUNT && cnt) {
         atomicAdd(&cnt->nodes, c4[0]); atomicAdd(&cnt->tris, c4[1]); atomicAdd(&cnt->insts, c4[2]); atomicAdd(&cnt->anyhits, c4[3]);
     }
