@@ -68,10 +68,10 @@ void gv_build_ubo(const gv_camera* cam, const gv_gui* gui, uint32_t* total_numbe
 
 /* PNG decoder used for embedded glTF images (8-bit, non-interlaced): returns RGBA8 via malloc */
 int  gv_decode_png(const uint8_t* data, size_t size, uint8_t** rgba, uint32_t* w, uint32_t* h);
-/* PNG (8 bit) or JPEG (baseline / progressive, 8 bit) -> RGBA8; replaces image::ImageReader::decode (image.rs:60-83) */
 /* geometry.rs:192-212,296-350: mikktspace::generate_tangents over an indexed triangle list (written into
    vertices[i].tangent; last face touching a vertex wins, w = -1 when the bitangent preserves orientation) */
 void gv_generate_tangents(rt_vertex* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices);
+/* PNG (8 bit) or JPEG (baseline / progressive, 8 bit) -> RGBA8; replaces image::ImageReader::decode (image.rs:60-83) */
 int  gv_decode_image(const uint8_t* data, size_t size, uint8_t** rgba, uint32_t* w, uint32_t* h);
 /* SkyBox::new (asset_loader/src/cubumap.rs:86-106): six faces of a directory in +x,-x,+y,-y,+z,-z order, RGBA8 (sRGB).
    Each faces[f] is malloc'd: release with gv_free. */

@@ -297,3 +297,32 @@ def test_mikktspace_degenerate_and_duplicate_vertices():
     t3 = _gen_tangents(pos3, nrm3, uv3, idx3)
     np.testing.assert_allclose(t3[:n0], base, atol=1e-6)
     assert (t3[n0:] == [1, 0, 0, 1]).all()
+
+
+VIEWER = Path(__file__).resolve().parents[1] / "host" / "_build" / "gltf_viewer"
+
+
+def test_cpp_gltf_viewer_cli_usage_and_errors(tmp_path):
+    """The C++ headless gltf_viewer (host/gltf_viewer.cpp) mirrors the reference CLI `-f <file>` (args.rs:4-10)."""
+    import subprocess
+    assert VIEWER.exists(), "run __graft_entry__.build() (host/Makefile links the viewer once the CUDA core is built)"
+    r = subprocess.run([str(VIEWER)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: gltf_viewer -f <file>" in r.stderr
+    r = subprocess.run([str(VIEWER), "-f", str(tmp_path / "missing.gltf")], capture_output=True, text=True)
+    assert r.returncode == 1 and "load_file" in r.stderr               # import errors are reported, not swallowed
+
+
+@pytest.mark.gpu
+def test_cpp_gltf_viewer_matches_python_viewer(tmp_path):
+    """Same file, same options: the compiled host (2 frames in flight, C ABI only) and the ctypes host give the same PNG."""
+    import subprocess
+    from PIL import Image
+    from rustracer_b200 import gltf_viewer
+    f = write_gltf(tmp_path)
+    common = ["-f", str(f), "--width", "96", "--height", "64", "--spp", "12", "--samples-per-frame", "3", "--bounces", "4", "--camera", "0", "0", "14"]
+    r = subprocess.run([str(VIEWER), *common, "-o", str(tmp_path / "cpp.png")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "12 spp in 4 frames" in r.stdout
+    gltf_viewer.main([*common, "-o", str(tmp_path / "py.png")])
+    a, b = np.asarray(Image.open(tmp_path / "cpp.png")), np.asarray(Image.open(tmp_path / "py.png"))
+    assert a.shape == (64, 96, 3) and (a == b).all() and a.std() > 0
