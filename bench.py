@@ -403,14 +403,16 @@ def run_ours(args):
     value = rays_all / (ms_max * 1e-3) / 1e6
 
     # ---- end-to-end through the C ABI with host buffers: UBO from host each frame, RGBA8 image read back each frame ----
-    # The host keeps NF frames in flight like the reference's draw loop: submit frame s (UBO by value + the frame's
-    # image copy to pinned host memory queued behind it), then wait on the fence of frame s-NF+1 (app/src/lib.rs:400-401).
+    # Like the reference's draw loop (app/src/lib.rs:400-401) the host submits frame s (UBO by value + the frame's image
+    # copy to pinned host memory queued behind it) and waits on the fence of an earlier frame before it reuses that
+    # frame's host buffer; with 2*NF host buffers the device never runs out of submitted frames.
     ctx.set_frames_in_flight(NF)
-    pinned = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True) for _ in range(NF)]
+    HB = 2 * NF     # host staging buffers: the host runs up to HB frames ahead, the device keeps NF in flight
+    pinned = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True) for _ in range(HB)]
     out_np = [p.numpy() for p in pinned]
     ctx.resize(WIDTH, HEIGHT)
     for s in range(0, Wm):
-        pre_step(s); ctx.render(scene, ubos[s], stream=stream); ctx.frame_wait(ctx.readback_async(out_np[s % NF]))
+        pre_step(s); ctx.render(scene, ubos[s], stream=stream); ctx.frame_wait(ctx.readback_async(out_np[s % HB]))
     ctx.synchronize()
     barrier()
     t0 = time.perf_counter()
@@ -418,13 +420,13 @@ def run_ours(args):
     e2.record()
     tickets = []
     for s in range(Wm, Wm + K):
+        if len(tickets) >= HB:
+            ctx.frame_wait(tickets[-HB])                   # the image of frame s-HB is in host memory; its buffer is reused now
         pre_step(s)                                        # config 4: 256 mat4 (16 KB) host -> device per step
         ctx.render(scene, ubos[s], stream=stream)
-        tickets.append(ctx.readback_async(out_np[s % NF]))  # device -> pinned host, 4 B/pixel, behind the frame
-        if len(tickets) >= NF:
-            ctx.frame_wait(tickets[-NF])                   # the slot (and its host buffer) is reused by the next frame
-    for t in tickets[-NF:]:
-        ctx.frame_wait(t)
+        tickets.append(ctx.readback_async(out_np[s % HB]))  # device -> pinned host, 4 B/pixel, behind the frame
+    for t in tickets[-HB:]:
+        ctx.frame_wait(t)                                  # every step's result has reached the host inside the timed region
     ctx.join(stream)
     e3.record(); torch.cuda.synchronize()
     e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)

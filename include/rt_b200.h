@@ -268,7 +268,8 @@ int rt_join(rt_context* ctx, void* stream);
    recorded in the same command buffer as the frame): queues the RGBA8 image's device->host copy behind that
    frame on its slot and returns the frame's ticket.  out_rgba8 should be pinned and must stay untouched until
    rt_frame_wait(ticket) returned (the in-flight fence wait, app/src/lib.rs:401); frames in flight need
-   distinct host buffers. */
+   distinct host buffers.  The host may run further ahead than the number of slots (slot reuse is ordered on the
+   device): keep one host buffer per frame between a submission and its rt_frame_wait. */
 int rt_readback_async(rt_context* ctx, uint8_t* out_rgba8, uint64_t* ticket);
 int rt_frame_wait(rt_context* ctx, uint64_t ticket);
 

@@ -62,6 +62,7 @@ using namespace rtcore;
 
 #define RT_MAX_FRAMES_IN_FLIGHT 4
 #define RT_MAX_SCENE_VERSIONS 4
+#define RT_TICKET_RING 12
 
 // One frame in flight: everything a frame writes except the shared accumulation image.  Mirrors the reference's
 // InFlightFrames (app/src/lib.rs:34,329,400-401: IN_FLIGHT_FRAMES = 2, one fence per frame) and its per-swapchain-image
@@ -93,6 +94,9 @@ struct rt_context {
     uint32_t n_slots = 1, cur = 0;       // cur: slot of the most recently submitted frame
     uint64_t frame_seq = 0;              // frames submitted so far (ticket of the next frame)
     rt_event ev_submit, ev_acc, ev_consumer; bool acc_pending = false, consumer_pending = false;
+    // fences of the last RT_TICKET_RING submissions (ticket % ring).  The ring length is a multiple of every slot count, so
+    // the frame that re-records an entry runs on the same slot stream as the one it replaces: waiting on it is conservative.
+    rt_event ticket_done[RT_TICKET_RING];
     bool timers = false;
     std::vector<void*> ipc_opened;
 };
@@ -663,6 +667,7 @@ int RT_API(rt_context_create)(int device, uint32_t width, uint32_t height, rt_co
     c->timers = true;
 #endif
     c->ev_submit.create(); c->ev_acc.create(); c->ev_consumer.create();
+    for (auto& e : c->ticket_done) e.create();
     if (alloc_frame(c, width, height)) { RT_API(rt_context_destroy)(c); return fail(std::string("rt_context_create: allocation failed: ") + rt_platform_error()); }
     *out = c;
     return 0;
@@ -680,6 +685,7 @@ void RT_API(rt_context_destroy)(rt_context* c) {
         rt_stream_destroy(f.stream);
     }
     c->ev_submit.destroy(); c->ev_acc.destroy(); c->ev_consumer.destroy();
+    for (auto& e : c->ticket_done) e.destroy();
 #ifndef RT_EMU
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1027,6 +1033,7 @@ int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_re
     else e = count ? render_frame<false, true>(c, f, s, P, tp, flags, st) : render_frame<false, false>(c, f, s, P, tp, flags, st);
     if (c->timers) f->ev_end.record(st);
     f->done.record(st); f->pending = true;
+    c->ticket_done[c->frame_seq % RT_TICKET_RING].record(st);
     f->scene = s; f->scene_version = s->cur_ver;
     c->cur = k; ++c->frame_seq;
 #ifndef RT_EMU
@@ -1093,6 +1100,7 @@ int RT_API(rt_readback_async)(rt_context* c, uint8_t* out, uint64_t* ticket) {
     rt_stream_t st = c->n_slots > 1 ? f->stream : (c->last_stream ? c->last_stream : c->stream);
     RT_CHECK(rt_d2h(out, f->fb.out, (size_t)c->width * c->height * 4, st), "rt_readback_async");
     f->done.record(st); f->pending = true;
+    c->ticket_done[(c->frame_seq - 1) % RT_TICKET_RING].record(st);
     if (ticket) *ticket = c->frame_seq - 1;
     return 0;
 }
@@ -1100,8 +1108,8 @@ int RT_API(rt_readback_async)(rt_context* c, uint8_t* out, uint64_t* ticket) {
 int RT_API(rt_frame_wait)(rt_context* c, uint64_t ticket) {
     if (!c) return fail("rt_frame_wait: null context");
     if (ticket >= c->frame_seq) return fail("rt_frame_wait: ticket of a frame that was never submitted");
-    FrameSlot* f = &c->slot[ticket % c->n_slots];
-    if (f->pending && f->done.sync()) return fail(std::string("rt_frame_wait: ") + rt_platform_error());
+    // older than the ring: its entry now belongs to a later frame of the same slot, which completes after it
+    if (c->ticket_done[ticket % RT_TICKET_RING].sync()) return fail(std::string("rt_frame_wait: ") + rt_platform_error());
     return 0;
 }
 
