@@ -314,6 +314,84 @@ def case_skinned_in_flight(api, n_tris=20000, joints=64, size=48, frames=7):
         sc.set_versions(5)
 
 
+def textured_scene(seed=17):
+    """Nine spheres / quads whose materials walk through every texture slot of MaterialRaw (Material.glsl:51-73):
+    base colour (sRGB), normal map + tangents, metallic-roughness, emissive, transmission, KHR_materials_specular
+    factors + textures, the specular-glossiness workflow with both of its textures, vertex colours, the second UV set,
+    nearest / linear filtering and clamp / mirror / repeat wrapping."""
+    rng = np.random.default_rng(seed)
+    b = scenes.SceneBuilder()
+
+    def noise(n, srgb, lo=0, hi=256):
+        return b.add_image(rng.integers(lo, hi, (n, n, 4), dtype=np.uint8), srgb=srgb)
+
+    def normal_map(n):
+        xy = rng.uniform(-0.5, 0.5, (n, n, 2)); z = np.sqrt(1 - (xy ** 2).sum(-1))
+        v = np.concatenate([xy, z[..., None], np.ones((n, n, 1))], -1)
+        return b.add_image(np.round((v * 0.5 + 0.5) * 255).astype(np.uint8), srgb=False)
+
+    TI = F.rt_texture_info
+    base = b.add_texture(noise(16, True), mag=1, wrap_s=2, wrap_t=2)
+    base_near = b.add_texture(noise(8, True), mag=0, wrap_s=0, wrap_t=1)
+    nrm = b.add_texture(normal_map(16), mag=1, wrap_s=1, wrap_t=2)
+    mr = b.add_texture(noise(16, False), mag=1, wrap_s=2, wrap_t=0)
+    emis = b.add_texture(noise(8, True, 0, 40), mag=1, wrap_s=2, wrap_t=2)
+    trans = b.add_texture(noise(8, False), mag=0, wrap_s=2, wrap_t=2)
+    spec = b.add_texture(noise(8, False), mag=1, wrap_s=2, wrap_t=2)
+    spec_col = b.add_texture(noise(8, True), mag=1, wrap_s=1, wrap_t=1)
+    sg_diff = b.add_texture(noise(16, True), mag=1, wrap_s=2, wrap_t=2)
+    sg_spec = b.add_texture(noise(16, True), mag=1, wrap_s=0, wrap_t=0)
+    mats = []
+    m = scenes.material((0.9, 0.8, 0.7, 1), metallic=0.1, roughness=0.6, base_color_texture=base); mats.append(m)
+    m = scenes.material((1, 1, 1, 1), metallic=0.0, roughness=0.8, base_color_texture=base_near); m.base_color_texture = TI(base_near, 1); mats.append(m)   # uv set 1
+    m = scenes.material((0.8, 0.8, 0.8, 1), metallic=0.0, roughness=0.5); m.normal_texture = TI(nrm, 0); mats.append(m)
+    m = scenes.material((0.9, 0.6, 0.3, 1), metallic=1.0, roughness=1.0); m.metallic_roughness_texture = TI(mr, 0); mats.append(m)
+    m = scenes.material((0.5, 0.5, 0.5, 1), metallic=0.0, roughness=0.9, emissive=(1.0, 0.8, 0.6)); m.emissive_texture = TI(emis, 0); mats.append(m)
+    m = scenes.material((0.9, 0.95, 1.0, 1), metallic=0.0, roughness=0.1, ior=1.45, transmission=0.9, volume=((0.8, 0.9, 0.7), 1.5)); m.transmission_texture = TI(trans, 0); mats.append(m)
+    m = scenes.material((0.6, 0.2, 0.2, 1), metallic=0.0, roughness=0.4); m.specular_exist, m.specular_factor = 1, 0.7
+    m.specular_color_factor[:] = (0.9, 0.7, 0.5, 1); m.specular_texture, m.specular_color_texture = TI(spec, 0), TI(spec_col, 0); mats.append(m)
+    m = scenes.material((1, 1, 1, 1), metallic=0.3, roughness=0.3); m.workflow = 1
+    m.sg_diffuse_factor[:] = (0.8, 0.7, 0.6, 1); m.sg_specular_glossiness_factor[:] = (0.6, 0.5, 0.4, 0.7)
+    m.sg_diffuse_texture, m.sg_specular_glossiness_texture = TI(sg_diff, 0), TI(sg_spec, 0); mats.append(m)
+    m = scenes.material((1, 1, 1, 1), metallic=0.0, roughness=1.0, unlit=True, base_color_texture=base); mats.append(m)
+    ids = [b.add_material(m) for m in mats]
+    for k, mid in enumerate(ids):
+        pos, nrmv, uv, idx = scenes.uv_sphere(0.8, 10, 14)
+        col = np.ones((len(pos), 4), np.float32); col[:, :3] = rng.uniform(0.6, 1.0, (len(pos), 3))
+        g = b.add_geometry(pos, nrmv, uv * 3.0 - 0.7, idx, mid, color=col)           # uvs outside [0,1]: the wrap modes matter
+        v = b.verts[g]
+        t = np.cross(np.array([0, 1.0, 0]), nrmv); t /= np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-6)
+        v["tangent"][:, :3] = t; v["tangent"][:, 3] = np.where(rng.random(len(pos)) < 0.5, -1.0, 1.0)
+        v["uv1"] = uv[:, ::-1] * 2.0
+        b.add_instance(g, scenes.trs(((k % 3 - 1) * 2.0, (k // 3 - 1) * 2.0, 0.0)))
+    wall = b.add_material(scenes.material((0.8, 0.8, 0.8, 1), metallic=0.0, roughness=1.0))
+    gw = b.add_geometry(*scenes.box_mesh((4.0, 4.0, 0.1)), wall); b.add_instance(gw, scenes.trs((0, 0, -1.5)))
+    lamp = b.add_material(scenes.material((1, 1, 1, 1), metallic=0.0, emissive=(4, 4, 4)))
+    gl = b.add_geometry(*scenes.box_mesh((1.5, 0.05, 1.5)), lamp); b.add_instance(gl, scenes.trs((0, 3.9, 2.0)))
+    b.dlights, b.plights = bright_lights()          # NEE + shadow rays through the textured BSDFs
+    return b.build()
+
+
+def case_textured_materials(api, size=96, frames=3, n_rays=20000):
+    d = textured_scene()
+    o = orc.OracleScene(d)
+    # closest hits bit-exact, then the rendered image and the texture-dependent debug channels
+    ctx, sc = make(api, d, 32, 32)
+    rays, _ = util.random_rays(n_rays, seed=23)
+    assert util.hits_equal(sc.trace_closest(rays, 1), o.trace_closest(rays, 1)).all()
+    del ctx, sc
+    o2 = o
+    ctx, sc, st = render_compare(api, d, o2, size, size, dict(number_of_samples=4, number_of_bounces=5), frames, cam_pos=(0, 0, 14.0))
+    for mapping in (6, 7, 9, 10, 11):          # albedo, normal, metallic, roughness, transmission style channels (RayTracing.rchit:258-286)
+        ctx.resize(size, size)
+        cam = host.Camera(size, size).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=1, mapping=mapping, antialiasing=0)
+        d1, d2 = host.FrameDriver(cam, gui, d.fully_opaque), host.FrameDriver(cam, gui, d.fully_opaque)
+        ctx.render(sc, d1.next_ubo()); _, out, _ = o2.render(d2.next_ubo(), size, size, None)
+        _, out_g = ctx.readback()
+        diff = np.abs(out_g.astype(int) - out.astype(int))
+        assert (diff > 1).mean() < 0.002, (mapping, diff.max(), (diff > 1).mean())    # texture-filtered channels: 1 LSB (silhouette pixels aside)
+
+
 def case_frame_options(api, cornell_desc, cornell_oracle, size=48):
     """UBO variants of RayTracing.rgen / Tonemapping.glsl / rchit debug path: thin lens (LCG stream), orthographic
     camera, every tone-map mode, DISTANCE and HEAT mappings, debug == 1, no anti-aliasing, spp > 1, bounce limits."""

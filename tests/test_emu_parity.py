@@ -55,3 +55,7 @@ def test_emu_frame_options(cornell_desc, cornell_oracle):
 
 def test_emu_skinned_in_flight_bookkeeping():
     pc.case_skinned_in_flight(emu_api(), n_tris=1500, joints=16, size=20, frames=4)
+
+
+def test_emu_textured_materials():
+    pc.case_textured_materials(emu_api(), size=40, frames=2, n_rays=4000)

@@ -152,6 +152,11 @@ def test_skinned_animation_with_frames_in_flight(api):
     pc.case_skinned_in_flight(api, n_tris=200000, joints=256, size=160, frames=9)
 
 
+def test_textured_materials(api):
+    """Every texture slot of MaterialRaw, the specular extension, the specular-glossiness workflow, sampler variants."""
+    pc.case_textured_materials(api, size=160, frames=4, n_rays=200000)
+
+
 def test_frame_options(api, cornell_desc, cornell_oracle):
     """Lens, orthographic camera, all tone-map modes, DISTANCE / HEAT / debug mappings, debug == 1, spp > 1."""
     pc.case_frame_options(api, cornell_desc, cornell_oracle, size=96)
