@@ -25,6 +25,6 @@ for depth in [int(x) for x in os.environ.get("DEPTHS", "1,2,3").split(",")]:
     print(f"  warp finish percentiles [10,50,90,99,100] = {np.percentile(fin, [10, 50, 90, 99, 100]).round(1)} us")
     print(f"  rays/warp [min,med,max] = {rays.min():.0f} {np.median(rays):.0f} {rays.max():.0f}; iterations/warp [med,90,max] = {np.median(iters):.0f} {np.percentile(iters, 90):.0f} {iters.max():.0f}")
     late = np.argsort(fin)[-8:]
-    print("  latest warps: " + ", ".join(f"w{w} sm{int(sm[w])} fin {fin[w]:.0f}us rays {int(rays[w])} it {int(iters[w])}" for w in late))
+    print("  latest warps: " + ", ".join(f"w{w} sm{int(sm[w])} fin {fin[w]:.0f}us exh@{(tx[w] - start) / 1e3 if tx[w] > 0 else -1:.0f}us rays {int(rays[w])} it {int(iters[w])}" for w in late))
     per_sm = np.array([fin[sm == k].max() for k in np.unique(sm)])
     print(f"  per-SM last finish [min,med,max] = {per_sm.min():.1f} {np.median(per_sm):.1f} {per_sm.max():.1f} us; mean of warp finish {fin.mean():.1f} us")
