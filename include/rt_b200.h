@@ -262,7 +262,8 @@ int rt_frame_resize(rt_context* ctx, uint32_t width, uint32_t height);
    rt_scene_update_* calls, rt_frame_resize) wait for the frames in flight; work of your own on another
    stream must call rt_join first.  Keeps the accumulation image; synchronises. */
 int rt_context_set_frames_in_flight(rt_context* ctx, uint32_t n);
-/* makes `stream` (NULL = the context's) wait, on the device, for every frame submitted so far */
+/* makes `stream` (NULL = the context's) wait, on the device, for every frame submitted so far: after it, the images
+   of rt_device_ptrs may be consumed on that stream (tests/test_gpu_parity.py::test_join_orders_foreign_stream...) */
 int rt_join(rt_context* ctx, void* stream);
 /* presentation of the frame submitted last (the storage image -> swapchain copy of app/src/lib.rs:563-611
    recorded in the same command buffer as the frame): queues the RGBA8 image's device->host copy behind that
@@ -290,6 +291,8 @@ int rt_scene_update_skins(rt_scene* scene, const float* skin_mats, uint32_t n_sk
    device, for the frames that still read it, so the update of frame f+1 overlaps the frames in flight; the host
    never blocks (rebuild != 0 and rt_scene_update_instances stay synchronous).  Synchronises. */
 int rt_scene_set_versions(rt_scene* scene, uint32_t n);
+/* A scene belongs to the context it was created on: updates wait for THAT context's frames.  Other contexts of the
+   same device may render it (read-only) only while no rt_scene_update_* call is in progress. */
 /* replaces dlights_buffer / plights_buffer.copy_data_to_buffer (main.rs:353-374) */
 int rt_scene_update_lights(rt_scene* scene, const rt_light* dlights, uint32_t n_dlights,
                            const rt_light* plights, uint32_t n_plights);

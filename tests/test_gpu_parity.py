@@ -121,6 +121,32 @@ def test_full_size_frames_in_flight(api):
     assert (acc4 == acc1).all() and (out4 == outs[-1]).all()
 
 
+def test_join_orders_foreign_stream_after_frames_in_flight(api, cornell_desc):
+    """Zero-copy interop: rt_join makes a caller's stream wait (on the device) for the frames in flight, after which
+    rt_device_ptrs' images can be consumed on that stream without a host synchronisation."""
+    import ctypes as C
+    import torch
+    W = H = 256
+    ctx = core.Context(W, H, api=api); sc = core.Scene(ctx, cornell_desc)
+    cam = host.Camera(W, H).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=8)
+    drv = host.FrameDriver(cam, gui, cornell_desc.fully_opaque)
+    ctx.set_frames_in_flight(3)
+    cudart = C.CDLL("libcudart.so.12")
+    cudart.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    side = torch.cuda.Stream()
+    acc_host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+    out_host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    for _ in range(7):
+        ctx.render(sc, drv.next_ubo())
+    acc_ptr, out_ptr = ctx.device_ptrs()               # out: the image of the frame submitted last
+    ctx.join(side.cuda_stream)
+    assert cudart.cudaMemcpyAsync(acc_host.data_ptr(), acc_ptr, acc_host.numel() * 4, 2, side.cuda_stream) == 0
+    assert cudart.cudaMemcpyAsync(out_host.data_ptr(), out_ptr, out_host.numel(), 2, side.cuda_stream) == 0
+    side.synchronize()
+    acc, out = ctx.readback()
+    assert (acc_host.numpy() == acc).all() and (out_host.numpy() == out).all() and acc[..., :3].max() > 0
+
+
 def test_errors_are_reported_not_swallowed(api, cornell_desc):
     ctx = core.Context(32, 32, api=api); sc = core.Scene(ctx, cornell_desc)
     u = F.rt_ubo()   # total_number_of_samples == 0
