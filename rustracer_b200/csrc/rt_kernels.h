@@ -211,13 +211,15 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 #define RT_REFILL_BELOW 22     // refill when fewer than this many lanes still hold a ray
 #endif
 #define RT_WARPS_PER_BLOCK (RT_EXTEND_THREADS / 32)
-#ifndef RT_TQ_ATOMIC_TAIL
-#define RT_TQ_ATOMIC_TAIL 1
+#ifndef RT_NODE_STEPS
+#define RT_NODE_STEPS 2         // node visits per lane between two triangle rounds: fuller rounds (+1.5 % on config 2)
 #endif
 #ifndef RT_TQ_PUSH_MAX
 #define RT_TQ_PUSH_MAX 7        // triangles a lane may queue per iteration (the rest stay parked in its tgroup)
 #endif
-#define RT_TQ_CAP 256u         // per-warp triangle queue capacity (power of two, >= 31 + 32 * RT_TQ_PUSH_MAX)
+#ifndef RT_TQ_CAP
+#define RT_TQ_CAP 512u         // per-warp triangle queue capacity (power of two, >= 31 + 32 * RT_TQ_PUSH_MAX * RT_NODE_STEPS)
+#endif
 #define RT_TQ_TRI_BITS 27      // item = owner lane << 27 | absolute triangle index
 
 #ifdef RT_PROBE
@@ -234,7 +236,7 @@ struct CoopShared {            // one per warp; SoA over the 32 owner lanes
     uint32_t inst[32];                       // 0xFFFFFFFF = merged BLAS (instance id in the triangle record)
     uint32_t geo[ALPHA ? 32 : 1], alpha[ALPHA ? 32 : 1], rng[4][ALPHA ? 32 : 1];   // any-hit context, only kept when alpha tests can run
     uint32_t items[RT_TQ_CAP];
-    uint32_t tail;                           // total items ever appended (RT_TQ_ATOMIC_TAIL)
+    uint32_t tail;                           // total items ever appended
 };
 
 template <bool ALPHA, bool SINGLE>
@@ -348,8 +350,11 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
         if (!__ballot_sync(0xFFFFFFFFu, active || outstanding != 0u)) break;
         uint32_t holding;
         do {
-            bool want_flush = false; uint32_t leaf_mask = 0u, leaf_base = 0u;
-            if (active) {
+            bool want_flush = false;
+#pragma unroll 1
+            for (int rep = 0; rep < RT_NODE_STEPS; ++rep) {
+            uint32_t leaf_mask = 0u, leaf_base = 0u;
+            if (active && !want_flush) {
                 // acquire the next node group: leave the BLAS / pop until ngroup holds an inner child or instances are parked
                 while (tv.ngroup.y <= 0x00FFFFFFu && tv.tgroup.y == 0u) {
                     if (!SINGLE && tv.blas_sp >= 0 && tv.sp == tv.blas_sp) {
@@ -387,7 +392,6 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             }
             // append this iteration's leaf triangles to the warp queue
             const uint32_t k = (uint32_t)__popc(leaf_mask);
-#if RT_TQ_ATOMIC_TAIL
             // queue positions from one shared-memory atomic per pushing lane (item order inside the queue is irrelevant:
             // hit resolution is order-independent) instead of a 5-step shuffle scan
             if (k) {
@@ -402,23 +406,8 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             }
             __syncwarp();
             q_count = sh.tail - q_head;
-#else
-            uint32_t incl = k;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if ((int)lane >= dd) incl += nn; }
-            const uint32_t pushed = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (k) {
-                uint32_t pos = q_head + q_count + (incl - k);
-                outstanding += k;
-                while (leaf_mask) {
-                    const int bit = 31 - __clz((int)leaf_mask);
-                    leaf_mask &= ~(1u << bit);
-                    sh.items[pos & (RT_TQ_CAP - 1u)] = (lane << RT_TQ_TRI_BITS) | (leaf_base + (uint32_t)bit);
-                    ++pos;
-                }
-            }
-            q_count += pushed;
-#endif
+            if (q_count + 32u * RT_TQ_PUSH_MAX + 32u > RT_TQ_CAP) break;     // (warp-uniform) no room for another round of pushes
+            }   // rep
             const bool flush = __any_sync(0xFFFFFFFFu, want_flush);
             __syncwarp();
             while (q_count >= 32u || (flush && q_count)) {
