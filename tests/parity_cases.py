@@ -100,6 +100,39 @@ def case_frames_in_flight(api, cornell_desc, golden, size=64, frames=7):
         ctx.frame_wait(10 ** 9)
 
 
+def case_lifecycle_in_flight(api, cornell_desc, size=48):
+    """Resize / destroy / scene updates while frames are in flight must synchronise internally: no stale frame may land
+    in a re-allocated image, nothing may crash, and the images equal those of a fresh, strictly ordered context."""
+    cam = host.Camera(size, size).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=5)
+    ubos = [host.FrameDriver(cam, gui, cornell_desc.fully_opaque).next_ubo() for _ in range(1)]
+    drv = host.FrameDriver(cam, gui, cornell_desc.fully_opaque)
+    ubos = [drv.next_ubo() for _ in range(6)]
+    ref_ctx, ref_sc = make(api, cornell_desc, size, size)
+    for u in ubos[:3]:
+        ref_ctx.render(ref_sc, u)
+    ref_acc, ref_out = ref_ctx.readback()
+    ctx, sc = make(api, cornell_desc, size * 2, size)
+    ctx.set_frames_in_flight(4)
+    big = host.FrameDriver(host.Camera(size * 2, size).set(position=(0, 0, 14.0)), gui, cornell_desc.fully_opaque)
+    for _ in range(5):
+        ctx.render(sc, big.next_ubo())
+    ctx.resize(size, size)                        # frames of the old size are still in flight here
+    for u in ubos[:3]:
+        ctx.render(sc, u)
+    acc, out = ctx.readback()
+    assert (acc == ref_acc).all() and (out == ref_out).all()
+    dl, pl = bright_lights()
+    for u in ubos[3:]:
+        ctx.render(sc, u)
+    sc.update_lights(dl, pl)                      # waits for the frames that still read the old light arrays
+    ctx.render(sc, ubos[0])
+    assert np.isfinite(ctx.readback()[0]).all()
+    for u in ubos:
+        ctx.render(sc, u)
+    sc.close(); ctx.close()                       # destroy with frames in flight
+    ref_sc.close(); ref_ctx.close()
+
+
 def case_instancing(api):
     b = scenes.SceneBuilder()
     m = b.add_material(scenes.material((0.8, 0.3, 0.2, 1), metallic=0.0))

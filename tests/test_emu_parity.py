@@ -59,3 +59,7 @@ def test_emu_skinned_in_flight_bookkeeping():
 
 def test_emu_textured_materials():
     pc.case_textured_materials(emu_api(), size=40, frames=2, n_rays=4000)
+
+
+def test_emu_lifecycle_in_flight(cornell_desc):
+    pc.case_lifecycle_in_flight(emu_api(), cornell_desc, size=16)

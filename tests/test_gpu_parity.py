@@ -35,6 +35,10 @@ def test_frames_in_flight_bit_identical(api, cornell_desc, golden):
     pc.case_frames_in_flight(api, cornell_desc, golden)
 
 
+def test_lifecycle_with_frames_in_flight(api, cornell_desc):
+    pc.case_lifecycle_in_flight(api, cornell_desc, size=96)
+
+
 def test_instancing_and_tlas_update(api):
     pc.case_instancing(api)
 
