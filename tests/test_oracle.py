@@ -148,3 +148,38 @@ def test_empty_and_degenerate_inputs():
     assert s.trace_closest(rays[:1], 1)["t"][0] == -1.0
     rays["tmax"][0] = 100; rays["tmin"][0] = 1.0
     assert s.trace_closest(rays[:1], 1)["t"][0] == -1.0
+
+
+def test_tonemap_operators_match_published_curves():
+    """lib/Tonemapping.glsl:9-53 against independent float64 restatements of the published operators (Hable's
+    Uncharted 2 filmic curve, Hejl / Burgess-Dawson, Narkowicz' ACES fit, Reinhard) plus known answers: each curve's
+    value at the white point / at zero."""
+    l = orc.lib()
+    rng = np.random.default_rng(9)
+    x = np.concatenate([rng.uniform(0, 4, (200, 3)), rng.uniform(0, 0.05, (50, 3)), [[0, 0, 0], [11.2 / 2] * 3, [1, 1, 1]]]).astype(np.float32)
+
+    def run(mode):
+        out = np.zeros_like(x)
+        for i in range(len(x)):
+            a = np.ascontiguousarray(x[i]); b = np.zeros(3, np.float32)
+            l.orc_tonemap(mode, F.as_ptr(a, F.c_f), F.as_ptr(b, F.c_f)); out[i] = b
+        return out.astype(np.float64)
+
+    X = x.astype(np.float64)
+    g = lambda c: np.power(c, 1 / 2.2)
+
+    def hable(c):
+        A, B, Cc, D, E, Fv = 0.15, 0.50, 0.10, 0.20, 0.02, 0.30
+        return (c * (A * c + Cc * B) + D * E) / (c * (A * c + B) + D * Fv) - E / Fv
+
+    np.testing.assert_allclose(run(0), g(X / (X + 1)), rtol=2e-5, atol=2e-6)                               # Reinhard + gamma
+    nz = X.min(1) > 0            # at exactly 0 the curve is a float32 rounding residue (~1e-9) that the 1/2.2 power lifts to ~2e-4
+    np.testing.assert_allclose(run(1)[nz], g(hable(2 * X[nz]) / hable(11.2)), rtol=5e-5, atol=5e-6)       # Uncharted 2, exposure bias 2, W = 11.2
+    h = np.maximum(0, X - 0.004)
+    np.testing.assert_allclose(run(2), (h * (6.2 * h + 0.5)) / (h * (6.2 * h + 1.7) + 0.06), rtol=2e-5, atol=2e-6)   # Hejl-Richard (gamma baked in)
+    np.testing.assert_allclose(run(3), g(np.clip((X * (2.51 * X + 0.03)) / (X * (2.43 * X + 0.59) + 0.14), 0, 1)), rtol=2e-5, atol=2e-6)   # ACES (Narkowicz)
+    np.testing.assert_allclose(run(7), g(X), rtol=2e-5, atol=2e-6)                                          # any other mode: gamma only
+    # known answers: the Uncharted curve maps its white point (input W/2 after the x2 exposure bias) to exactly 1, zero to zero
+    np.testing.assert_allclose(run(1)[-2], [1, 1, 1], atol=2e-6)
+    assert np.abs(run(1)[-3]).max() < 1e-3
+    np.testing.assert_allclose(run(0)[-1], [0.5 ** (1 / 2.2)] * 3, rtol=1e-6)
