@@ -228,7 +228,16 @@ static int alloc_versions(rt_scene* s, uint32_t n) {
 static int run_skinning(rt_scene* s) {
     rt_stream_t st = s->ctx->stream;
     const rt_vertex* vin = s->d_vin; rt_vertex* vout = s->d_vout; const float* skins = s->d_skins; const uint32_t ns = s->n_skins;
+#ifndef RT_EMU
+    if (s->n_vertices) {
+        size_t blocks = ((size_t)s->n_vertices + RT_SKIN_TILE - 1) / RT_SKIN_TILE; const size_t cap = (size_t)g_rt_sm_count * 12;
+        if (blocks > cap) blocks = cap;
+        skin_kernel<<<(unsigned)blocks, RT_SKIN_TILE, 0, st>>>(vin, vout, skins, ns, s->n_vertices);
+        ++g_rt_launch_count;
+    }
+#else
     rt_launch(s->n_vertices, st, RT_LAMBDA(size_t i) { skin_item(vin, vout, skins, ns, (uint32_t)i); });
+#endif
     return 0;
 }
 

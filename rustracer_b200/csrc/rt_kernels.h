@@ -136,12 +136,8 @@ RT_D void accumulate_item(const FrameParams& P, const TilePart& tp, const FrameB
     accumulate_pixel(P.ubo, fb.acc, fb.out, pixel, mk3(r.x, r.y, r.z), a.x, (uint32_t)a.y);
 }
 
-// AnimationCompute.comp:14-39
-RT_D void skin_item(const rt_vertex* vin, rt_vertex* vout, const float* skins, uint32_t n_skins, uint32_t i) {
-    const float4* src = reinterpret_cast<const float4*>(vin + i);
-    float4 r[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = src[k];
+// AnimationCompute.comp:14-39 on one vertex held as its 8 float4 (position, normal, tangent, color, weights, joints, uv0|uv1, skin_index|pad)
+RT_D void skin_transform(float4 (&r)[8], const float* skins, uint32_t n_skins) {
     const int skin_index = (int)rt_float_as_uint(r[7].x);
     if (skin_index >= 0 && (uint32_t)skin_index < n_skins) {
         const float* bones = skins + (size_t)skin_index * (RT_MAX_JOINTS * 16);
@@ -167,6 +163,13 @@ RT_D void skin_item(const rt_vertex* vin, rt_vertex* vout, const float* skins, u
         r[1].x = nn.x; r[1].y = nn.y; r[1].z = nn.z;
         r[2].x = tt.x; r[2].y = tt.y; r[2].z = tt.z;   // w (handedness) kept
     }
+}
+RT_D void skin_item(const rt_vertex* vin, rt_vertex* vout, const float* skins, uint32_t n_skins, uint32_t i) {
+    const float4* src = reinterpret_cast<const float4*>(vin + i);
+    float4 r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = src[k];
+    skin_transform(r, skins, n_skins);
     float4* dst = reinterpret_cast<float4*>(vout + i);
 #pragma unroll
     for (int k = 0; k < 8; ++k) dst[k] = r[k];
@@ -186,6 +189,31 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 
 #ifndef RT_EMU
 // ---- CUDA kernels -------------------------------------------------------------------------------------
+// Skinning as a streaming kernel: a CTA stages 128 vertices (16 KB) through shared memory so that every global access is
+// a fully coalesced 16-byte-per-lane stream (one thread per vertex reading its own 128-byte record touches 32 cache
+// lines per load instruction); each thread then transforms its vertex out of shared memory.  Rows are padded to 9
+// float4 so the per-vertex accesses of a quarter warp fall into distinct banks.
+#define RT_SKIN_TILE 128
+__global__ void __launch_bounds__(RT_SKIN_TILE) skin_kernel(const rt_vertex* vin, rt_vertex* vout, const float* skins, uint32_t n_skins, uint32_t n) {
+    __shared__ float4 tile[RT_SKIN_TILE * 9];
+    const float4* src = reinterpret_cast<const float4*>(vin); float4* dst = reinterpret_cast<float4*>(vout);
+    for (uint32_t base = blockIdx.x * RT_SKIN_TILE; base < n; base += gridDim.x * RT_SKIN_TILE) {
+        const uint32_t cnt = n - base < RT_SKIN_TILE ? n - base : RT_SKIN_TILE;
+        for (uint32_t f = threadIdx.x; f < cnt * 8u; f += RT_SKIN_TILE) tile[(f >> 3) * 9u + (f & 7u)] = __ldcs(src + (size_t)base * 8u + f);
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            float4 r[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = tile[threadIdx.x * 9u + k];
+            skin_transform(r, skins, n_skins);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tile[threadIdx.x * 9u + k] = r[k];      // only position / normal / tangent change
+        }
+        __syncthreads();
+        for (uint32_t f = threadIdx.x; f < cnt * 8u; f += RT_SKIN_TILE) dst[(size_t)base * 8u + f] = tile[(f >> 3) * 9u + (f & 7u)];
+        __syncthreads();
+    }
+}
 #define RT_EXTEND_THREADS 128
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 6   // <= 85 registers: 24 warps per SM
