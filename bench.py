@@ -476,7 +476,8 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(desc) | {"parallelism": f"sample-pass sharding x{world} (frames g = step*{world}+rank), fused peer-memory reduce+tonemap at the end",
                                                    "frames_in_flight": NF,
-                                                   "bvh": {"nodes": int(info.blas_nodes), "depth": int(info.max_depth_blas), "bytes": int(info.bytes), "build_s": build_s}},
+                                                   "bvh": {"nodes": int(info.blas_nodes), "depth": int(info.max_depth_blas), "bytes": int(info.bytes), "build_s": build_s,
+                                                           "build_ms_device": float(info.build_ms), "tlas_ms_device": float(info.tlas_ms)}},
                 "samples_per_s": samples_all / (ms_max * 1e-3),
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 324 + (16384 if POSE is not None else 0), "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
                 "refit": ((upd | {"skinning_gbs": 256.0 * desc.n_vertices / (upd["skin_ms"] * 1e-3) / 1e9 if upd["skin_ms"] > 0 else None,
