@@ -151,6 +151,47 @@ def test_join_orders_foreign_stream_after_frames_in_flight(api, cornell_desc):
     assert (acc_host.numpy() == acc).all() and (out_host.numpy() == out).all() and acc[..., :3].max() > 0
 
 
+def test_baseline_sized_configs_properties(api):
+    """BASELINE configs 3, 4 and 5 at their full sizes, through properties that need no full oracle render:
+    config 3 (10k instances x 100k triangles, alpha MASK): ids bit-exact vs the oracle on a ray sample, determinism;
+    config 4 (1M-triangle skinned character): the refit BVH returns the hits of a full rebuild of the same pose;
+    config 5 (3840x2160 glass / volume): determinism, 8-way strip partition == whole frame, finite output."""
+    # ---- config 3
+    d = scenes.instanced_foliage(n_side=100, tris_per_mesh=100_000, cards=64, tex_size=1024, sky=scenes.procedural_sky(64))
+    from oracle import orc
+    o = orc.OracleScene(d)
+    ctx = core.Context(1920, 1080, api=api); sc = core.Scene(ctx, d)
+    rays, rng4 = util.random_rays(50000, seed=41, extent=5.0)
+    for flags in (0, 1):
+        assert util.hits_equal(sc.trace_closest(rays, flags, rng4), o.trace_closest(rays, flags, rng4)).all()
+    cam = host.Camera(1920, 1080).set(position=(0, 1.2, 7.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=8, sky=1)
+    u = host.FrameDriver(cam, gui, False).next_ubo()
+    ctx.render(sc, u); a0, o0 = ctx.readback()
+    ctx.resize(1920, 1080); ctx.render(sc, u); a1, o1 = ctx.readback()
+    assert (a0 == a1).all() and (o0 == o1).all() and np.isfinite(a0).all() and a0[..., :3].max() > 0
+    del sc, ctx, o
+    # ---- config 4
+    d, pose = scenes.skinned_character(n_tris=1_000_000, joints=256)
+    ctx = core.Context(256, 144, api=api); sc = core.Scene(ctx, d)
+    rays, _ = util.random_rays(200000, seed=43, extent=3.0)
+    sc.update_skins(pose(17)); h_refit = sc.trace_closest(rays, 1)
+    sc.update_skins(pose(17), rebuild=True); h_build = sc.trace_closest(rays, 1)
+    assert util.hits_equal(h_refit, h_build).all() and (h_refit["t"] > 0).mean() > 0.01
+    del sc, ctx
+    # ---- config 5
+    d = scenes.glass_box(n_objects=64)
+    W, H = 3840, 2160
+    ctx = core.Context(W, H, api=api); sc = core.Scene(ctx, d)
+    cam = host.Camera(W, H).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=8)
+    u = host.FrameDriver(cam, gui, bool(d.fully_opaque)).next_ubo()
+    ctx.render(sc, u); a0, o0 = ctx.readback()
+    ctx.resize(W, H)
+    for part in range(8):
+        ctx.render(sc, u, strip_rows=8, n_parts=8, part=part)
+    a1, o1 = ctx.readback()
+    assert (a0 == a1).all() and (o0 == o1).all() and np.isfinite(a0).all() and (o0[..., 3] == 255).all()
+
+
 def test_errors_are_reported_not_swallowed(api, cornell_desc):
     ctx = core.Context(32, 32, api=api); sc = core.Scene(ctx, cornell_desc)
     u = F.rt_ubo()   # total_number_of_samples == 0
