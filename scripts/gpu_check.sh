@@ -12,7 +12,7 @@ echo "== bench" | tee gpurun_out/bench.log
 timeout 600 python bench.py --steps ${BENCH_STEPS:-30} --warmup 5 2>&1 | tail -5 | tee -a gpurun_out/bench.log
 if [ "${NCU:-1}" = "1" ]; then
   echo "== ncu launch list"
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   tail -3 gpurun_out/ncu_bench.log
 fi
