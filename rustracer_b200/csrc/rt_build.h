@@ -309,6 +309,9 @@ inline void emu_sah_binary_build(const DAabb* boxes, int n, uint32_t* vals, int2
 #ifndef RT_PLOC_RADIUS
 #define RT_PLOC_RADIUS 16
 #endif
+#ifndef RT_PLOC_BATCH
+#define RT_PLOC_BATCH 16     // rounds between two host reads of the cluster count (465 k triangles: 113 rounds, ~10 ms)
+#endif
 inline int builder_kind() {
     static int kind = -1;
     if (kind < 0) { const char* e = getenv("RT_B200_BUILDER"); kind = (e && e[0] == 'l') ? 0 : 1; }   // "lbvh" | "ploc" (default)
@@ -327,49 +330,62 @@ inline int ploc_build(const DAabb* prim_boxes, int n, BuildScratch& sc, rt_strea
             cl[i] = leaf;
         });
     }
-    uint32_t c = (uint32_t)n, merged = 0, rounds = 0;
-    while (c > 1) {
-        const uint32_t* cl = cl_in; uint32_t* co = cl_out; const int ci = (int)c;
-        rt_launch(c, stream, RT_LAMBDA(size_t i) {
-            const DAabb a = bin_box[cl[i]];
-            const int lo = (int)i - RT_PLOC_RADIUS < 0 ? 0 : (int)i - RT_PLOC_RADIUS;
-            const int hi = (int)i + RT_PLOC_RADIUS > ci - 1 ? ci - 1 : (int)i + RT_PLOC_RADIUS;
-            float best = 3.0e38f; int bj = -1;
-            for (int j = lo; j <= hi; ++j) {
-                if (j == (int)i) continue;
-                const float d = aabb_half_area(aabb_union(a, bin_box[cl[j]]));
-                if (d < best || bj < 0) { best = d; bj = j; }   // ties -> lowest position, which guarantees a mutual pair
-            }
-            nn[i] = (uint32_t)bj;
-        });
-        rt_launch(c, stream, RT_LAMBDA(size_t i) {
-            const uint32_t j = nn[i];
-            valid[i] = (nn[j] == (uint32_t)i && j < (uint32_t)i) ? 0u : 1u;   // the higher half of a pair is absorbed
-        });
-        if (rt_exclusive_scan_u32(valid, pos, c, stream)) return 1;
-        const uint32_t merged_before = merged;
-        rt_launch(c, stream, RT_LAMBDA(size_t i) {
-            if (i == (size_t)(ci - 1)) counters[3] = pos[i] + valid[i];
-            if (!valid[i]) return;
-            const uint32_t j = nn[i];
-            uint32_t id = cl[i];
-            if (nn[j] == (uint32_t)i) {
-                const uint32_t rank = j - pos[j];   // absorbed entries before j == merges before this one
-                const uint32_t a = id, b = cl[j];
-                id = (uint32_t)(n - 2) - (merged_before + rank);
-                bin_children[id] = make_int2((int)a, (int)b);
-                bin_box[id] = aabb_union(bin_box[a], bin_box[b]);
-                bin_count[id] = (a >= (uint32_t)(n - 1) ? 1u : bin_count[a]) + (b >= (uint32_t)(n - 1) ? 1u : bin_count[b]);
-            }
-            co[pos[i]] = id;
-        });
+    // The cluster count c and the number of merges so far live on the device (counters[4..5] and [6..7], alternating by
+    // round), so that RT_PLOC_BATCH rounds run back to back with launches sized for the count at the start of the batch;
+    // the host reads c once per batch instead of once per round (45 rounds for the 465 k triangles of config 2).
+    uint32_t c_ub = (uint32_t)n, rounds = 0;
+    { const uint32_t init[4] = {(uint32_t)n, 0u, (uint32_t)n, 0u}; if (rt_h2d(&counters[4], init, sizeof init, stream)) return 1; }
+    while (c_ub > 1) {
+        for (int r = 0; r < RT_PLOC_BATCH; ++r, ++rounds) {
+            const uint32_t* cl = cl_in; uint32_t* co = cl_out;
+            const uint32_t* cur = counters + 4 + 2 * (rounds & 1u); uint32_t* nxt = counters + 4 + 2 * ((rounds + 1u) & 1u);
+            rt_launch(c_ub, stream, RT_LAMBDA(size_t i) {
+                const int ci = (int)cur[0];
+                if ((int)i >= ci || ci <= 1) return;
+                const DAabb a = bin_box[cl[i]];
+                const int lo = (int)i - RT_PLOC_RADIUS < 0 ? 0 : (int)i - RT_PLOC_RADIUS;
+                const int hi = (int)i + RT_PLOC_RADIUS > ci - 1 ? ci - 1 : (int)i + RT_PLOC_RADIUS;
+                float best = 3.0e38f; int bj = -1;
+                for (int j = lo; j <= hi; ++j) {
+                    if (j == (int)i) continue;
+                    const float d = aabb_half_area(aabb_union(a, bin_box[cl[j]]));
+                    if (d < best || bj < 0) { best = d; bj = j; }   // ties -> lowest position, which guarantees a mutual pair
+                }
+                nn[i] = (uint32_t)bj;
+            });
+            rt_launch(c_ub, stream, RT_LAMBDA(size_t i) {
+                const uint32_t ci = cur[0];
+                if (i >= ci || ci <= 1u) { valid[i] = (ci <= 1u && i == 0) ? 1u : 0u; return; }
+                const uint32_t j = nn[i];
+                valid[i] = (nn[j] == (uint32_t)i && j < (uint32_t)i) ? 0u : 1u;   // the higher half of a pair is absorbed
+            });
+            if (rt_exclusive_scan_u32(valid, pos, c_ub, stream)) return 1;
+            rt_launch(c_ub, stream, RT_LAMBDA(size_t i) {
+                const uint32_t ci = cur[0], merged_before = cur[1];
+                if (ci <= 1u) { if (i == 0) { nxt[0] = ci; nxt[1] = merged_before; co[0] = cl[0]; } return; }
+                if (i >= ci) return;
+                if (i == (size_t)(ci - 1u)) { const uint32_t c_new = pos[i] + valid[i]; nxt[0] = c_new; nxt[1] = merged_before + (ci - c_new); }
+                if (!valid[i]) return;
+                const uint32_t j = nn[i];
+                uint32_t id = cl[i];
+                if (nn[j] == (uint32_t)i) {
+                    const uint32_t rank = j - pos[j];   // absorbed entries before j == merges before this one
+                    const uint32_t a = id, b = cl[j];
+                    id = (uint32_t)(n - 2) - (merged_before + rank);
+                    bin_children[id] = make_int2((int)a, (int)b);
+                    bin_box[id] = aabb_union(bin_box[a], bin_box[b]);
+                    bin_count[id] = (a >= (uint32_t)(n - 1) ? 1u : bin_count[a]) + (b >= (uint32_t)(n - 1) ? 1u : bin_count[b]);
+                }
+                co[pos[i]] = id;
+            });
+            uint32_t* t = cl_in; cl_in = cl_out; cl_out = t;
+        }
         uint32_t c_new = 0;
-        if (rt_d2h(&c_new, &counters[3], 4, stream)) return 1;
+        if (rt_d2h(&c_new, counters + 4 + 2 * (rounds & 1u), 4, stream)) return 1;
         if (rt_stream_sync(stream)) return 1;
-        if (c_new == 0 || c_new >= c) return 4;   // cannot happen: every round has at least one mutual pair
-        merged += c - c_new; c = c_new;
-        uint32_t* t = cl_in; cl_in = cl_out; cl_out = t;
-        if (++rounds > 100000u) return 4;
+        if (c_new == 0 || c_new > c_ub || (c_new == c_ub && c_ub > 1)) return 4;   // cannot happen: every round has at least one mutual pair
+        c_ub = c_new;
+        if (rounds > 100000u) return 4;
     }
     return 0;
 }
