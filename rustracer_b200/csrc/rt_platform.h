@@ -169,7 +169,7 @@ template <class F> inline void rt_launch(size_t n, rt_stream_t s, F f) {
 
 struct rt_timer {
     cudaEvent_t e = nullptr;
-    void create() { cudaEventCreate(&e); }
+    void create() { if (!e) cudaEventCreate(&e); }
     void destroy() { if (e) cudaEventDestroy(e); e = nullptr; }
     void record(rt_stream_t s) { cudaEventRecord(e, s); }
 };
