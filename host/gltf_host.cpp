@@ -42,7 +42,7 @@ struct Json {
     int integer(const char* k, int def) const { auto j = get(k); return (j && j->type == Num) ? (int)j->num : def; }
     std::string string(const char* k, const std::string& def = "") const { auto j = get(k); return (j && j->type == Str) ? j->str : def; }
     size_t size() const { return type == Arr ? arr.size() : 0; }
-    const Json& operator[](size_t i) const { return arr[i]; }
+    const Json& operator[](size_t i) const { if (type != Arr || i >= arr.size()) die("json: array index out of range"); return arr[i]; }
 };
 
 struct JsonParser {
@@ -694,12 +694,17 @@ struct Loader {
         View v; v.ctype = a.integer("componentType", 5126); v.ncomp = ncomp_of(a.string("type")); v.count = (size_t)a.number("count", 0);
         v.normalized = a.get("normalized") && a.get("normalized")->b;
         int bv = a.integer("bufferView", -1); if (bv < 0) die("accessor without bufferView unsupported");
-        const Json& b = (*root.get("bufferViews"))[bv];
+        const Json* bvs = root.get("bufferViews");
+        if (!bvs) die("accessor refers to a bufferView but the file has none");
+        const Json& b = (*bvs)[(size_t)bv];
         size_t off = (size_t)b.number("byteOffset", 0) + (size_t)a.number("byteOffset", 0);
         size_t elem = (size_t)csize(v.ctype) * v.ncomp;
         v.stride = (size_t)b.number("byteStride", 0); if (!v.stride) v.stride = elem;
-        const std::vector<uint8_t>& buf = buffers.at(b.integer("buffer", 0));
-        if (v.count && off + v.stride * (v.count - 1) + elem > buf.size()) die("accessor out of buffer range");
+        const int bi = b.integer("buffer", 0);
+        if (bi < 0 || (size_t)bi >= buffers.size()) die("bufferView refers to a missing buffer");
+        const std::vector<uint8_t>& buf = buffers[(size_t)bi];
+        if (v.ncomp <= 0) die("accessor with an unknown type");
+        if (v.count && (v.count > buf.size() || off > buf.size() || v.stride > buf.size() || off + v.stride * (v.count - 1) + elem > buf.size())) die("accessor out of buffer range");
         v.base = buf.data() + off; return v;
     }
     static float comp_f32(const View& v, size_t i, int c, bool normalize_ints) {
@@ -841,8 +846,36 @@ struct Loader {
             if (sk.ibm.size() != sk.joints.size()) die("ibm/joint count mismatch");
             doc.skins.push_back(sk);
         }
+        validate_graph();
         if (!doc.skins.empty()) tag_skinned_vertices();
         load_scene();
+    }
+
+    // The gltf crate validates indices at import and the reference unwraps / panics on what is left; here every index the
+    // scene graph follows is checked once so that a malformed file is an error, never an out-of-bounds access.
+    void validate_graph() {
+        const int nn = (int)doc.nodes.size(), nm = (int)doc.meshes.size(), ns = (int)doc.skins.size();
+        for (const auto& sc : doc.scenes) for (int r : sc) if (r < 0 || r >= nn) die("scene refers to a missing node");
+        for (const Node& n : doc.nodes) {
+            if (n.mesh < -1 || n.mesh >= nm) die("node refers to a missing mesh");
+            if (n.skin < -1 || n.skin >= ns) die("node refers to a missing skin");
+            for (int c : n.children) if (c < 0 || c >= nn) die("node refers to a missing child");
+        }
+        for (const Skin& sk : doc.skins) for (int j : sk.joints) if (j < 0 || j >= nn) die("skin refers to a missing joint node");
+        for (const Channel& ch : doc.channels) if (ch.target < 0 || ch.target >= nn) die("animation channel targets a missing node");
+        // the hierarchy must be a forest: every node reachable at most once from the scene roots
+        std::vector<char> seen((size_t)nn, 0);
+        std::vector<int> stack;
+        for (const auto& sc : doc.scenes) {
+            std::fill(seen.begin(), seen.end(), 0);
+            for (int r : sc) stack.push_back(r);
+            while (!stack.empty()) {
+                const int i = stack.back(); stack.pop_back();
+                if (seen[(size_t)i]) die("node hierarchy is not a tree (a node is reachable twice)");
+                seen[(size_t)i] = 1;
+                for (int c : doc.nodes[(size_t)i].children) stack.push_back(c);
+            }
+        }
     }
 
     Primitive make_primitive(const Json& pr, const Json& at) {
@@ -968,7 +1001,9 @@ struct Loader {
             const Json& an = (*anims)[a]; const Json* chs = an.get("channels"); const Json* sms = an.get("samplers");
             for (size_t c = 0; chs && c < chs->size(); ++c) {
                 const Json& ch = (*chs)[c]; const Json* tg = ch.get("target"); if (!tg || !tg->has("node")) continue;
-                const Json& sm = (*sms)[ch.integer("sampler", 0)];
+                if (!sms) die("animation channel without samplers");
+                const int si = ch.integer("sampler", 0); if (si < 0) die("animation channel refers to a missing sampler");
+                const Json& sm = (*sms)[(size_t)si];
                 Channel out; out.target = tg->integer("node", 0);
                 std::string path = tg->string("path"); out.prop = path == "translation" ? 0 : path == "rotation" ? 1 : path == "scale" ? 2 : 3;
                 std::string ip = sm.string("interpolation", "LINEAR"); out.interp = ip == "STEP" ? 1 : ip == "CUBICSPLINE" ? 2 : 0;

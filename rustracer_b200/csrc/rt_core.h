@@ -759,6 +759,11 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
     rt_stream_t st = c->stream;
     // ---- validation (the reference panics on malformed input; we return an error) ----
     if (d->n_geometries && (!d->prim_infos || !d->geometries)) return fail("rt_scene_create: geometry arrays missing");
+    if ((d->n_vertices && !d->vertices) || (d->n_indices && !d->indices) || (d->n_materials && !d->materials) || (d->n_instances && !d->instances) ||
+        (d->n_images && !d->images) || (d->n_samplers && !d->samplers) || (d->n_textures && !d->textures) || (d->n_dlights && !d->dlights) ||
+        (d->n_plights && !d->plights) || (d->n_skins && !d->skins))
+        return fail("rt_scene_create: an array pointer is null although its count is not zero");
+    for (uint32_t i = 0; i < d->n_images; ++i) if (!d->images[i].rgba8 || !d->images[i].width || !d->images[i].height) return fail("rt_scene_create: empty image");
     if (!d->n_materials) return fail("rt_scene_create: at least one material is required");
     for (uint32_t g = 0; g < d->n_geometries; ++g) {
         const rt_prim_info& pi = d->prim_infos[g]; const rt_geometry& ge = d->geometries[g];

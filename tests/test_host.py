@@ -326,3 +326,29 @@ def test_cpp_gltf_viewer_matches_python_viewer(tmp_path):
     gltf_viewer.main([*common, "-o", str(tmp_path / "py.png")])
     a, b = np.asarray(Image.open(tmp_path / "cpp.png")), np.asarray(Image.open(tmp_path / "py.png"))
     assert a.shape == (64, 96, 3) and (a == b).all() and a.std() > 0
+
+
+def test_malformed_gltf_is_an_error_not_a_crash(tmp_path):
+    """The gltf crate validates indices at import and the reference panics on the rest; the C++ loader must turn every
+    dangling index / wrong type into an error (found by fuzzing the tiny file: these used to read out of bounds)."""
+    base = json.loads(write_gltf(tmp_path).read_text())
+
+    def broken(mutate):
+        g = json.loads(json.dumps(base)); mutate(g)
+        p = tmp_path / "bad.gltf"; p.write_text(json.dumps(g))
+        with pytest.raises(RuntimeError):
+            host.load_file(p).scene_desc()
+
+    broken(lambda g: g["scenes"][0].__setitem__("nodes", [7]))                  # scene -> missing node
+    broken(lambda g: g["nodes"][0].__setitem__("mesh", 1))                      # node -> missing mesh
+    broken(lambda g: g.__setitem__("meshes", []))
+    broken(lambda g: g.__setitem__("nodes", 0))                                 # wrong JSON type
+    broken(lambda g: g["nodes"][0].__setitem__("children", [0]))                # cycle
+    broken(lambda g: g["nodes"][0].__setitem__("skin", 0))                      # node -> missing skin
+    broken(lambda g: g["accessors"][0].__setitem__("bufferView", 9))            # accessor -> missing bufferView
+    broken(lambda g: g["bufferViews"][0].__setitem__("buffer", 3))              # bufferView -> missing buffer
+    broken(lambda g: g["accessors"][2].__setitem__("count", 10 ** 9))           # accessor beyond the buffer
+    broken(lambda g: g.pop("bufferViews"))
+    broken(lambda g: g["meshes"][0]["primitives"][0]["attributes"].__setitem__("POSITION", 5))
+    broken(lambda g: g.__setitem__("animations", [{"channels": [{"sampler": 0, "target": {"node": 4, "path": "translation"}}],
+                                                   "samplers": [{"input": 0, "output": 0}]}]))   # channel -> missing node
