@@ -708,6 +708,7 @@ struct Loader {
         v.base = buf.data() + off; return v;
     }
     static float comp_f32(const View& v, size_t i, int c, bool normalize_ints) {
+        if (c >= v.ncomp || i >= v.count) return 0.0f;     // view() only vouches for ncomp components of count elements
         const uint8_t* p = v.base + i * v.stride + (size_t)c * csize(v.ctype);
         switch (v.ctype) {
             case 5126: { float f; memcpy(&f, p, 4); return f; }
@@ -720,6 +721,7 @@ struct Loader {
         return 0;
     }
     static uint32_t comp_u32(const View& v, size_t i, int c) {
+        if (c >= v.ncomp || i >= v.count) return 0u;
         const uint8_t* p = v.base + i * v.stride + (size_t)c * csize(v.ctype);
         switch (v.ctype) {
             case 5121: return p[0];
@@ -889,6 +891,7 @@ struct Loader {
         std::vector<uint32_t> idx;
         if (pr.has("indices")) { View iv = view(pr.integer("indices", -1)); idx.resize(iv.count); for (size_t i = 0; i < iv.count; ++i) idx[i] = comp_u32(iv, i, 0); }
         else { idx.resize(nv); for (size_t i = 0; i < nv; ++i) idx[i] = (uint32_t)i; }
+        for (uint32_t v : idx) if (v >= nv) die("vertex index out of range");      // the normal / tangent generators below index the vertices with it
         if (at.has("NORMAL")) { View v = view(at.integer("NORMAL", -1)); for (size_t i = 0; i < nv && i < v.count; ++i) for (int c = 0; c < 3; ++c) verts[i].normal[c] = comp_f32(v, i, c, true); }
         else {   // create_geo_normal geometry.rs:270-290
             for (size_t t = 0; t + 2 < idx.size(); t += 3) {
@@ -1011,6 +1014,10 @@ struct Loader {
                 out.input.resize(in.count); for (size_t i = 0; i < in.count; ++i) out.input[i] = comp_f32(in, i, 0, false);
                 out.comps = ov.ncomp; out.out.resize(ov.count * ov.ncomp);
                 for (size_t i = 0; i < ov.count; ++i) for (int k = 0; k < ov.ncomp; ++k) out.out[i * ov.ncomp + k] = comp_f32(ov, i, k, true);
+                if (out.prop != 3) {   // the sampler below reads input.size() keys (three per key for CUBICSPLINE) of 3 or 4 floats
+                    const size_t keys = out.interp == 2 ? out.input.size() * 3 : out.input.size();
+                    if (out.comps < (out.prop == 1 ? 4 : 3) || out.out.size() < keys * (size_t)out.comps) die("animation sampler output does not match its input");
+                }
                 doc.channels.push_back(std::move(out));
             }
         }

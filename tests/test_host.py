@@ -352,3 +352,17 @@ def test_malformed_gltf_is_an_error_not_a_crash(tmp_path):
     broken(lambda g: g["meshes"][0]["primitives"][0]["attributes"].__setitem__("POSITION", 5))
     broken(lambda g: g.__setitem__("animations", [{"channels": [{"sampler": 0, "target": {"node": 4, "path": "translation"}}],
                                                    "samplers": [{"input": 0, "output": 0}]}]))   # channel -> missing node
+    g1 = json.loads(json.dumps(base)); g1["accessors"][0].update(type="SCALAR", componentType=5123)   # POSITION with one component:
+    p1 = tmp_path / "narrow.gltf"; p1.write_text(json.dumps(g1))                                # missing components read as 0, never outside the buffer
+    try:
+        host.load_file(p1).scene_desc()
+    except RuntimeError:
+        pass
+    broken(lambda g: g.__setitem__("animations", [{"channels": [{"sampler": 0, "target": {"node": 0, "path": "rotation"}}],
+                                                   "samplers": [{"input": 0, "output": 2}]}]))   # sampler output shorter / narrower than its input
+    idx_bad = np.array([0, 1, 2, 2, 1, 9], np.uint16).tobytes()
+
+    def bad_index(g):
+        raw = bytearray(base64.b64decode(g["buffers"][0]["uri"].split(",", 1)[1])); raw[64:76] = idx_bad
+        g["buffers"][0]["uri"] = "data:application/octet-stream;base64," + base64.b64encode(bytes(raw)).decode()
+    broken(bad_index)                                                                           # vertex index beyond the vertex count
