@@ -13,5 +13,7 @@ print("frames-in-flight case: PASS")
 PY
 for tool in memcheck racecheck; do
   ( timeout 600 compute-sanitizer --tool $tool python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -E "smoke:|ERROR SUMMARY|RACECHECK SUMMARY|=========  *(Invalid|Race|Error)" | head -20
-    timeout 600 compute-sanitizer --tool $tool python /tmp/fif_case.py 2>&1 | grep -E "PASS|ERROR SUMMARY|RACECHECK SUMMARY|Traceback|Error|=========  *(Invalid|Race)" | head -20 ) | tee gpurun_out/sanitizer_$tool.txt
+    timeout 600 compute-sanitizer --tool $tool python /tmp/fif_case.py 2>&1 | grep -E "PASS|ERROR SUMMARY|RACECHECK SUMMARY|Traceback|Error|=========  *(Invalid|Race)" | head -20
+    # skinning kernel, cooperative BLAS / TLAS refit, multi-buffered scene, lifecycle with frames in flight
+    timeout 900 compute-sanitizer --tool $tool python -m pytest tests -x -q -m gpu -k "skinning_refit or skinned_animation or lifecycle" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|=========  *(Invalid|Race)" | head -20 ) | tee gpurun_out/sanitizer_$tool.txt
 done
