@@ -5,8 +5,10 @@
     python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on the host cores
     torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU (sample-pass sharding, §8e B)
 
-A step is one frame: 1 spp per pixel at max depth 8 over the Lucy-in-Cornell stand-in scene (config 2: the real
-Lucy scan is not shipped), accumulated like the reference does (RayTracing.rgen:132-166).
+A step is one frame: 1 spp per pixel at max depth 8 over the Lucy-in-Cornell stand-in scene (config 2: Cornell shell
+from the bundled cornellBox asset (tests/golden/cornell_box_scene.npz), the real Lucy scan is not shipped),
+seen from the reference's default camera (app/src/lib.rs:331-338: position (0,0,1) looking down -z, fov 60), accumulated
+like the reference does (RayTracing.rgen:132-166).
 Mrays/s counts every traced segment (path segments + shadow rays), SURVEY.md §8d.
 Rank 0 prints ONE JSON line.
 """
@@ -32,7 +34,9 @@ WIDTH, HEIGHT, BOUNCES, SPP = 1920, 1080, 8, 1
 CONFIG = 2          # BASELINE.json configs[1] is the headline workload; --config selects the others (extra, not the driver's line)
 POSE = None         # config 4: per-frame skin matrices
 GUI_KW = {}
-CAM_POS = (0, 0, 14.0)
+CAM_POS = (0, 0, 1.0)    # the reference's default camera (app/src/lib.rs:331-338): inside the box, looking down -z
+CAM_ALT = (0, 0, 14.0)   # round-1 headline camera (outside the box: 2.4 rays/pixel, 30 % misses); kept as a second, labelled figure
+SHELL = ROOT / "tests" / "golden" / "cornell_box_scene.npz"   # the real cornellBox.gltf shell, exported by tests/golden/make_golden.py
 NAMES = {1: "procedural Cornell box (configs[0]) 512x512, 1 spp/frame, max depth 8",
          2: "Lucy-in-Cornell stand-in (BASELINE configs[1]) 1920x1080, 1 spp/frame accumulated, max depth 8",
          3: "10k instances of a 100k-triangle BLAS + alpha-MASK foliage cards (configs[2]) 1920x1080, sky + directional light, max depth 8",
@@ -45,6 +49,8 @@ def select_config(c: int):
     CONFIG = c
     if c == 1:
         WIDTH, HEIGHT = 512, 512
+    elif c == 2:
+        pass
     elif c == 3:
         GUI_KW = {"sky": 1}; CAM_POS = (0, 1.2, 7.0)
     elif c == 4:
@@ -169,8 +175,9 @@ class ClockSampler:
 def build_scene_desc():
     global POSE
     from rustracer_b200 import scenes
+    shell = SHELL if SHELL.exists() else None
     if CONFIG == 1:
-        return scenes.cornell_box(lucy=False)
+        return scenes.cornell_box(lucy=False, shell=shell)
     if CONFIG == 3:
         return scenes.instanced_foliage(n_side=100, tris_per_mesh=100_000, cards=64, tex_size=1024, sky=scenes.procedural_sky(256))
     if CONFIG == 4:
@@ -178,7 +185,14 @@ def build_scene_desc():
         return d
     if CONFIG == 5:
         return scenes.glass_box(n_objects=64)
-    return scenes.cornell_box(lucy=True)
+    return scenes.cornell_box(lucy=True, shell=shell)
+
+
+def make_gui():
+    from rustracer_b200 import host
+    # max_number_of_samples: Gui::new's 5000 would silently end the sample budget (number_of_samples -> 0) in long or
+    # many-GPU runs; the bench accumulates without a budget
+    return host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES, max_number_of_samples=0x7FFFFFFF, **GUI_KW)
 
 
 def frame_ubo(cam, gui, frame_index: int, fully_opaque: bool):
@@ -187,20 +201,26 @@ def frame_ubo(cam, gui, frame_index: int, fully_opaque: bool):
     u = F.rt_ubo()
     total = F.c_u32(frame_index)
     F.load_host().gv_build_ubo(C.byref(cam.c), C.byref(gui.g), C.byref(total), frame_index, int(fully_opaque), 3, C.byref(u))
+    assert u.number_of_samples == SPP and u.total_number_of_samples == frame_index + 1 or gui.g.animation, "sample budget exhausted"
     return u
 
 
+COUNTER_KEYS = ("rays_extend", "rays_shadow", "shaded_hits", "pixel_samples", "nodes", "tris", "insts", "anyhits", "tex_taps", "light_cands")
+
+
 def algorithmic_bytes(st, spp=SPP):
-    """SURVEY.md §8d formula.  Returns (extend-kernel bytes, whole-frame bytes)."""
+    """SURVEY.md §8d formula, every count taken from in-kernel counters of the same frames.  Returns (traversal bytes of
+    extend + shadow rays, whole-frame bytes).  shaded_hits are closest hits only (misses run the miss stage: no vertex /
+    material gather); texture taps of shading and of the any-hit stage share one counter (16 B per bilinear tap)."""
     rays = st["rays_extend"] + st["rays_shadow"]
     trav = 48 * rays + 80 * st["nodes"] + 48 * st["tris"] + 64 * st["insts"] + (12 + 96 + 32) * st["anyhits"]
-    shade = (12 + 384 + 16 + 256 + 48 + 128) * st["shaded_hits"]
+    shade = (12 + 384 + 16 + 256 + 48 + 128) * st["shaded_hits"] + 16 * st["tex_taps"] + 48 * st["light_cands"]
     pix = 36 * st["pixel_samples"] / spp
     return trav, trav + shade + pix
 
 
 def stats_dict(st):
-    return {k: int(getattr(st, k)) for k in ("rays_extend", "rays_shadow", "shaded_hits", "pixel_samples", "nodes", "tris", "insts", "anyhits")}
+    return {k: int(getattr(st, k)) for k in COUNTER_KEYS}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -212,7 +232,7 @@ def cpu_sample(desc, frames: int, rows, warm: int = 0):
     from rustracer_b200 import host
     s = orc.OracleScene(desc)
     cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS)
-    gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES, **GUI_KW)
+    gui = make_gui()
     acc = np.zeros((HEIGHT, WIDTH, 4), np.float32)
     rays, secs = 0, 0.0
     for f in range(warm + frames):
@@ -231,14 +251,17 @@ def run_reference(args):
         return
     from oracle import orc
     desc = build_scene_desc()
-    cores = orc.lib().orc_num_threads() if hasattr(orc.lib(), "orc_num_threads") else os.cpu_count()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core regardless
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc.lib().orc_set_num_threads(int(ncpu))
+    cores = orc.lib().orc_num_threads() if hasattr(orc.lib(), "orc_num_threads") else ncpu
     # calibrate a row band so that one step takes ~1 s
     m, rays, secs = cpu_sample(desc, 1, (HEIGHT // 2 - 20, HEIGHT // 2 + 20))
     band = int(max(8, min(HEIGHT, 40 * (1.0 / max(secs, 1e-3)))))
     r0 = (HEIGHT - band) // 2
     from rustracer_b200 import host
     s = orc.OracleScene(desc)
-    cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS); gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES, **GUI_KW)
+    cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS); gui = make_gui()
     acc = np.zeros((HEIGHT, WIDTH, 4), np.float32)
     total_rays, t_total, samples = 0, 0.0, 0
     for f in range(args.warmup + args.steps):
@@ -250,7 +273,8 @@ def run_reference(args):
     sample = f"rows {r0}..{r0 + band} of each {WIDTH}x{HEIGHT} frame, {args.steps} frames x 1 spp, depth 8, all host threads"
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(desc) | {"note": "reference cannot be built/run here (Rust+Vulkan RT, no toolchain): CPU oracle port stands in (BASELINE.md §3)"},
+            "config": workload_config(desc),
+            "note": "reference cannot be built/run here (Rust+Vulkan RT, no toolchain): CPU oracle port stands in (BASELINE.md §3)",
             "samples_per_s": samples / t_total,
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": int(cores), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -259,6 +283,9 @@ def run_reference(args):
 
 def workload_config(desc):
     return {"workload": NAMES[CONFIG],
+            "camera": {"position": list(CAM_POS), "direction": [0, 0, -1], "fov_deg": 60,
+                       "note": "reference default camera (app/src/lib.rs:331-338)" if CAM_POS == (0, 0, 1.0) else "scene-specific camera"},
+            "shell": "cornellBox.gltf asset (tests/golden/cornell_box_scene.npz)" if (CONFIG in (1, 2) and SHELL.exists()) else "procedural",
             "triangles": int(desc.n_indices // 3), "instances": int(desc.n_instances), "width": WIDTH, "height": HEIGHT, "spp_per_step": SPP, "max_depth": BOUNCES,
             "l2": "per-frame path-state/hit streams (~480 MB at 1080p) exceed the 126 MB L2; the ~28 MB BVH is L2-resident by design (SURVEY.md App. G)"}
 
@@ -291,27 +318,12 @@ def run_ours(args):
     t0 = time.perf_counter(); scene = core.Scene(ctx, desc); build_s = time.perf_counter() - t0
     info = scene.bvh_info()
     cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS)
-    gui = host.Gui(number_of_samples=SPP, number_of_bounces=BOUNCES, **GUI_KW)
+    gui = make_gui()
     K, Wm = args.steps, args.warmup
     # sample-pass sharding (§8e B): global frame g = step * world + rank; every rank starts from a zero accumulation
     from rustracer_b200 import sharding
     ubos = [frame_ubo(cam, gui, sharding.global_frame(s, rank, world), desc.fully_opaque) for s in range(Wm + K)]
     final_ubo = frame_ubo(cam, gui, (Wm + K) * world - 1, desc.fully_opaque)
-
-    peers = []
-    if world > 1:
-        handle = (C.c_uint8 * 64)()
-        ctx.api.check(ctx.api.rt_ipc_export(ctx._h, handle))
-        gathered = [None] * world
-        dist.all_gather_object(gathered, bytes(handle))
-        for r, hb in enumerate(gathered):
-            if r == rank:
-                continue
-            p = C.c_void_p(); buf = (C.c_uint8 * 64).from_buffer_copy(hb)
-            ctx.api.check(ctx.api.rt_ipc_open(ctx._h, buf, C.byref(p)))
-            peers.append(p.value)
-    peer_arr = (C.c_void_p * max(1, len(peers)))(*peers)
-    row0, row1 = sharding.reduce_rows(rank, world, HEIGHT)
 
     def barrier():
         torch.cuda.synchronize()
@@ -342,6 +354,23 @@ def run_ours(args):
     if POSE is not None:
         scene.set_versions(max(2, min(4, args.scene_versions)))   # skin updates write the next copy while frames read the previous ones
     ctx.resize(WIDTH, HEIGHT)
+    # peers map the accumulation image only now, after the last (re)allocation: rt_frame_resize with unchanged dimensions
+    # clears in place and a size change is refused while a handle is exported
+    peers = []
+    if world > 1:
+        handle = (C.c_uint8 * 64)()
+        ctx.api.check(ctx.api.rt_ipc_export(ctx._h, handle))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(handle))
+        for r, hb in enumerate(gathered):
+            if r == rank:
+                continue
+            p = C.c_void_p(); buf = (C.c_uint8 * 64).from_buffer_copy(hb)
+            ctx.api.check(ctx.api.rt_ipc_open(ctx._h, buf, C.byref(p)))
+            peers.append(p.value)
+    peer_arr = (C.c_void_p * max(1, len(peers)))(*peers)
+    row0, row1 = sharding.reduce_rows(rank, world, HEIGHT)
+
     frames(0, Wm)
     ctx.synchronize()
     sampler = ClockSampler(local).prepare()
@@ -376,7 +405,7 @@ def run_ours(args):
     ctx.set_frames_in_flight(1)                # per-frame statistics and per-kernel event timing: one frame at a time
     ctx.resize(WIDTH, HEIGHT)
     frames(0, Wm)
-    tot = dict.fromkeys(("rays_extend", "rays_shadow", "shaded_hits", "pixel_samples", "nodes", "tris", "insts", "anyhits"), 0)
+    tot = dict.fromkeys(COUNTER_KEYS, 0)
     ext_ms, launches, n_ext = 0.0, 0, 0
     for s in range(Wm, Wm + K):
         pre_step(s)
@@ -440,25 +469,59 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = rays_all / (float(t_e2e.item()) * 1e-3) / 1e6
 
+    # ---- second, labelled figure: the round-1 camera outside the box (not the headline; kept for continuity) ----
+    alt = None
+    if CONFIG == 2 and world == 1 and not args.no_alt_camera:
+        cam2 = host.Camera(WIDTH, HEIGHT).set(position=CAM_ALT)
+        ubos2 = [frame_ubo(cam2, gui, s, desc.fully_opaque) for s in range(Wm + K)]
+        ctx.set_frames_in_flight(NF); ctx.resize(WIDTH, HEIGHT)
+        for s in range(Wm):
+            ctx.render(scene, ubos2[s], stream=stream)
+        ctx.synchronize(); torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for s in range(Wm, Wm + K):
+            ctx.render(scene, ubos2[s], stream=stream)
+        ctx.join(stream); a1.record(); torch.cuda.synchronize()
+        alt_ms = a0.elapsed_time(a1)
+        ctx.set_frames_in_flight(1); ctx.resize(WIDTH, HEIGHT)
+        alt_rays = 0
+        for s in range(Wm + K):
+            ctx.render(scene, ubos2[s], stream=stream)
+            if s >= Wm:
+                st2 = ctx.stats(); alt_rays += st2.rays_extend + st2.rays_shadow
+        alt = {"camera": {"position": list(CAM_ALT), "direction": [0, 0, -1], "note": "round-1 headline camera, outside the box (about half the rays per pixel, ~30 % misses)"},
+               "value": alt_rays / (alt_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": alt_ms / K, "rays_per_step": alt_rays / K}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         trav_bytes, frame_bytes = algorithmic_bytes(tot)
-        ext_bytes = 48 * tot["rays_extend"] + 80 * tot["nodes"] + 48 * tot["tris"] + 64 * tot["insts"]   # shadow rays: none in this scene
-        achieved = ext_bytes / (stage["extend"] * 1e-3) / 1e9 if stage["extend"] > 0 else None
-        traffic = None
-        tj = ROOT / "profiles" / "r01_extend_traffic.json"     # dram__bytes_read+write per launch from the committed ncu capture
+        # dominant kernel = the persistent traversal (extend_kernel; shadow_kernel is the same code in any-hit mode and is
+        # included when the scene casts shadow rays): algorithmic bytes of every traced ray / sum of the launch durations
+        trav_ms = stage["extend"] + stage["shadow"]
+        achieved = trav_bytes / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        traffic, issue = None, None
+        tj = ROOT / "profiles" / "r02_extend_traffic.json"     # dram bytes per launch + issue-slot figures from the committed ncu capture
         if tj.exists():
             try:
-                traffic = float(json.loads(tj.read_text())["mean_dram_bytes_per_launch"])
+                tjd = json.loads(tj.read_text())
+                traffic = float(tjd["mean_dram_bytes_per_launch"]); issue = tjd.get("issue_slots")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "extend_kernel (BVH8 traversal + watertight test)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_extend_traffic.json)",
-                "algorithmic_bytes_per_launch": ext_bytes / max(1, n_ext), "peak_source": peak_src,
-                "algorithmic_bytes_per_ray": ext_bytes / max(1, tot["rays_extend"]), "avg_launch_ms": stage["extend"] / max(1, n_ext), "launches": n_ext,
+        n_trav = n_ext * (2 if tot["rays_shadow"] else 1)
+        roof = {"bound": "hbm", "kernel": "extend_kernel (persistent BVH8 traversal + watertight test)" + (" + shadow_kernel" if tot["rays_shadow"] else ""),
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r02_extend_traffic.json)",
+                "algorithmic_bytes_per_launch": trav_bytes / max(1, n_trav), "peak_source": peak_src,
+                "algorithmic_bytes_per_ray": trav_bytes / max(1, rays_rank), "avg_launch_ms": trav_ms / max(1, n_trav), "launches": n_trav,
                 "nodes_per_ray": tot["nodes"] / max(1, rays_rank), "tris_per_ray": tot["tris"] / max(1, rays_rank),
-                "timing": "kernel durations: CUDA events around each launch, one frame at a time (frames in flight = 1) over the same K frames; value/e2e: frames in flight overlapped",
+                "regimes": {"lone": "frac/achieved: CUDA events around each launch, one frame at a time (frames in flight = 1) over the same K frames",
+                            "overlapped_upper_bound_frac": trav_bytes / (ms * 1e-3) / 1e9 / peak,
+                            "overlapped": "traversal bytes / the whole timed region of `value` (frames in flight overlap traversal with shading): an upper bound for the kernel's share"},
+                "issue_slots": issue,
+                "note": "HBM is the roofline BASELINE.json names; the BVH is L2-resident, DRAM traffic is a small fraction of the algorithmic bytes and the kernel is bound by instruction issue (see issue_slots and DESIGN.md §4)",
                 "whole_frame_algorithmic_gbs": frame_bytes / (ms * 1e-3) / 1e9, "whole_frame_frac": frame_bytes / (ms * 1e-3) / 1e9 / peak,
+                "whole_frame_bytes_per_step": frame_bytes / K, "counters_per_step": {k: v / K for k, v in tot.items()},
                 "stage_ms_per_step": {k: v / K for k, v in stage.items()}}
         cpu = None
         if not args.no_cpu_baseline and world == 1:     # reported at N=1 only (torchrun pins OMP_NUM_THREADS=1)
@@ -474,17 +537,18 @@ def run_ours(args):
                 cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(desc) | {"parallelism": f"sample-pass sharding x{world} (frames g = step*{world}+rank), fused peer-memory reduce+tonemap at the end",
-                                                   "frames_in_flight": NF,
-                                                   "bvh": {"nodes": int(info.blas_nodes), "depth": int(info.max_depth_blas), "bytes": int(info.bytes), "build_s": build_s,
-                                                           "build_ms_device": float(info.build_ms), "tlas_ms_device": float(info.tlas_ms)}},
+                "config": workload_config(desc),      # identical keys / values in both arms
+                "engine": {"parallelism": f"sample-pass sharding x{world} (frames g = step*{world}+rank), fused peer-memory reduce+tonemap at the end",
+                           "frames_in_flight": NF,
+                           "bvh": {"nodes": int(info.blas_nodes), "depth": int(info.max_depth_blas), "bytes": int(info.bytes), "build_s": build_s,
+                                   "build_ms_device": float(info.build_ms), "tlas_ms_device": float(info.tlas_ms)}},
                 "samples_per_s": samples_all / (ms_max * 1e-3),
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 324 + (16384 if POSE is not None else 0), "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
                 "refit": ((upd | {"skinning_gbs": 256.0 * desc.n_vertices / (upd["skin_ms"] * 1e-3) / 1e9 if upd["skin_ms"] > 0 else None,
                                   "refit_algorithmic_gbs": (160.0 * info.blas_nodes + 36.0 * info.blas_tris) / (upd["refit_ms"] * 1e-3) / 1e9 if upd["refit_ms"] > 0 else None,
                                   "vertices": int(desc.n_vertices), "timing": "CUDA events per update stage, one frame at a time"}) if POSE is not None else None),
                 "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "alt_camera": alt,
                 "rays_per_step": rays_rank / K}
         print(json.dumps(line))
     if dist is not None:
@@ -500,10 +564,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene-versions", type=int, default=3, help="config 4: copies of the buffers a skin update rewrites (2..4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt-camera", action="store_true", help="skip the second (round-1 camera) figure of config 2")
+    ap.add_argument("--size", default=None, help="WxH override (experiments only; the headline size is 1920x1080)")
+    ap.add_argument("--camera-z", type=float, default=None, help="camera z override (experiments only)")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="frames whose path tracing may overlap on one GPU (1..4; reference: IN_FLIGHT_FRAMES = 2)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (default 2 = the headline workload)")
     args = ap.parse_args()
     select_config(args.config)
+    global WIDTH, HEIGHT, CAM_POS
+    if args.size:
+        WIDTH, HEIGHT = (int(x) for x in args.size.lower().split("x"))
+    if args.camera_z is not None:
+        CAM_POS = (CAM_POS[0], CAM_POS[1], float(args.camera_z))
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
         run_reference(args)

@@ -208,7 +208,10 @@ typedef struct rt_hit {
 } rt_hit;                   /* 24 B */
 
 enum {
-    RT_TRACE_OPAQUE = 1     /* gl_RayFlagsOpaqueEXT: never run the alpha test */
+    RT_TRACE_OPAQUE = 1,    /* gl_RayFlagsOpaqueEXT: never run the alpha test */
+    RT_TRACE_SCALAR = 2     /* cross-check path: one thread per ray, plain while-while loop.  Default (flag clear): the
+                               ray set runs through the persistent wavefront traversal of the frame kernels
+                               (dynamic fetch + warp-cooperative triangle rounds), i.e. the code rt_render times */
 };
 
 typedef struct rt_stats {
@@ -247,7 +250,8 @@ const char* rt_version(void);
    (app/src/lib.rs:305-325).  device = CUDA ordinal. */
 int rt_context_create(int device, uint32_t width, uint32_t height, rt_context** out);
 void rt_context_destroy(rt_context* ctx);
-/* replaces BaseApp::recreate_swapchain (app/src/lib.rs:355-385): drops the accumulation */
+/* replaces BaseApp::recreate_swapchain (app/src/lib.rs:355-385): drops the accumulation.  With unchanged dimensions the
+   images are cleared in place (allocations and peers' IPC mappings stay valid); a size change after rt_ipc_export fails. */
 int rt_frame_resize(rt_context* ctx, uint32_t width, uint32_t height);
 
 /* replaces InFlightFrames (app/src/lib.rs:34 IN_FLIGHT_FRAMES = 2, :329, :400-401 per-frame fence) and the

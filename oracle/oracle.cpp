@@ -205,7 +205,15 @@ struct Instance {
 
 }  // namespace
 
+// Test helper (SURVEY.md §8d ray set iv): while a recorder is attached, raygen() / castShadowRay() append every traced
+// segment of bounce >= min_bounce (and every shadow ray) together with the payload RNG state the any-hit stage would see.
+struct RayRecorder {
+    uint32_t min_bounce = 0; size_t max_rays = 0, max_shadow = 0;
+    std::vector<rt_ray> rays, shadow; std::vector<uint32_t> rng, shadow_rng;
+};
+
 struct orc_scene {
+    RayRecorder* rec = nullptr;
     std::vector<rt_vertex> vertices_in;   // as uploaded
     std::vector<rt_vertex> vertices;      // after skinning (what BLASes and shading read)
     std::vector<uint32_t> indices;
@@ -222,7 +230,7 @@ struct orc_scene {
     Bvh tlas;
     float srgb_lut[256];
     // statistics of the last render
-    std::atomic<uint64_t> rays_extend{0}, rays_shadow{0}, shaded{0};
+    mutable std::atomic<uint64_t> rays_extend{0}, rays_shadow{0}, shaded{0}, tex_taps{0}, light_cands{0};
 };
 
 namespace {
@@ -356,6 +364,7 @@ vec4 sample_image(const orc_scene& s, const Image& im, uint32_t filter, uint32_t
 }
 vec4 texture2d(const orc_scene& s, int tex_index, vec2 uv) {
     if (tex_index < 0 || (size_t)tex_index >= s.textures.size()) return V4(1, 1, 1, 1);
+    s.tex_taps.fetch_add(1, std::memory_order_relaxed);   // 16 B x 4 texels per tap
     const rt_texture_desc& t = s.textures[tex_index];
     const Image& im = s.images[t.image_index];
     const rt_sampler_desc& sm = s.samplers[t.sampler_index];
@@ -789,6 +798,11 @@ void miss_shader(const orc_scene& s, const rt_ubo& ubo, vec3 worldRayDirection, 
 bool castShadowRay(orc_scene& s, const rt_ubo& ubo, vec3 hitPosition, vec3 directionToLight, float tmax, const RayPayload& Ray) {
     TraceCtx c; c.ray_opaque = ubo.fully_opaque != 0; c.terminate_first = true; c.rng = Ray.rngState;
     s.rays_shadow.fetch_add(1, std::memory_order_relaxed);
+    if (s.rec && s.rec->shadow.size() < s.rec->max_shadow) {
+        rt_ray r = {{hitPosition.x, hitPosition.y, hitPosition.z}, 0.1f, {directionToLight.x, directionToLight.y, directionToLight.z}, tmax};
+        s.rec->shadow.push_back(r);
+        for (uint32_t v : {c.rng.x, c.rng.y, c.rng.z, c.rng.w}) s.rec->shadow_rng.push_back(v);
+    }
     Hit h = trace(s, hitPosition, directionToLight, 0.1f, tmax, c);
     return !h.valid;
 }
@@ -801,6 +815,7 @@ bool sampleLightRIS(const orc_scene& s, uvec4& rngState, vec3 hitPosition, vec3 
     uint32_t candidates_num = std::min(light_num, 3u);
     for (uint32_t i = 0; i < candidates_num; i++) {
         if (luminance(ld3(s.plights[i].color) * s.plights[i].intensity) < 0.1f) continue;
+        s.light_cands.fetch_add(1, std::memory_order_relaxed);
         uint32_t randomLightIndex = std::min(light_num - 1, (uint32_t)(rnd(rngState) * (float)light_num));
         const rt_light& candidate = s.plights[randomLightIndex];
         float candidateWeight = (float)light_num;
@@ -1103,6 +1118,11 @@ void raygen(orc_scene& s, const rt_ubo& ubo, uint32_t px, uint32_t py, uint32_t 
         Ray.volume_dis = -1.0f;
         for (uint32_t b = 0; b < ubo.number_of_bounces; b++) {
             TraceCtx c; c.ray_opaque = ubo.fully_opaque != 0; c.terminate_first = false; c.rng = Ray.rngState;
+            if (s.rec && b >= s.rec->min_bounce && s.rec->rays.size() < s.rec->max_rays) {
+                rt_ray r = {{origin.x, origin.y, origin.z}, tMin, {direction.x, direction.y, direction.z}, tFar};
+                s.rec->rays.push_back(r);
+                for (uint32_t v : {c.rng.x, c.rng.y, c.rng.z, c.rng.w}) s.rec->rng.push_back(v);
+            }
             Hit h = trace(s, xyz(origin), xyz(direction), tMin, tFar, c);
             s.rays_extend.fetch_add(1, std::memory_order_relaxed); n_traces++;
             if (h.valid) { s.shaded.fetch_add(1, std::memory_order_relaxed); closest_hit(s, ubo, h, xyz(direction), Ray); }
@@ -1361,7 +1381,7 @@ int orc_render(orc_scene* s, const rt_ubo* ubo, uint32_t W, uint32_t H, float* a
     if (row1 > H) row1 = H;
     if (row0 > row1) row0 = row1;
     if (ubo->total_number_of_samples == 0) return fail("total_number_of_samples must be > 0");
-    s->rays_extend = 0; s->rays_shadow = 0; s->shaded = 0;
+    s->rays_extend = 0; s->rays_shadow = 0; s->shaded = 0; s->tex_taps = 0; s->light_cands = 0;
     auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(dynamic, 1)
     for (long long y = row0; y < (long long)row1; ++y)
@@ -1371,8 +1391,31 @@ int orc_render(orc_scene* s, const rt_ubo* ubo, uint32_t W, uint32_t H, float* a
         std::memset(stats, 0, sizeof *stats);
         stats->ms_total = std::chrono::duration<float, std::milli>(t1 - t0).count();
         stats->rays_extend = s->rays_extend; stats->rays_shadow = s->rays_shadow; stats->shaded_hits = s->shaded;
+        stats->tex_taps = s->tex_taps; stats->light_cands = s->light_cands;
         stats->pixel_samples = (uint64_t)(row1 - row0) * W * ubo->number_of_samples;
     }
+    return 0;
+}
+
+// SURVEY.md §8d ray set (iv): the rays the path tracer itself generates at bounce >= min_bounce (incoherent, starting ON
+// surfaces with tMin = 0.001, lib/Camera.glsl:2-3) and its shadow rays (tMin = 0.1, RayTracing.rchit:43) for one frame,
+// sampled every `stride` pixels in scan order (single-threaded: deterministic order).
+int orc_record_bounce_rays(orc_scene* s, const rt_ubo* ubo, uint32_t W, uint32_t H, uint32_t stride, uint32_t min_bounce,
+                           rt_ray* rays, uint32_t* rng4, uint32_t max_rays, rt_ray* srays, uint32_t* srng4, uint32_t max_shadow,
+                           uint32_t* n_rays, uint32_t* n_shadow) {
+    if (!s || !ubo || !n_rays || !n_shadow) return fail("orc_record_bounce_rays: null argument");
+    if (ubo->total_number_of_samples == 0) return fail("total_number_of_samples must be > 0");
+    if (!stride) stride = 1;
+    RayRecorder rec; rec.min_bounce = min_bounce; rec.max_rays = rays ? max_rays : 0; rec.max_shadow = srays ? max_shadow : 0;
+    std::vector<float> acc((size_t)W * H * 4, 0.0f); std::vector<uint8_t> out((size_t)W * H * 4);
+    s->rec = &rec;
+    for (uint64_t p = 0; p < (uint64_t)W * H && (rec.rays.size() < rec.max_rays || rec.shadow.size() < rec.max_shadow); p += stride) {
+        raygen(*s, *ubo, (uint32_t)(p % W), (uint32_t)(p / W), W, H, acc.data(), out.data());
+    }
+    s->rec = nullptr;
+    *n_rays = (uint32_t)rec.rays.size(); *n_shadow = (uint32_t)rec.shadow.size();
+    if (*n_rays) { std::memcpy(rays, rec.rays.data(), rec.rays.size() * sizeof(rt_ray)); if (rng4) std::memcpy(rng4, rec.rng.data(), rec.rng.size() * 4); }
+    if (*n_shadow) { std::memcpy(srays, rec.shadow.data(), rec.shadow.size() * sizeof(rt_ray)); if (srng4) std::memcpy(srng4, rec.shadow_rng.data(), rec.shadow_rng.size() * 4); }
     return 0;
 }
 

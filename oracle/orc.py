@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
         l.orc_trace_any.argtypes = [vp, C.POINTER(F.rt_ray), F.c_u32, F.c_u32, C.POINTER(F.c_u32), F.c_u8p]
         l.orc_render.argtypes = [vp, C.POINTER(F.rt_ubo), F.c_u32, F.c_u32, C.POINTER(F.c_f), F.c_u8p, F.c_u32, F.c_u32,
                                  C.POINTER(F.rt_stats)]
+        l.orc_record_bounce_rays.argtypes = [vp, C.POINTER(F.rt_ubo), F.c_u32, F.c_u32, F.c_u32, F.c_u32, C.POINTER(F.rt_ray), C.POINTER(F.c_u32), F.c_u32,
+                                             C.POINTER(F.rt_ray), C.POINTER(F.c_u32), F.c_u32, C.POINTER(F.c_u32), C.POINTER(F.c_u32)]
         l.orc_trace_pixel.argtypes = [vp, C.POINTER(F.rt_ubo), F.c_u32, F.c_u32, F.c_u32, F.c_u32, C.POINTER(F.c_f), F.c_u32]
         l.orc_tea.argtypes = [F.c_u32, F.c_u32]
         l.orc_tea.restype = F.c_u32
@@ -115,6 +117,17 @@ class OracleScene:
                               r0, r1, C.byref(st)):
             raise OracleError(self._l.orc_last_error().decode())
         return acc, out, st
+
+    def record_bounce_rays(self, ubo: F.rt_ubo, width: int, height: int, stride: int = 1, min_bounce: int = 1, max_rays: int = 1 << 20,
+                           max_shadow: int = 1 << 18):
+        """SURVEY.md §8d ray set (iv): (rays, rng4, shadow_rays, shadow_rng4) the oracle's own path tracer generates for this frame."""
+        rays = np.zeros(max_rays, F.RAY_DTYPE); rng4 = np.zeros((max_rays, 4), np.uint32)
+        srays = np.zeros(max_shadow, F.RAY_DTYPE); srng4 = np.zeros((max_shadow, 4), np.uint32)
+        n, ns = F.c_u32(), F.c_u32()
+        if self._l.orc_record_bounce_rays(self._h, C.byref(ubo), width, height, stride, min_bounce, F.as_ptr(rays, F.rt_ray), F.as_ptr(rng4, F.c_u32), max_rays,
+                                          F.as_ptr(srays, F.rt_ray), F.as_ptr(srng4, F.c_u32), max_shadow, C.byref(n), C.byref(ns)):
+            raise OracleError(self._l.orc_last_error().decode())
+        return rays[:n.value].copy(), rng4[:n.value].copy(), srays[:ns.value].copy(), srng4[:ns.value].copy()
 
     def trace_pixel(self, ubo: F.rt_ubo, width: int, height: int, x: int, y: int, max_records: int = 16) -> np.ndarray:
         rec = np.zeros((max_records, 16), np.float32)

@@ -5,7 +5,7 @@
 #include <cub/device/device_scan.cuh>
 
 int g_rt_sm_count = 148;
-unsigned long long g_rt_launch_count = 0;
+std::atomic<unsigned long long> g_rt_launch_count{0};
 static thread_local cudaError_t g_last_cuda = cudaSuccess;
 
 static int chk(cudaError_t e) { if (e != cudaSuccess) { g_last_cuda = e; return 1; } return 0; }
@@ -18,32 +18,33 @@ int rt_d2d(void* d, const void* s_, size_t n, rt_stream_t s) { return chk(cudaMe
 int rt_memset(void* d, int v, size_t n, rt_stream_t s) { return chk(cudaMemsetAsync(d, v, n, s)); }
 int rt_stream_sync(rt_stream_t s) { return chk(cudaStreamSynchronize(s)); }
 
-static void* g_sort_tmp = nullptr; static size_t g_sort_tmp_bytes = 0;
-int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, size_t n, rt_stream_t s) {
+// cub temporary storage is owned by the caller (BuildScratch of the scene being built): it lives on that scene's device and
+// is only touched by work queued on that scene's stream.
+static int grow_tmp(void** tmp, size_t* tmp_bytes, size_t need, rt_stream_t s) {
+    if (need <= *tmp_bytes) return 0;
+    if (*tmp) { cudaStreamSynchronize(s); cudaFree(*tmp); *tmp = nullptr; *tmp_bytes = 0; }
+    const size_t cap = need + need / 4 + 256;
+    if (chk(cudaMalloc(tmp, cap))) { *tmp = nullptr; return 1; }
+    *tmp_bytes = cap;
+    return 0;
+}
+int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, size_t n, void** tmp, size_t* tmp_bytes, rt_stream_t s) {
     size_t need = 0;
     if (chk(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys_tmp, vals, vals_tmp, (int)n, 0, 63, s))) return 1;
-    if (need > g_sort_tmp_bytes) {
-        if (g_sort_tmp) { cudaStreamSynchronize(s); cudaFree(g_sort_tmp); }
-        g_sort_tmp_bytes = need + need / 4 + 256;
-        if (chk(cudaMalloc(&g_sort_tmp, g_sort_tmp_bytes))) { g_sort_tmp = nullptr; g_sort_tmp_bytes = 0; return 1; }
-    }
-    size_t bytes = g_sort_tmp_bytes;
-    if (chk(cub::DeviceRadixSort::SortPairs(g_sort_tmp, bytes, keys, keys_tmp, vals, vals_tmp, (int)n, 0, 63, s))) return 1;
+    if (grow_tmp(tmp, tmp_bytes, need, s)) return 1;
+    size_t bytes = *tmp_bytes;
+    if (chk(cub::DeviceRadixSort::SortPairs(*tmp, bytes, keys, keys_tmp, vals, vals_tmp, (int)n, 0, 63, s))) return 1;
     g_rt_launch_count += 4;
     if (rt_d2d(keys, keys_tmp, n * 8, s)) return 1;
     return rt_d2d(vals, vals_tmp, n * 4, s);
 }
 
-int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, rt_stream_t s) {
+int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void** tmp, size_t* tmp_bytes, rt_stream_t s) {
     size_t need = 0;
     if (chk(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, s))) return 1;
-    if (need > g_sort_tmp_bytes) {
-        if (g_sort_tmp) { cudaStreamSynchronize(s); cudaFree(g_sort_tmp); }
-        g_sort_tmp_bytes = need + need / 4 + 256;
-        if (chk(cudaMalloc(&g_sort_tmp, g_sort_tmp_bytes))) { g_sort_tmp = nullptr; g_sort_tmp_bytes = 0; return 1; }
-    }
-    size_t bytes = g_sort_tmp_bytes;
-    if (chk(cub::DeviceScan::ExclusiveSum(g_sort_tmp, bytes, in, out, (int)n, s))) return 1;
+    if (grow_tmp(tmp, tmp_bytes, need, s)) return 1;
+    size_t bytes = *tmp_bytes;
+    if (chk(cub::DeviceScan::ExclusiveSum(*tmp, bytes, in, out, (int)n, s))) return 1;
     g_rt_launch_count += 1;
     return 0;
 }
@@ -81,6 +82,7 @@ int rt_ipc_export(rt_context* c, void* handle64) {
     cudaIpcMemHandle_t h;
     if (chk(cudaIpcGetMemHandle(&h, c->acc))) return fail(std::string("rt_ipc_export: ") + rt_platform_error());
     memcpy(handle64, &h, 64);
+    c->ipc_exported = true;
     return 0;
 }
 int rt_ipc_open(rt_context* c, const void* handle64, void** peer_acc) {

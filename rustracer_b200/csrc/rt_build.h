@@ -45,6 +45,7 @@ struct BuildScratch {
     uint32_t* bounds = nullptr;       // 6 ordered-uint centroid bounds
     uint2 *q_a = nullptr, *q_b = nullptr;   // collapse work queues: (binary node, wide node)
     uint32_t* counters = nullptr;     // [0] wide nodes, [1] primitives emitted, [2] next queue size
+    void* lib_tmp = nullptr; size_t lib_tmp_bytes = 0;   // radix sort / scan temporary storage: per scene (device + stream of its context)
 };
 
 inline int scratch_reserve(BuildScratch& s, size_t n) {
@@ -72,6 +73,8 @@ inline void scratch_free(BuildScratch& s) {
                      (void**)&s.bin_box, (void**)&s.bin_range, (void**)&s.flags, (void**)&s.bounds, (void**)&s.q_a, (void**)&s.q_b, (void**)&s.counters,
                      (void**)&s.bin_count, (void**)&s.cl_a, (void**)&s.cl_b, (void**)&s.nn, (void**)&s.valid, (void**)&s.pos};
     for (void** p : ptrs) { if (*p) rt_free(*p); *p = nullptr; }
+    if (s.lib_tmp) rt_free(s.lib_tmp);
+    s.lib_tmp = nullptr; s.lib_tmp_bytes = 0;
     s.capacity = 0;
 }
 
@@ -359,7 +362,7 @@ inline int ploc_build(const DAabb* prim_boxes, int n, BuildScratch& sc, rt_strea
                 const uint32_t j = nn[i];
                 valid[i] = (nn[j] == (uint32_t)i && j < (uint32_t)i) ? 0u : 1u;   // the higher half of a pair is absorbed
             });
-            if (rt_exclusive_scan_u32(valid, pos, c_ub, stream)) return 1;
+            if (rt_exclusive_scan_u32(valid, pos, c_ub, &sc.lib_tmp, &sc.lib_tmp_bytes, stream)) return 1;
             rt_launch(c_ub, stream, RT_LAMBDA(size_t i) {
                 const uint32_t ci = cur[0], merged_before = cur[1];
                 if (ci <= 1u) { if (i == 0) { nxt[0] = ci; nxt[1] = merged_before; co[0] = cl[0]; } return; }
@@ -429,7 +432,7 @@ inline int build_wide_bvh(const DAabb* prim_boxes, uint32_t n, BuildScratch& sc,
         keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
         vals[i] = (uint32_t)i;
     });
-    if (rt_sort_pairs_u64(sc.keys, sc.vals, sc.keys_tmp, sc.vals_tmp, n, stream)) return 1;
+    if (rt_sort_pairs_u64(sc.keys, sc.vals, sc.keys_tmp, sc.vals_tmp, n, &sc.lib_tmp, &sc.lib_tmp_bytes, stream)) return 1;
     int2* bin_children = sc.bin_children; uint32_t* bin_parent = sc.bin_parent; uint2* bin_range = sc.bin_range;
     DAabb* bin_box = sc.bin_box; uint32_t* flags = sc.flags; uint32_t* bin_count = sc.bin_count;
     const int ni = (int)n;

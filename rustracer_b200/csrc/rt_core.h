@@ -73,7 +73,7 @@ struct FrameSlot {
     DQueue q[2]{};
     DHits hits{};
     DShadowQueue sq{};
-    uint32_t* counters = nullptr; size_t counters_cap = 0;   // qcount | scount | fetch_extend | fetch_shadow
+    uint32_t* counters = nullptr; size_t counters_cap = 0;   // qcount | scount | fetch_extend | fetch_shadow | shaded hits
     RtCounters* dev_cnt = nullptr;
     // last frame rendered on this slot
     uint32_t last_S = 0, last_B = 0; uint64_t last_pixels = 0; bool last_counted = false; bool last_valid = false;
@@ -99,6 +99,7 @@ struct rt_context {
     rt_event ticket_done[RT_TICKET_RING];
     bool timers = false;
     std::vector<void*> ipc_opened;
+    bool ipc_exported = false;          // rt_ipc_export handed out a handle of `acc`: it must not be re-allocated
 };
 
 // One BLAS: either a geometry's own object-space BLAS (needed only when a non-baked instance references it) or the
@@ -564,11 +565,12 @@ static void launch_shadow(FrameSlot* c, const DScene& S, const FrameParams& P, c
 }
 template <bool SIMPLE, bool COUNT>
 static void launch_shade(FrameSlot* c, const DScene& S, const FrameParams& P, const DQueue& qin, const DQueue& qout, const uint32_t* count, uint32_t* out_count,
-                         uint32_t* shadow_count, uint32_t bounce, rt_stream_t st) {
+                         uint32_t* shadow_count, uint32_t* hit_count, uint32_t bounce, rt_stream_t st) {
 #ifdef RT_EMU
     const uint32_t n = *count;
     for (uint32_t i = 0; i < n; ++i) {
         ShadeResult r = shade_item<SIMPLE, COUNT>(S, P, c->fb, qin, c->hits, i, bounce, c->dev_cnt);
+        if (r.hit) ++*hit_count;
         if (r.alive) store_path(qout, (*out_count)++, r.next);
         if (r.has_shadow) {
             const uint32_t k = (*shadow_count)++;
@@ -579,7 +581,7 @@ static void launch_shade(FrameSlot* c, const DScene& S, const FrameParams& P, co
     }
     (void)st;
 #else
-    shade_kernel<SIMPLE, COUNT><<<persistent_grid(8), 128, 0, st>>>(S, P, c->fb, qin, c->hits, qout, c->sq, count, out_count, shadow_count, bounce, c->dev_cnt);
+    shade_kernel<SIMPLE, COUNT><<<persistent_grid(8), 128, 0, st>>>(S, P, c->fb, qin, c->hits, qout, c->sq, count, out_count, shadow_count, hit_count, bounce, c->dev_cnt);
     ++g_rt_launch_count;
 #endif
 }
@@ -590,13 +592,13 @@ static int render_frame(rt_context* ctx, FrameSlot* c, rt_scene* s, const FrameP
     const uint32_t S = P.ubo.number_of_samples, B = P.ubo.number_of_bounces;
     const uint32_t n_local = owned_rows(tp) * tp.width;
     const size_t per = (size_t)(S ? S : 1) * (B + 1);
-    if (per * 4 > c->counters_cap) {
+    if (per * 5 > c->counters_cap) {
         if (c->counters) rt_free(c->counters);
-        c->counters_cap = per * 4 + 64;
+        c->counters_cap = per * 5 + 64;
         RT_CHECK(dev_alloc(&c->counters, c->counters_cap), "counter allocation");
     }
-    uint32_t* qcount = c->counters; uint32_t* scount = c->counters + per; uint32_t* fetch_e = c->counters + 2 * per; uint32_t* fetch_s = c->counters + 3 * per;
-    rt_memset(c->counters, 0, per * 4 * sizeof(uint32_t), st);
+    uint32_t* qcount = c->counters; uint32_t* scount = c->counters + per; uint32_t* fetch_e = c->counters + 2 * per; uint32_t* fetch_s = c->counters + 3 * per; uint32_t* hcount = c->counters + 4 * per;
+    rt_memset(c->counters, 0, per * 5 * sizeof(uint32_t), st);
     if (COUNT) rt_memset(c->dev_cnt, 0, sizeof(RtCounters), st);
     const bool timing = (flags & 4u) != 0;
     c->stage_used = 0;
@@ -618,8 +620,8 @@ static int render_frame(rt_context* ctx, FrameSlot* c, rt_scene* s, const FrameP
             launch_extend<ALPHA, COUNT>(c, DS, P, qin, qcount + idx, fetch_e + idx, n_local, st);
             stage_end(ev, st);
             ev = stage_begin(c, timing, 2, st);
-            if (simple) launch_shade<true, COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, b, st);
-            else launch_shade<false, COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, b, st);
+            if (simple) launch_shade<true, COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, hcount + idx, b, st);
+            else launch_shade<false, COUNT>(c, DS, P, qin, qout, qcount + idx, qcount + idx + 1, scount + idx, hcount + idx, b, st);
             stage_end(ev, st);
             if (s->has_nee) {
                 ev = stage_begin(c, timing, 3, st);
@@ -704,7 +706,24 @@ void RT_API(rt_context_destroy)(rt_context* c) {
 
 int RT_API(rt_frame_resize)(rt_context* c, uint32_t width, uint32_t height) {
     if (!c || !width || !height) return fail("rt_frame_resize: bad arguments");
+#ifndef RT_EMU
+    cudaSetDevice(c->device);
+#endif
     sync_all(c);
+    if (width == c->width && height == c->height && c->acc) {
+        // same size: drop the accumulation in place.  The allocation (and with it any CUDA IPC mapping a peer holds on the
+        // accumulation image, rt_ipc_export) stays valid.
+        const size_t n = (size_t)width * height;
+        rt_memset(c->acc, 0, n * sizeof(float4), c->stream);
+        for (uint32_t k = 0; k < c->n_slots; ++k) {
+            FrameSlot& f = c->slot[k];
+            rt_memset(f.fb.out, 0, n * 4, c->stream); rt_memset(f.fb.rad, 0, n * sizeof(float4), c->stream); rt_memset(f.fb.aux, 0, n * sizeof(float2), c->stream);
+            f.last_valid = false; f.pending = false;
+        }
+        c->cur = 0; c->acc_pending = false; c->consumer_pending = false;
+        return rt_stream_sync(c->stream) ? fail(std::string("rt_frame_resize: ") + rt_platform_error()) : 0;
+    }
+    if (c->ipc_exported) return fail("rt_frame_resize: the accumulation image is exported to peers (rt_ipc_export); a size change would free memory they have mapped");
     if (alloc_frame(c, width, height)) return fail(std::string("rt_frame_resize: allocation failed: ") + rt_platform_error());
     return 0;
 }
@@ -912,9 +931,10 @@ int RT_API(rt_scene_update_instances)(rt_scene* s, const rt_instance* inst, uint
 }
 
 // stage timers of the last skin update are read on demand (rt_scene_bvh_info): the update itself never blocks the host
-static void collect_update_timers(rt_scene* s) {
+static void collect_update_timers(rt_scene* s, bool block = true) {
     if (!s->upd_timers_pending) return;
-    rt_stream_sync(s->ctx->stream);
+    if (!block && !s->upd_t[3].ready()) return;   // the previous update is still running: its timings are simply dropped
+    if (block) rt_stream_sync(s->ctx->stream);
     s->skin_ms = rt_timer_ms(s->upd_t[0], s->upd_t[1]); s->refit_ms = rt_timer_ms(s->upd_t[1], s->upd_t[2]); s->tlas_ms = rt_timer_ms(s->upd_t[2], s->upd_t[3]);
     s->upd_timers_pending = false;
 }
@@ -940,7 +960,7 @@ int RT_API(rt_scene_update_skins)(rt_scene* s, const float* mats, uint32_t n_ski
         use_version(s, next);
     }
     if (!s->upd_timers_created) { for (auto& t : s->upd_t) t.create(); s->ev_updated.create(); s->upd_timers_created = true; }
-    collect_update_timers(s);     // (the events are about to be re-recorded)
+    collect_update_timers(s, false);     // (the events are about to be re-recorded; never blocks the host)
     RT_CHECK(rt_h2d(s->d_skins, mats, (size_t)n_skins * RT_MAX_JOINTS * 16 * 4, st), "skin upload");
     s->upd_t[0].record(st);
     run_skinning(s);
@@ -1134,11 +1154,11 @@ int RT_API(rt_last_frame_stats)(rt_context* c, rt_stats* o) {
     if (!f->last_valid) return fail("rt_last_frame_stats: no frame rendered yet");
     if (sync_all(c)) return fail(std::string("rt_last_frame_stats: ") + rt_platform_error());
     const size_t per = (size_t)(f->last_S ? f->last_S : 1) * (f->last_B + 1);
-    std::vector<uint32_t> h(per * 2);
-    RT_CHECK(rt_d2h(h.data(), f->counters, per * 2 * 4, c->stream), "rt_last_frame_stats");
+    std::vector<uint32_t> h(per * 5);
+    RT_CHECK(rt_d2h(h.data(), f->counters, per * 5 * 4, c->stream), "rt_last_frame_stats");
     rt_stream_sync(c->stream);
     for (uint32_t smp = 0; smp < f->last_S; ++smp)
-        for (uint32_t b = 0; b < f->last_B; ++b) { o->rays_extend += h[(size_t)smp * (f->last_B + 1) + b]; o->rays_shadow += h[per + (size_t)smp * (f->last_B + 1) + b]; }
+        for (uint32_t b = 0; b < f->last_B; ++b) { o->rays_extend += h[(size_t)smp * (f->last_B + 1) + b]; o->rays_shadow += h[per + (size_t)smp * (f->last_B + 1) + b]; o->shaded_hits += h[4 * per + (size_t)smp * (f->last_B + 1) + b]; }
     o->pixel_samples = f->last_pixels;
     if (f->last_counted) {
         RtCounters k; RT_CHECK(rt_d2h(&k, f->dev_cnt, sizeof k, c->stream), "rt_last_frame_stats"); rt_stream_sync(c->stream);
@@ -1150,9 +1170,6 @@ int RT_API(rt_last_frame_stats)(rt_context* c, rt_stats* o) {
         switch (e.stage) { case 0: o->ms_raygen += ms; break; case 1: o->ms_extend += ms; o->n_extend_launches++; break; case 2: o->ms_shade += ms; break; case 3: o->ms_shadow += ms; break; default: o->ms_accum += ms; }
     }
     o->n_kernel_launches = (uint32_t)(f->launches_after - f->launches_before);
-    // shaded hits = extend rays that hit something = rays_extend - misses; approximated by the next-queue inputs is wrong
-    // (terminated paths also shade), so report the number of shade invocations
-    o->shaded_hits = o->rays_extend;
     return 0;
 }
 
@@ -1184,9 +1201,22 @@ static int trace_common(rt_scene* s, const rt_ray* rays, uint32_t n, uint32_t fl
         }
     }
 #else
-    const unsigned grid = persistent_grid(8);
-    if (alpha) trace_rays_kernel<true, false><<<grid, 128, 0, st>>>(DS, d_rays, n, d_rng, d_hits, d_occ, nullptr);
-    else trace_rays_kernel<false, false><<<grid, 128, 0, st>>>(DS, d_rays, n, d_rng, d_hits, d_occ, nullptr);
+    if (flags & RT_TRACE_SCALAR) {      // one thread per ray, plain while-while loop (cross-check of the wavefront path)
+        const unsigned grid = persistent_grid(8);
+        if (alpha) trace_rays_kernel<true, false><<<grid, 128, 0, st>>>(DS, d_rays, n, d_rng, d_hits, d_occ, nullptr);
+        else trace_rays_kernel<false, false><<<grid, 128, 0, st>>>(DS, d_rays, n, d_rng, d_hits, d_occ, nullptr);
+    } else {                            // the persistent traversal the frame kernels run
+        uint32_t* d_fetch = nullptr;
+        if (dev_alloc(&d_fetch, 1)) { rt_free(d_rays); rt_free(d_rng); rt_free(d_hits); rt_free(d_occ); return fail(std::string("rt_trace: allocation failed: ") + rt_platform_error()); }
+        rt_memset(d_fetch, 0, 4, st);
+        const unsigned grid = trace_grid();
+#define RT_TW(MODE, A, SG) trace_wavefront_kernel<MODE, A, SG><<<grid, RT_EXTEND_THREADS, 0, st>>>(DS, d_rays, n, d_rng, d_hits, d_occ, d_fetch)
+        const bool single = DS.single_merged != 0u;
+        if (d_occ) { if (alpha) { if (single) RT_TW(RT_MODE_ANY, true, true); else RT_TW(RT_MODE_ANY, true, false); } else { if (single) RT_TW(RT_MODE_ANY, false, true); else RT_TW(RT_MODE_ANY, false, false); } }
+        else { if (alpha) { if (single) RT_TW(RT_MODE_CLOSEST, true, true); else RT_TW(RT_MODE_CLOSEST, true, false); } else { if (single) RT_TW(RT_MODE_CLOSEST, false, true); else RT_TW(RT_MODE_CLOSEST, false, false); } }
+#undef RT_TW
+        rt_stream_sync(st); rt_free(d_fetch);
+    }
     ++g_rt_launch_count;
 #endif
     if (hits) e = rt_d2h(hits, d_hits, (size_t)n * sizeof(rt_hit), st); else e = rt_d2h(occ, d_occ, n, st);

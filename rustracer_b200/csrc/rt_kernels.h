@@ -65,7 +65,7 @@ RT_D void extend_item(const DScene& S, const FrameParams& P, const DQueue& q, co
 }
 
 // returns true when the path continues; slot allocation is done by the caller (warp-aggregated on the GPU)
-struct ShadeResult { bool alive; PathState next; bool has_shadow; ShadowRay shadow; };
+struct ShadeResult { bool alive; PathState next; bool has_shadow; ShadowRay shadow; bool hit; };
 
 template <bool SIMPLE, bool COUNT>
 RT_D ShadeResult shade_item(const DScene& S, const FrameParams& P, const FrameBuffers& fb, const DQueue& q, const DHits& hits,
@@ -75,9 +75,9 @@ RT_D ShadeResult shade_item(const DScene& S, const FrameParams& P, const FrameBu
     RtHit h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.prim = rt_float_as_uint(hv.w); h.inst = hits.inst[i];
     ShadeOut so;
     if (h.t < 0.0f) shade_miss(S, P, st.dir, bounce == 0, so, cnt);
-    else shade_hit<SIMPLE>(S, P, h, st, so, cnt);
+    else shade_hit<SIMPLE, COUNT>(S, P, h, st, so, cnt);
 
-    ShadeResult r; r.alive = false; r.has_shadow = so.has_shadow;
+    ShadeResult r; r.alive = false; r.has_shadow = so.has_shadow; r.hit = !(h.t < 0.0f);
     if (so.has_shadow) { r.shadow = so.shadow; r.shadow.contrib = so.shadow.contrib * st.throughput; }
     // RayTracing.rgen:94-129
     const f3 add = st.throughput * so.emittance;
@@ -311,7 +311,7 @@ RT_D void coop_round(Trav& tv, const DScene& S, CoopShared<ALPHA>& sh, uint32_t 
             if (alpha) {
                 if (COUNT) c4[3]++;
                 u4 rng; rng.x = sh.rng[0][owner]; rng.y = sh.rng[1][owner]; rng.z = sh.rng[2][owner]; rng.w = sh.rng[3][owner];
-                if (anyhit_ignore(S, inst, prim, geo, bu, bv, rng)) hit = false;
+                if (anyhit_ignore(S, inst, prim, geo, bu, bv, rng, COUNT ? c4 + 4 : nullptr)) hit = false;
             }
         }
         if (hit) { key = ((unsigned long long)float_to_ordered(tt) << 32) | rt_float_as_uint(c.w); atomicMin(&sh.best_ip[owner], key); }
@@ -345,7 +345,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint2 stack[RT_STACK_SIZE];
-    unsigned long long c4[4] = {0, 0, 0, 0};
+    unsigned long long c4[5] = {0, 0, 0, 0, 0};
     Trav tv;
     tv.tgroup = make_uint2(0u, 0u); tv.ngroup = make_uint2(0u, 0u); tv.sp = 0; tv.blas_sp = -1; tv.found = false;
     bool active = false, exhausted = false;
@@ -477,7 +477,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
     }
 #endif
     if (COUNT && cnt) {
-        atomicAdd(&cnt->nodes, c4[0]); atomicAdd(&cnt->tris, c4[1]); atomicAdd(&cnt->insts, c4[2]); atomicAdd(&cnt->anyhits, c4[3]);
+        atomicAdd(&cnt->nodes, c4[0]); atomicAdd(&cnt->tris, c4[1]); atomicAdd(&cnt->insts, c4[2]); atomicAdd(&cnt->anyhits, c4[3]); atomicAdd(&cnt->tex_taps, c4[4]);
     }
 }
 
@@ -528,7 +528,7 @@ RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" :
 #endif
 template <bool SIMPLE, bool COUNT>
 __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
-                                                    const uint32_t* count_ptr, uint32_t* out_count, uint32_t* shadow_count, uint32_t bounce, RtCounters* cnt) {
+                                                    const uint32_t* count_ptr, uint32_t* out_count, uint32_t* shadow_count, uint32_t* hit_count, uint32_t bounce, RtCounters* cnt) {
     const uint32_t count = *count_ptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -544,8 +544,12 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
             }
         }
 #endif
-        ShadeResult r; r.alive = false; r.has_shadow = false;
+        ShadeResult r; r.alive = false; r.has_shadow = false; r.hit = false;
         if (i < count) r = shade_item<SIMPLE, COUNT>(S, P, fb, qin, hits, i, bounce, cnt);
+        {   // closest hits actually shaded (rt_stats::shaded_hits; misses run the miss stage only)
+            const uint32_t hit_mask = __ballot_sync(0xFFFFFFFFu, r.hit);
+            if (hit_mask && lane == 0) atomicAdd(hit_count, (uint32_t)__popc(hit_mask));
+        }
         const uint32_t alive_mask = __ballot_sync(0xFFFFFFFFu, r.alive);
         if (alive_mask) {
             uint32_t slot0 = 0;
@@ -566,6 +570,28 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
             }
         }
     }
+}
+
+// rt_trace_closest / rt_trace_any (default path): the caller's ray set goes through the SAME persistent traversal as the
+// frame kernels above (persistent_trace + coop_round: dynamic fetch, deferred warp-cooperative triangle rounds, 64-bit
+// atomicMin tie-break, SINGLE specialisation) — only the ray source and the hit sink differ from extend_kernel /
+// shadow_kernel, so per-ray ID parity is established on the code the bench times.
+template <int MODE, bool ALPHA, bool SINGLE>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOCKS_SINGLE : RT_EXTEND_MIN_BLOCKS) trace_wavefront_kernel(DScene S, const rt_ray* rays, uint32_t n, const uint32_t* rng4, rt_hit* hits, uint8_t* occluded, uint32_t* fetch) {
+    persistent_trace<MODE, ALPHA, false, SINGLE>(S, n, fetch, nullptr,
+        [&](uint32_t i, Trav& tv) {
+            const float4 a = rt_ld(reinterpret_cast<const float4*>(rays + i)), b = rt_ld(reinterpret_cast<const float4*>(rays + i) + 1);
+            u4 rng; rng.x = rng.y = rng.z = rng.w = 0;
+            if (ALPHA && rng4) { const uint4 r = rt_ld(reinterpret_cast<const uint4*>(rng4) + i); rng.x = r.x; rng.y = r.y; rng.z = r.z; rng.w = r.w; }
+            trav_init<SINGLE>(tv, S, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w, rng);
+        },
+        [&](uint32_t i, const Trav& tv) {
+            if (MODE == RT_MODE_ANY) { occluded[i] = tv.found ? 1 : 0; return; }
+            rt_hit o;
+            if (tv.found) { o.t = tv.hit.t; o.u = tv.hit.u; o.v = tv.hit.v; o.instance_id = tv.hit.inst; o.primitive_id = tv.hit.prim; o.geo_id = rt_float_as_uint(S.inst_w2o[(size_t)tv.hit.inst * RT_INST_F4 + 3].y); }
+            else { o.t = -1.0f; o.u = 0.0f; o.v = 0.0f; o.instance_id = o.primitive_id = o.geo_id = 0xFFFFFFFFu; }
+            hits[i] = o;
+        });
 }
 
 template <bool ALPHA, bool COUNT>

@@ -76,7 +76,7 @@ inline const char* rt_platform_error() { return "emu"; }
 
 template <class F> inline void rt_launch(size_t n, rt_stream_t, F f) { for (size_t i = 0; i < n; ++i) f(i); }
 
-inline int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, size_t n, rt_stream_t) {
+inline int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, size_t n, void**, size_t*, rt_stream_t) {
     std::vector<uint32_t> idx(n);
     for (size_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
     std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
@@ -85,13 +85,13 @@ inline int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp,
     return 0;
 }
 
-inline int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, rt_stream_t) {
+inline int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void**, size_t*, rt_stream_t) {
     uint32_t acc = 0;
     for (size_t i = 0; i < n; ++i) { const uint32_t v = in[i]; out[i] = acc; acc += v; }
     return 0;
 }
 
-struct rt_timer { void create() {} void destroy() {} void record(rt_stream_t) {} };
+struct rt_timer { void create() {} void destroy() {} void record(rt_stream_t) {} bool ready() { return true; } };
 inline float rt_timer_ms(rt_timer&, rt_timer&) { return 0.0f; }
 struct rt_event { void create() {} void destroy() {} void record(rt_stream_t) {} void wait(rt_stream_t) {} int sync() { return 0; } };
 inline int rt_stream_create(rt_stream_t* s) { *s = nullptr; return 0; }
@@ -102,6 +102,7 @@ inline void rt_stream_destroy(rt_stream_t) {}
 // CUDA (product)
 // ----------------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
+#include <atomic>
 #define RT_HD __host__ __device__ __forceinline__
 #define RT_D __device__ __forceinline__
 #define RT_D_COLD __device__ __noinline__   // rarely executed helpers kept out of line: smaller hot path, fewer registers
@@ -149,15 +150,16 @@ int rt_d2h(void* h, const void* d, size_t n, rt_stream_t s);
 int rt_d2d(void* d, const void* s_, size_t n, rt_stream_t s);
 int rt_memset(void* d, int v, size_t n, rt_stream_t s);
 int rt_stream_sync(rt_stream_t s);
-int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, size_t n, rt_stream_t s);
-int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, rt_stream_t s);
+// tmp / tmp_bytes: caller-owned temporary storage (grown on demand; lives in the scene's BuildScratch, i.e. on that scene's device)
+int rt_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, size_t n, void** tmp, size_t* tmp_bytes, rt_stream_t s);
+int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void** tmp, size_t* tmp_bytes, rt_stream_t s);
 
 // generic element-wise launch: grid-stride, 256 threads, grid capped at a multiple of the SM count
 template <class F> __global__ void __launch_bounds__(256) rt_foreach_kernel(size_t n, F f) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f(i);
 }
 extern int g_rt_sm_count;
-extern unsigned long long g_rt_launch_count;
+extern std::atomic<unsigned long long> g_rt_launch_count;   // kernels launched by this library (all contexts of the process)
 template <class F> inline void rt_launch(size_t n, rt_stream_t s, F f) {
     if (n == 0) return;
     size_t blocks = (n + 255) / 256;
@@ -172,6 +174,7 @@ struct rt_timer {
     void create() { if (!e) cudaEventCreate(&e); }
     void destroy() { if (e) cudaEventDestroy(e); e = nullptr; }
     void record(rt_stream_t s) { cudaEventRecord(e, s); }
+    bool ready() { return cudaEventQuery(e) == cudaSuccess; }
 };
 inline float rt_timer_ms(rt_timer& a, rt_timer& b) { float ms = 0; cudaEventElapsedTime(&ms, a.e, b.e); return ms; }
 // ordering-only event (no timing): cross-stream dependencies of the frames in flight

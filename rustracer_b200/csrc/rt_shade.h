@@ -257,9 +257,12 @@ RT_D void shade_miss(const DScene& S, const FrameParams& P, f3 world_dir, bool p
 // SIMPLE: the scene has no textures and no specular-glossiness material and the frame uses mapping == RENDER with
 // debug == 0 (checked on the host per frame) — the same kind of specialisation as the reference's any-hit-free pipeline
 // for fully opaque scenes (pipeline_res.rs:155-166).  It removes the texture / debug code from the hot kernel.
-template <bool SIMPLE>
+// COUNT: texture taps and light candidates of this hit are added to `cnt` (SURVEY.md §8d algorithmic bytes).
+template <bool SIMPLE, bool COUNT = false>
 RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, PathState& st, ShadeOut& o, RtCounters* cnt) {
     const rt_ubo& ubo = P.ubo;
+    uint32_t n_taps = 0, n_cands = 0;
+#define RT_TEX(idx, uvc) (n_taps += COUNT ? 1u : 0u, texture2d(S, (idx), (uvc)))
     const float4* op = S.inst_o2w + (size_t)hit.inst * RT_O2W_F4;
     const float4 m0 = rt_ld(op), m1 = rt_ld(op + 1), m2 = rt_ld(op + 2), m3 = rt_ld(op + 3);
     rt_prim_info pinfo;     // copy of prim_infos[geo_id] kept in the instance record (one dependent load less)
@@ -283,10 +286,10 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     f3 origin = mk3(m0.x * pos.x + m0.y * pos.y + m0.z * pos.z + m0.w, m1.x * pos.x + m1.y * pos.y + m1.z * pos.z + m1.w, m2.x * pos.x + m2.y * pos.y + m2.z * pos.z + m2.w);
 
     f4 color4 = vcolor * ld_f4(mat.base_color);
-    if (!SIMPLE && mat.base_color_texture.index >= 0) color4 *= texture2d(S, mat.base_color_texture.index, get_uv(uv, mat.base_color_texture.coord));
+    if (!SIMPLE && mat.base_color_texture.index >= 0) color4 *= RT_TEX(mat.base_color_texture.index, get_uv(uv, mat.base_color_texture.coord));
     f3 color = xyz(color4);
     if (!SIMPLE && mat.normal_texture.index >= 0) {
-        const f3 nt = normalize(xyz(texture2d(S, mat.normal_texture.index, get_uv(uv, mat.normal_texture.coord))) * 2.0f - 1.0f);
+        const f3 nt = normalize(xyz(RT_TEX(mat.normal_texture.index, get_uv(uv, mat.normal_texture.coord))) * 2.0f - 1.0f);
         const f3 tm = xyz(tangent);                                         // getNormal :124-129
         const f3 tg = normalize(tm - dot(tm, normal) * normal);
         const f3 bt = normalize(cross(normal, tg) * tangent.w);
@@ -301,18 +304,18 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     const f3 N = dot(geo_normal, normal) < 0.0f ? -normal : normal;
 
     f3 emissive = mk3(mat.emissive_factor[0], mat.emissive_factor[1], mat.emissive_factor[2]);
-    if (!SIMPLE && mat.emissive_texture.index >= 0) emissive *= xyz(texture2d(S, mat.emissive_texture.index, get_uv(uv, mat.emissive_texture.coord)));
+    if (!SIMPLE && mat.emissive_texture.index >= 0) emissive *= xyz(RT_TEX(mat.emissive_texture.index, get_uv(uv, mat.emissive_texture.coord)));
     float metallic = mat.metallic_factor, roughness = mat.roughness_factor;
     if (!SIMPLE && mat.metallic_roughness_texture.index >= 0) {
-        const f4 mr = texture2d(S, mat.metallic_roughness_texture.index, get_uv(uv, mat.metallic_roughness_texture.coord));
+        const f4 mr = RT_TEX(mat.metallic_roughness_texture.index, get_uv(uv, mat.metallic_roughness_texture.coord));
         roughness *= mr.y; metallic *= mr.z;
     }
     f3 spec_wf = mk3(1.0f);
     const bool sg = !SIMPLE && mat.workflow == 1u;
     if (sg) {
         f4 diffuse_factor = ld_f4(mat.sg_diffuse_factor), sgf = ld_f4(mat.sg_specular_glossiness_factor);
-        if (mat.sg_diffuse_texture.index >= 0) diffuse_factor *= texture2d(S, mat.sg_diffuse_texture.index, get_uv(uv, mat.sg_diffuse_texture.coord));
-        if (mat.sg_specular_glossiness_texture.index >= 0) sgf *= texture2d(S, mat.sg_specular_glossiness_texture.index, get_uv(uv, mat.sg_specular_glossiness_texture.coord));
+        if (mat.sg_diffuse_texture.index >= 0) diffuse_factor *= RT_TEX(mat.sg_diffuse_texture.index, get_uv(uv, mat.sg_diffuse_texture.coord));
+        if (mat.sg_specular_glossiness_texture.index >= 0) sgf *= RT_TEX(mat.sg_specular_glossiness_texture.index, get_uv(uv, mat.sg_specular_glossiness_texture.coord));
         spec_wf = xyz(sgf);
         roughness = 1.0f - sgf.w;
         color = xyz(vcolor) * xyz(diffuse_factor);
@@ -321,11 +324,13 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     float transmission = 0.0f;
     if (mat.transmission_exist) {
         transmission = mat.transmission_factor;
-        if (!SIMPLE && mat.transmission_texture.index >= 0) transmission *= texture2d(S, mat.transmission_texture.index, get_uv(uv, mat.transmission_texture.coord)).x;
+        if (!SIMPLE && mat.transmission_texture.index >= 0) transmission *= RT_TEX(mat.transmission_texture.index, get_uv(uv, mat.transmission_texture.coord)).x;
     }
 
     o.t = hit.t; o.need_scatter = false; o.has_shadow = false; o.hit_value = mk3(0.0f);
     o.next_origin = pos; o.next_dir = mk3(0.0f);
+    if (COUNT && cnt && n_taps) rt_atomic_add64(&cnt->tex_taps, n_taps);   // (taps below this point are flushed at the end)
+    n_taps = 0;
     uint32_t mapping = SIMPLE ? (uint32_t)RT_MAP_RENDER : ubo.mapping;
     if (mat.unlit) mapping = RT_MAP_ALBEDO;
     switch (mapping) {   // :258-286 debug channels return through Ray.emittance
@@ -344,8 +349,8 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
 
     float spec_factor = mat.specular_factor;
     f3 spec_color = mk3(mat.specular_color_factor[0], mat.specular_color_factor[1], mat.specular_color_factor[2]);
-    if (!SIMPLE && mat.specular_texture.index >= 0) spec_factor *= texture2d(S, mat.specular_texture.index, get_uv(uv, mat.specular_texture.coord)).w;
-    if (!SIMPLE && mat.specular_color_texture.index >= 0) spec_color *= xyz(texture2d(S, mat.specular_color_texture.index, get_uv(uv, mat.specular_color_texture.coord)));
+    if (!SIMPLE && mat.specular_texture.index >= 0) spec_factor *= RT_TEX(mat.specular_texture.index, get_uv(uv, mat.specular_texture.coord)).w;
+    if (!SIMPLE && mat.specular_color_texture.index >= 0) spec_color *= xyz(RT_TEX(mat.specular_color_texture.index, get_uv(uv, mat.specular_color_texture.coord)));
 
     o.emittance = emissive * ubo.exposure;
     Surface m;
@@ -372,6 +377,7 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
         for (uint32_t i = 0; i < ncand; i++) {
             const rt_light& li = S.plights[i];
             if (luminance(mk3(li.color[0], li.color[1], li.color[2]) * li.intensity) < 0.1f) continue;
+            if (COUNT) ++n_cands;
             uint32_t k = (uint32_t)(rng_next(rng) * (float)S.n_plights);
             if (k > S.n_plights - 1u) k = S.n_plights - 1u;
             const rt_light& cand = S.plights[k];
@@ -439,6 +445,8 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
         st.lens_seed = seed;
     }
     st.path_w = rng.w;
+    if (COUNT && cnt) { if (n_taps) rt_atomic_add64(&cnt->tex_taps, n_taps); if (n_cands) rt_atomic_add64(&cnt->light_cands, n_cands); }
+#undef RT_TEX
 }
 
 // ---- lib/Tonemapping.glsl, lib/Heatmap.glsl, RayTracing.rgen:132-166 ------------------------------------

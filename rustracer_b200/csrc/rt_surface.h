@@ -118,7 +118,7 @@ RT_D TriIndices fetch_indices(const DScene& S, const rt_prim_info& pi, uint32_t 
 }
 
 // ---- any-hit alpha test (RayTracing.rahit:44-104); true = ignore the candidate --------------------------
-RT_D bool anyhit_ignore(const DScene& S, uint32_t instance_id, uint32_t primitive_id, uint32_t geo_id, float bu, float bv, u4 rng) {
+RT_D bool anyhit_ignore(const DScene& S, uint32_t instance_id, uint32_t primitive_id, uint32_t geo_id, float bu, float bv, u4 rng, unsigned long long* taps = nullptr) {
     const rt_prim_info pi = S.prim_infos[geo_id];
     const rt_material& mat = S.materials[pi.material_id];
     const uint32_t alpha_mode = mat.alpha_mode;
@@ -129,11 +129,11 @@ RT_D bool anyhit_ignore(const DScene& S, uint32_t instance_id, uint32_t primitiv
     f4 uv = mk4(v0.uv0[0], v0.uv0[1], v0.uv1[0], v0.uv1[1]) * b0 + mk4(v1.uv0[0], v1.uv0[1], v1.uv1[0], v1.uv1[1]) * bu + mk4(v2.uv0[0], v2.uv0[1], v2.uv1[0], v2.uv1[1]) * bv;
     f4 vcolor = ld_f4(v0.color) * b0 + ld_f4(v1.color) * bu + ld_f4(v2.color) * bv;
     f4 color4 = vcolor * ld_f4(mat.base_color);
-    if (mat.base_color_texture.index >= 0) color4 *= texture2d(S, mat.base_color_texture.index, get_uv(uv, mat.base_color_texture.coord));
+    if (mat.base_color_texture.index >= 0) { if (taps) ++*taps; color4 *= texture2d(S, mat.base_color_texture.index, get_uv(uv, mat.base_color_texture.coord)); }
     float opacity = color4.w;
     if (mat.workflow == 1) {
         f4 diffuse_factor = ld_f4(mat.sg_diffuse_factor);
-        if (mat.sg_diffuse_texture.index >= 0) diffuse_factor *= texture2d(S, mat.sg_diffuse_texture.index, get_uv(uv, mat.sg_diffuse_texture.coord));
+        if (mat.sg_diffuse_texture.index >= 0) { if (taps) ++*taps; diffuse_factor *= texture2d(S, mat.sg_diffuse_texture.index, get_uv(uv, mat.sg_diffuse_texture.coord)); }
         opacity = (vcolor * diffuse_factor).w;
     }
     if (alpha_mode == 2) return opacity < mat.alpha_cutoff;

@@ -266,7 +266,7 @@ RT_D bool trav_prim_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
         trav_alpha_context(S, t.merged, inst, t.cur_geo, t.cur_alpha, geo, alpha);
         if (alpha) {
             if (COUNT) c4[3]++;
-            if (anyhit_ignore(S, inst, prim, geo, bu, bv, t.rng)) return false;
+            if (anyhit_ignore(S, inst, prim, geo, bu, bv, t.rng, COUNT ? c4 + 4 : nullptr)) return false;
         }
     }
     trav_commit(t, tt, bu, bv, inst, prim);
@@ -278,7 +278,7 @@ RT_D void trav_finish(Trav& t) { if (!t.found) t.hit.t = -1.0f; }
 template <int MODE, bool ALPHA, bool COUNT>
 RT_D bool trace_ray(const DScene& S, f3 ow, f3 dw, float tmin, float tmax, u4 rng, RtHit& hit, RtCounters* cnt) {
     uint2 stack[RT_STACK_SIZE];
-    unsigned long long c4[4] = {0, 0, 0, 0};
+    unsigned long long c4[5] = {0, 0, 0, 0, 0};
     Trav t;
     trav_init(t, S, ow, dw, tmin, tmax, rng);
     bool done = false;
@@ -289,7 +289,7 @@ RT_D bool trace_ray(const DScene& S, f3 ow, f3 dw, float tmin, float tmax, u4 rn
     trav_finish(t);
     if (COUNT && cnt) {
         rt_atomic_add64(&cnt->nodes, c4[0]); rt_atomic_add64(&cnt->tris, c4[1]);
-        rt_atomic_add64(&cnt->insts, c4[2]); rt_atomic_add64(&cnt->anyhits, c4[3]);
+        rt_atomic_add64(&cnt->insts, c4[2]); rt_atomic_add64(&cnt->anyhits, c4[3]); rt_atomic_add64(&cnt->tex_taps, c4[4]);
     }
     hit = t.hit;
     return t.found;

@@ -85,9 +85,10 @@ def uv_sphere(radius=1.0, stacks=64, slices=65):
     return (n * radius).astype(np.float32), n.astype(np.float32), uv.astype(np.float32), grid_indices(stacks, slices)
 
 
-def lucy_standin(rows=474, cols=473, seed=0xC0FFEE):
+def lucy_standin(rows=574, cols=391, seed=0xC0FFEE):
     """Procedural statue-like closed surface filling Lucy's local AABB (SURVEY.md §8c: the real blob is missing;
-    min (-141.4,-257.1,-866.5) max (153.5,205.8,-11.9)); ~448k triangles with scan-like high-frequency relief."""
+    min (-141.4,-257.1,-866.5) max (153.5,205.8,-11.9)); 2*rows*cols triangles (default 574 x 391 = 448 868, the triangle
+    count of the real scan) with scan-like high-frequency relief."""
     rng = np.random.default_rng(seed)
     lo = np.array([-141.44540405273438, -257.1471862792969, -866.5087280273438])
     hi = np.array([153.5471954345703, 205.83340454101562, -11.90410041809082])
@@ -268,11 +269,30 @@ class SceneBuilder:
 # ----------------------------------------------------------------------------------------------------
 # named scenes
 # ----------------------------------------------------------------------------------------------------
-def cornell_box(lucy: bool = False, blend_sphere: bool = True, lucy_rows=474, lucy_cols=473) -> F.rt_scene_desc:
-    """Procedural Cornell box with the node layout and materials of assets/models/CornellBox/cornellBox.gltf
-    (config 1) or CornellBoxLucy/cornellBoxLucy.gltf (config 2, `lucy=True`: all materials OPAQUE, glass sphere
-    and a ~448k-triangle procedural stand-in for the missing Lucy scan, deviation D4)."""
+def cornell_box(lucy: bool = False, blend_sphere: bool = True, lucy_rows=574, lucy_cols=391, shell=None) -> F.rt_scene_desc:
+    """Cornell box with the node layout and materials of assets/models/CornellBox/cornellBox.gltf (config 1) or
+    CornellBoxLucy/cornellBoxLucy.gltf (config 2, `lucy=True`: all materials OPAQUE, glass sphere and a ~448k-triangle
+    procedural stand-in for the missing Lucy scan, deviation D4).
+    shell: path of an .npz written by tests/util.save_scene_npz from the real cornellBox.gltf / cornellBox.bin
+    (tests/golden/cornell_box_scene.npz): the nine shell meshes (walls, light, boxes, two spheres) then carry the
+    asset's own vertices / normals / uvs / tangents / indices ("Cornell shell from
+    cornellBox.bin"); without it the shell is procedural (same node transforms, 64x65 uv spheres)."""
     b = SceneBuilder()
+    shell_z = np.load(shell) if shell is not None else None
+
+    def shell_mesh(k, fallback):
+        if shell_z is None:
+            return fallback
+        vo, io = int(shell_z["prim_infos"][k][0]), int(shell_z["prim_infos"][k][1])
+        nv, ni = int(shell_z["geometries"][k][0]), int(shell_z["geometries"][k][1])
+        return (shell_z["position"][vo:vo + nv], shell_z["normal"][vo:vo + nv], shell_z["uv0"][vo:vo + nv], shell_z["indices"][io:io + ni])
+
+    def shell_tangents():
+        if shell_z is None:
+            return
+        for k in range(9):
+            vo, nv = int(shell_z["prim_infos"][k][0]), int(shell_z["geometries"][k][0])
+            b.verts[k]["tangent"] = shell_z["tangent"][vo:vo + nv]
     white = b.add_material(material(metallic=0.0))
     white2 = b.add_material(material(metallic=0.0))
     green = b.add_material(material((0.054592281579971313, 1.0, 0.0, 1.0), metallic=0.0))
@@ -288,15 +308,16 @@ def cornell_box(lucy: bool = False, blend_sphere: bool = True, lucy_rows=474, lu
     else:
         sph_b = b.add_material(material(roughness=0.0, ior=1.76))
     e = 0.05000000074505806
-    g_back = b.add_geometry(*box_mesh((5, 5, e)), white)
-    g_floor = b.add_geometry(*box_mesh((5, e, 5)), white2)
-    g_left = b.add_geometry(*box_mesh((e, 5, 5)), green)
-    g_right = b.add_geometry(*box_mesh((e, 5, 5)), red)
-    g_light = b.add_geometry(*box_mesh((0.5, e, 0.5)), light)
-    g_cube = b.add_geometry(*box_mesh((0.5, 0.5, 0.5)), grey)
-    g_tall = b.add_geometry(*box_mesh((1.25, 3.0, 1.25)), default)
-    g_sa = b.add_geometry(*uv_sphere(), sph_a)
-    g_sb = b.add_geometry(*uv_sphere(), sph_b)
+    g_back = b.add_geometry(*shell_mesh(0, box_mesh((5, 5, e))), white)
+    g_floor = b.add_geometry(*shell_mesh(1, box_mesh((5, e, 5))), white2)
+    g_left = b.add_geometry(*shell_mesh(2, box_mesh((e, 5, 5))), green)
+    g_right = b.add_geometry(*shell_mesh(3, box_mesh((e, 5, 5))), red)
+    g_light = b.add_geometry(*shell_mesh(4, box_mesh((0.5, e, 0.5))), light)
+    g_cube = b.add_geometry(*shell_mesh(5, box_mesh((0.5, 0.5, 0.5))), grey)
+    g_tall = b.add_geometry(*shell_mesh(6, box_mesh((1.25, 3.0, 1.25))), default)
+    g_sa = b.add_geometry(*shell_mesh(7, uv_sphere()), sph_a)
+    g_sb = b.add_geometry(*shell_mesh(8, uv_sphere()), sph_b)
+    shell_tangents()
     b.add_instance(g_back, trs((0, 0, -5)))
     b.add_instance(g_floor, trs((0, -5, 0)))
     b.add_instance(g_floor, trs((0, 5, 0)))          # mesh 1 is instanced twice (floor and ceiling)

@@ -17,18 +17,54 @@ def make(api, desc, w=64, h=64):
     return ctx, core.Scene(ctx, desc)
 
 
+SCALAR = 2   # RT_TRACE_SCALAR: one thread per ray; default = the persistent wavefront traversal rt_render runs
+
+
+def check_ids(sc, o, rays, flags=0, rng4=None, what=""):
+    """Closest-hit ids / t / u / v bit-exact vs the oracle through BOTH GPU paths: the persistent wavefront traversal of the
+    frame kernels (default of rt_trace_closest) and the scalar per-thread loop."""
+    ho = o.trace_closest(rays, flags, rng4)
+    for mode in (0, SCALAR):
+        hg = sc.trace_closest(rays, flags | mode, rng4)
+        bad = ~util.hits_equal(hg, ho)
+        assert not bad.any(), (what, "scalar" if mode else "wavefront", int(bad.sum()), hg[bad][:3], ho[bad][:3])
+    return ho
+
+
+def check_any(sc, o, rays, flags=0, rng4=None, what=""):
+    oo = o.trace_any(rays, flags, rng4)
+    for mode in (0, SCALAR):
+        og = sc.trace_any(rays, flags | mode, rng4)
+        assert (og == oo).all(), (what, "scalar" if mode else "wavefront", int((og != oo).sum()))
+    return oo
+
+
+def bounce_ray_sets(o, ubo, W, H, stride=1, max_rays=1 << 19, max_shadow=1 << 17):
+    """SURVEY.md §8d ray set (iv): the oracle's own bounce >= 1 segments (origin on a surface, tMin = 0.001) and shadow rays."""
+    return o.record_bounce_rays(ubo, W, H, stride=stride, min_bounce=1, max_rays=max_rays, max_shadow=max_shadow)
+
+
 def case_trace_golden(api, cornell_desc, cornell_oracle, golden, n_adv=3000):
     ctx, sc = make(api, cornell_desc)
     for flags, key in ((1, "hits_opaque"), (0, "hits_alpha")):
-        h = sc.trace_closest(golden["rays"], flags, golden["rng4"])
-        assert util.hits_equal(h, golden[key]).all(), key
+        for mode in (0, SCALAR):
+            h = sc.trace_closest(golden["rays"], flags | mode, golden["rng4"])
+            assert util.hits_equal(h, golden[key]).all(), (key, mode)
     adv = util.adversarial_rays(cornell_desc, n_adv, seed=11)
     for flags in (0, 1):
-        a, b = sc.trace_closest(adv, flags), cornell_oracle.trace_closest(adv, flags)
-        assert util.hits_equal(a, b).all()
+        check_ids(sc, cornell_oracle, adv, flags, what="adversarial")
     srays = golden["rays"].copy(); srays["tmin"] = 0.1; srays["tmax"] = 6.0
-    assert (sc.trace_any(srays, 0, golden["rng4"]) == golden["any_alpha"]).all()
+    for mode in (0, SCALAR):
+        assert (sc.trace_any(srays, mode, golden["rng4"]) == golden["any_alpha"]).all()
     assert len(sc.trace_closest(np.zeros(0, F.RAY_DTYPE))) == 0   # empty input
+    # ray set (iv): bounce >= 1 segments and shadow rays of the oracle's own path tracer (BLEND sphere: alpha test with the payload RNG)
+    W = H = 96
+    cam = host.Camera(W, H); gui = host.Gui(number_of_samples=1, number_of_bounces=8)
+    ubo = host.FrameDriver(cam, gui, cornell_desc.fully_opaque).next_ubo()
+    rays, rng4, srays, srng4 = bounce_ray_sets(cornell_oracle, ubo, W, H)
+    assert len(rays) > 5000
+    check_ids(sc, cornell_oracle, rays, 0, rng4, what="bounce rays")
+    check_ids(sc, cornell_oracle, rays, 1, None, what="bounce rays opaque")
 
 
 def case_render_golden(api, cornell_desc, golden):
@@ -150,12 +186,12 @@ def case_instancing(api):
     o = orc.OracleScene(d)
     ctx, sc = make(api, d, 32, 32)
     rays, _ = util.random_rays(4000, seed=8, extent=9.0)
-    assert util.hits_equal(sc.trace_closest(rays, 1), o.trace_closest(rays, 1)).all()
+    check_ids(sc, o, rays, 1)
     assert sc.bvh_info().tlas_nodes >= 2
     inst = np.frombuffer(util._arr(d.instances, d.n_instances, F.rt_instance), F.INSTANCE_DTYPE).copy()
     inst["transform"][:, 3] += 1.5
     sc.update_instances(inst); o.update_instances(inst)
-    assert util.hits_equal(sc.trace_closest(rays, 1), o.trace_closest(rays, 1)).all()
+    check_ids(sc, o, rays, 1)
 
 
 def bright_lights():
@@ -178,7 +214,16 @@ def case_lights(api, cornell_desc, size=48, frames=2):
     acc_e, out_e = ctx.readback()
     s = ctx.stats()
     assert st.rays_shadow > 0 and abs(int(s.rays_shadow) - int(st.rays_shadow)) <= 0.001 * st.rays_shadow
+    assert abs(int(s.shaded_hits) - int(st.shaded_hits)) <= 0.002 * st.shaded_hits and s.shaded_hits < s.rays_extend   # real hits, not shade invocations
     assert util.mean_rel_err(acc_e, acc, 2 * frames) < MRE_TOL and util.psnr(out_e[..., :3], out[..., :3]) >= PSNR_TOL
+    # counted frame: texture taps / light candidates feed bench.py's algorithmic bytes and must follow the oracle's
+    u = d2.next_ubo(); ctx.render(sc, u, flags=1); sg = ctx.stats(); _, _, so = o.render(d1.next_ubo(), size, size, acc)
+    assert so.light_cands > 0 and abs(int(sg.light_cands) - int(so.light_cands)) <= 0.002 * so.light_cands and sg.tex_taps == so.tex_taps == 0
+    # ray set (iv): the oracle's shadow rays (tMin 0.1, any-hit with the BLEND sphere) and bounce rays with NEE on
+    rays, rng4, srays, srng4 = bounce_ray_sets(o, u, size, size)
+    assert len(srays) > 100
+    check_any(sc, o, srays, 0, srng4, what="shadow rays")
+    check_ids(sc, o, rays, 0, rng4, what="bounce rays (lights)")
 
 
 def skinned_scene(seed=3, rows=24, cols=16, joints=8):
@@ -250,12 +295,18 @@ def case_skinning(api):
 
 
 def case_lucy_ids(api, n_rays=100000, rows=120, cols=121):
-    d = scenes.cornell_box(lucy=True, lucy_rows=rows, lucy_cols=cols)
+    d = scenes.cornell_box(lucy=True, lucy_rows=rows, lucy_cols=cols, shell=util.GOLDEN / "cornell_box_scene.npz")   # §8d config 2: real shell + stand-in
     o = orc.OracleScene(d)
     ctx, sc = make(api, d, 32, 32)
     rays, _ = util.random_rays(n_rays, seed=5)
-    hg, ho = sc.trace_closest(rays, 1), o.trace_closest(rays, 1)
-    assert util.hits_equal(hg, ho).all()
+    check_ids(sc, o, rays, 1, what="lucy random")
+    check_ids(sc, o, util.adversarial_rays(d, min(20000, n_rays), seed=13), 1, what="lucy adversarial")
+    # ray set (iv): the oracle's own bounce >= 1 rays at the reference camera (inside the box, incoherent, origin on surfaces)
+    W, H = 480, 270
+    ubo = host.FrameDriver(host.Camera(W, H), host.Gui(number_of_samples=1, number_of_bounces=8), True).next_ubo()
+    brays, brng, _, _ = bounce_ray_sets(o, ubo, W, H, max_rays=min(n_rays, 1 << 19))
+    assert len(brays) > min(n_rays, 1 << 19) // 4
+    check_ids(sc, o, brays, 1, what="lucy bounce rays")
     return d, o, ctx, sc
 
 
@@ -281,9 +332,9 @@ def case_foliage(api, n_side=6, tris=2000, size=64, n_rays=20000):
     ctx, sc = make(api, d, 16, 16)
     rays, rng4 = util.random_rays(n_rays, seed=31, extent=4.0)
     for flags in (0, 1):
-        assert util.hits_equal(sc.trace_closest(rays, flags, rng4), o.trace_closest(rays, flags, rng4)).all()
+        check_ids(sc, o, rays, flags, rng4)
     srays = rays.copy(); srays["tmin"] = 0.1; srays["tmax"] = 3.0
-    assert (sc.trace_any(srays, 0, rng4) == o.trace_any(srays, 0, rng4)).all()
+    check_any(sc, o, srays, 0, rng4)
     assert not d.fully_opaque
     render_compare(api, d, o, size, size, dict(number_of_samples=2, number_of_bounces=6, sky=1), 3, cam_pos=(0, 1.0, 6.0))
 
@@ -411,10 +462,16 @@ def case_textured_materials(api, size=96, frames=3, n_rays=20000):
     # closest hits bit-exact, then the rendered image and the texture-dependent debug channels
     ctx, sc = make(api, d, 32, 32)
     rays, _ = util.random_rays(n_rays, seed=23)
-    assert util.hits_equal(sc.trace_closest(rays, 1), o.trace_closest(rays, 1)).all()
+    check_ids(sc, o, rays, 1)
     del ctx, sc
     o2 = o
     ctx, sc, st = render_compare(api, d, o2, size, size, dict(number_of_samples=4, number_of_bounces=5), frames, cam_pos=(0, 0, 14.0))
+    # counted frame: texture taps and light candidates (bench.py's algorithmic bytes) follow the oracle's counts
+    cam = host.Camera(size, size).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=5)
+    u = host.FrameDriver(cam, gui, d.fully_opaque).next_ubo()
+    ctx.resize(size, size); ctx.render(sc, u, flags=1); sg = ctx.stats(); _, _, so = o2.render(u, size, size, None)
+    assert so.tex_taps > 0 and abs(int(sg.tex_taps) - int(so.tex_taps)) <= 0.003 * so.tex_taps, (sg.tex_taps, so.tex_taps)
+    assert abs(int(sg.light_cands) - int(so.light_cands)) <= 0.003 * so.light_cands and abs(int(sg.shaded_hits) - int(so.shaded_hits)) <= 0.003 * so.shaded_hits
     for mapping in (6, 7, 9, 10, 11):          # albedo, normal, metallic, roughness, transmission style channels (RayTracing.rchit:258-286)
         ctx.resize(size, size)
         cam = host.Camera(size, size).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=1, mapping=mapping, antialiasing=0)

@@ -53,7 +53,7 @@ def test_skinning_refit_and_rebuild(api):
 
 def test_lucy_scene_ids_and_image(api):
     """Config-2 scene at full triangle count: 2^20 random rays bit-exact, then a 256x144 8-spp image within tolerance."""
-    d, o, ctx, sc = pc.case_lucy_ids(api, n_rays=1 << 20, rows=474, cols=473)
+    d, o, ctx, sc = pc.case_lucy_ids(api, n_rays=1 << 20, rows=574, cols=391)
     W, H = 256, 144
     ctx.resize(W, H)
     cam = host.Camera(W, H).set(position=(0, 0, 14.0)); gui = host.Gui(number_of_samples=2, number_of_bounces=8)
@@ -163,9 +163,12 @@ def test_baseline_sized_configs_properties(api):
     ctx = core.Context(1920, 1080, api=api); sc = core.Scene(ctx, d)
     rays, rng4 = util.random_rays(50000, seed=41, extent=5.0)
     for flags in (0, 1):
-        assert util.hits_equal(sc.trace_closest(rays, flags, rng4), o.trace_closest(rays, flags, rng4)).all()
+        pc.check_ids(sc, o, rays, flags, rng4, what='config 3 random')
     cam = host.Camera(1920, 1080).set(position=(0, 1.2, 7.0)); gui = host.Gui(number_of_samples=1, number_of_bounces=8, sky=1)
     u = host.FrameDriver(cam, gui, False).next_ubo()
+    brays, brng, _, _ = pc.bounce_ray_sets(o, u, 1920, 1080, stride=97, max_rays=40000)      # ray set (iv) through the two-level alpha-tested path
+    assert len(brays) > 5000
+    pc.check_ids(sc, o, brays, 0, brng, what='config 3 bounce rays')
     ctx.render(sc, u); a0, o0 = ctx.readback()
     ctx.resize(1920, 1080); ctx.render(sc, u); a1, o1 = ctx.readback()
     assert (a0 == a1).all() and (o0 == o1).all() and np.isfinite(a0).all() and a0[..., :3].max() > 0
