@@ -60,6 +60,9 @@ struct StageEvent { int stage; rt_timer a, b; };
 }  // namespace rtcore
 using namespace rtcore;
 
+#ifndef RT_MIN_RAYS_PER_CTA
+#define RT_MIN_RAYS_PER_CTA 0
+#endif
 #define RT_MAX_FRAMES_IN_FLIGHT 4
 #define RT_MAX_SCENE_VERSIONS 4
 #define RT_TICKET_RING 12
@@ -539,6 +542,15 @@ static inline unsigned trace_grid() {
 }
 #endif
 
+#ifndef RT_EMU
+// CTAs of a traversal launch beyond queue size / this leave immediately (0 = every CTA stays); RT_B200_MIN_RAYS_PER_CTA overrides
+static inline uint32_t min_rays_per_cta() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RT_B200_MIN_RAYS_PER_CTA"); v = e ? atoi(e) : RT_MIN_RAYS_PER_CTA; if (v < 0) v = 0; }
+    return (uint32_t)v;
+}
+#endif
+
 template <bool ALPHA, bool COUNT>
 static void launch_extend(FrameSlot* c, const DScene& S, const FrameParams& P, const DQueue& q, const uint32_t* count, uint32_t* fetch, uint32_t max_count, rt_stream_t st) {
 #ifdef RT_EMU
@@ -546,8 +558,8 @@ static void launch_extend(FrameSlot* c, const DScene& S, const FrameParams& P, c
     for (uint32_t i = 0; i < n; ++i) extend_item<ALPHA, COUNT>(S, P, q, c->hits, i, c->dev_cnt);
     (void)fetch; (void)max_count; (void)st;
 #else
-    if (S.single_merged) extend_kernel<ALPHA, COUNT, true><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
-    else extend_kernel<ALPHA, COUNT, false><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt);
+    if (S.single_merged) extend_kernel<ALPHA, COUNT, true><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt, min_rays_per_cta());
+    else extend_kernel<ALPHA, COUNT, false><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, q, c->hits, count, fetch, c->dev_cnt, min_rays_per_cta());
     ++g_rt_launch_count; (void)max_count;
 #endif
 }
@@ -558,8 +570,8 @@ static void launch_shadow(FrameSlot* c, const DScene& S, const FrameParams& P, c
     for (uint32_t i = 0; i < n; ++i) shadow_item<ALPHA, COUNT>(S, P, c->fb, c->sq, i, c->dev_cnt);
     (void)fetch; (void)st;
 #else
-    if (S.single_merged) shadow_kernel<ALPHA, COUNT, true><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
-    else shadow_kernel<ALPHA, COUNT, false><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt);
+    if (S.single_merged) shadow_kernel<ALPHA, COUNT, true><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt, min_rays_per_cta());
+    else shadow_kernel<ALPHA, COUNT, false><<<trace_grid(), RT_EXTEND_THREADS, 0, st>>>(S, P, c->fb, c->sq, count, fetch, c->dev_cnt, min_rays_per_cta());
     ++g_rt_launch_count;
 #endif
 }

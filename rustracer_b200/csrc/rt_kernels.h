@@ -339,7 +339,10 @@ RT_D void coop_round(Trav& tv, const DScene& S, CoopShared<ALPHA>& sh, uint32_t 
 // SINGLE: the scene is one merged world-space BLAS (DScene::single_merged) — no TLAS level, no instance entry / exit,
 // node and triangle bases come from the kernel parameters (uniform registers) instead of per-lane state.
 template <int MODE, bool ALPHA, bool COUNT, bool SINGLE, class LoadRay, class StoreHit>
-RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetch, RtCounters* cnt, LoadRay load_ray, StoreHit store_hit) {
+RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetch, RtCounters* cnt, LoadRay load_ray, StoreHit store_hit, uint32_t min_rays_per_cta = 0u) {
+    // thin queues (late bounces): the launch is sized for the largest queue; CTAs beyond count / min_rays_per_cta leave at
+    // once so that the remaining warps are refilled several times instead of every warp draining a single batch of rays
+    if (min_rays_per_cta && (unsigned long long)blockIdx.x * min_rays_per_cta >= count && blockIdx.x != 0u) return;
     __shared__ CoopShared<ALPHA> coop_smem[RT_WARPS_PER_BLOCK];
     CoopShared<ALPHA>& sh = coop_smem[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
@@ -482,7 +485,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
 }
 
 template <bool ALPHA, bool COUNT, bool SINGLE>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOCKS_SINGLE : RT_EXTEND_MIN_BLOCKS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOCKS_SINGLE : RT_EXTEND_MIN_BLOCKS) extend_kernel(DScene S, FrameParams P, DQueue q, DHits hits, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt, uint32_t min_rays_per_cta) {
     persistent_trace<RT_MODE_CLOSEST, ALPHA, COUNT, SINGLE>(S, *count_ptr, fetch, cnt,
         [&](uint32_t i, Trav& tv) {
             const float4 a = q.o_tmin[i], b = q.d_tmax[i];
@@ -493,11 +496,11 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOC
         [&](uint32_t i, const Trav& tv) {
             hits.tuvp[i] = make_float4(tv.hit.t, tv.hit.u, tv.hit.v, rt_uint_as_float(tv.hit.prim));
             hits.inst[i] = tv.hit.inst;
-        });
+        }, min_rays_per_cta);
 }
 
 template <bool ALPHA, bool COUNT, bool SINGLE>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOCKS_SINGLE : RT_EXTEND_MIN_BLOCKS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt) {
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOCKS_SINGLE : RT_EXTEND_MIN_BLOCKS) shadow_kernel(DScene S, FrameParams P, FrameBuffers fb, DShadowQueue sq, const uint32_t* count_ptr, uint32_t* fetch, RtCounters* cnt, uint32_t min_rays_per_cta) {
     persistent_trace<RT_MODE_ANY, ALPHA, COUNT, SINGLE>(S, *count_ptr, fetch, cnt,
         [&](uint32_t i, Trav& tv) {
             const float4 a = sq.o_tmax[i], b = sq.d_pix[i];
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, SINGLE ? RT_EXTEND_MIN_BLOC
                 cur.x += c.x; cur.y += c.y; cur.z += c.z;
                 fb.rad[pixel] = cur;
             }
-        });
+        }, min_rays_per_cta);
 }
 
 #ifndef RT_SHADE_PREFETCH

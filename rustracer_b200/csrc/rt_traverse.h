@@ -48,7 +48,7 @@ RT_D bool tri_test(const RayShear& r, f3 o, f3 v0, f3 v1, f3 v2, float tmin, flo
     if (det == 0.0f) return false;
     const float Az = rt_fmul(r.Sz, Akz), Bz = rt_fmul(r.Sz, Bkz), Cz = rt_fmul(r.Sz, Ckz);
     const float T = rt_fadd(rt_fadd(rt_fmul(U, Az), rt_fmul(V, Bz)), rt_fmul(W, Cz));
-    const float inv = rt_fdiv(1.0f, det);
+    const float inv = rt_rcp(det);            // correctly rounded reciprocal == the oracle's 1.0f / det
     const float tt = rt_fmul(T, inv);
     if (!(tt > tmin && tt < tmax)) return false;
     t = tt; bu = rt_fmul(V, inv); bv = rt_fmul(W, inv);
