@@ -177,10 +177,10 @@ class Scene:
         return v
 
     def read_nodes(self, geo: int = -1) -> np.ndarray:
-        """80-byte compressed nodes of one BLAS as (n, 20) uint32 (geo < 0: the merged world-space BLAS)."""
+        """128-byte wide nodes of one BLAS as (n, 32) uint32 (geo < 0: the merged world-space BLAS)."""
         n = F.c_u32()
         self.api.check(self.api.rt_scene_read_nodes(self._h, geo, None, 0, C.byref(n)))
-        out = np.zeros((n.value, 20), np.float32)
+        out = np.zeros((n.value, 32), np.float32)
         if n.value:
             self.api.check(self.api.rt_scene_read_nodes(self._h, geo, F.as_ptr(out, F.c_f), n.value, C.byref(n)))
         return out.view(np.uint32)

@@ -1,5 +1,5 @@
 // rt_build.h — GPU BVH builder: Morton codes -> radix sort -> Karras LBVH -> bottom-up AABB fit ->
-// surface-area-guided collapse to 8-wide nodes with quantised child boxes (80 B/node), plus bottom-up refit.
+// surface-area-guided collapse to 8-wide nodes with bfloat16 child planes (128 B/node = one cache line), plus bottom-up refit.
 // Replaces vkCmdBuildAccelerationStructuresKHR (crates/libs/vulkan/src/ray_tracing/acceleration_structure.rs:95-173)
 // as driven by create_as / create_top_as (crates/libs/asset_loader/src/acceleration_structures.rs:79-249).
 // The same builder serves BLASes (primitives = triangles) and the TLAS (primitives = instance boxes).
@@ -120,46 +120,39 @@ struct WideOut {
     uint32_t max_nodes;
 };
 
-RT_D uint32_t pack4(const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); }
+// ---- bfloat16 child planes (rt_scene_dev.h: node layout) ----------------------------------------------------
+// plane value = child coordinate - node origin, evaluated exactly in double, then rounded conservatively: lo planes towards
+// -inf, hi planes towards +inf.  Inputs are >= 0 (the origin is the minimum of the child lows).
+RT_D float float_round_down(double d) { float f = (float)d; if ((double)f > d) f = nextafterf(f, -3.0e38f); return f; }
+RT_D float float_round_up(double d) { float f = (float)d; if ((double)f < d) f = nextafterf(f, 3.0e38f); return f; }
+RT_D uint32_t bf16_lo_plane(float child_lo, float origin) { return rt_float_as_uint(float_round_down((double)child_lo - (double)origin)) >> 16; }   // truncation == floor for values >= 0
+RT_D uint32_t bf16_hi_plane(float child_hi, float origin) { return (rt_float_as_uint(float_round_up((double)child_hi - (double)origin)) + 0xFFFFu) >> 16; }
+#define RT_PLANE_EMPTY 0x00007F80u      // hi = 0, lo = +inf: the slab is never entered
+// exponent byte E with 2^(E-127) >= every plane value the traversal can read from a node whose largest hi plane is hi_max
+// (a hi word read as a float is < hi + one bf16 ulp)
+RT_D uint32_t plane_bound_exponent(uint32_t hi_max_bf16) { uint32_t e = (((hi_max_bf16 + 1u) << 16) >> 23) + 1u; return e > 254u ? 254u : e; }
 
-// Quantise and write one wide node.  child_box[i] valid for meta[i] != 0.  Conservative: the de-quantised box
-// always contains the child box (checked in double precision).
+// Writes one wide node.  child_box[i] valid for meta[i] != 0.  Conservative: the planes the traversal reconstructs
+// always contain the child box.
 RT_D void write_wide_node(float4* node, const DAabb& box, const DAabb* child_box, const uint32_t* meta, uint32_t imask,
                           uint32_t child_base, uint32_t prim_base) {
-    int ex[3]; double scale[3];
-    for (int a = 0; a < 3; ++a) {
-        const double ext = (double)box.hi[a] - (double)box.lo[a];
-        int e = -100;
-        if (ext > 0.0) { int fe; frexp(ext / 255.0, &fe); e = fe; if (e < -100) e = -100; }   // 2^e >= ext/255
-        for (;;) {
-            const double sc = ldexp(1.0, e);
-            bool ok = true;
-            for (int i = 0; i < 8 && ok; ++i) {
-                if (!meta[i]) continue;
-                if (ceil(((double)child_box[i].hi[a] - (double)box.lo[a]) / sc) > 255.0) ok = false;
-            }
-            if (ok) break;
-            ++e;
-        }
-        ex[a] = e; scale[a] = ldexp(1.0, e);
-    }
-    uint32_t qlo[3][8], qhi[3][8];
+    uint32_t w[3][8]; uint32_t hi_max = 0u;
     for (int i = 0; i < 8; ++i) {
         for (int a = 0; a < 3; ++a) {
-            if (!meta[i]) { qlo[a][i] = 255; qhi[a][i] = 0; continue; }
-            double lo = floor(((double)child_box[i].lo[a] - (double)box.lo[a]) / scale[a]);
-            double hi = ceil(((double)child_box[i].hi[a] - (double)box.lo[a]) / scale[a]);
-            if (lo < 0.0) lo = 0.0; if (lo > 255.0) lo = 255.0;
-            if (hi < 0.0) hi = 0.0; if (hi > 255.0) hi = 255.0;
-            qlo[a][i] = (uint32_t)lo; qhi[a][i] = (uint32_t)hi;
+            if (!meta[i]) { w[a][i] = RT_PLANE_EMPTY; continue; }
+            const uint32_t lo = bf16_lo_plane(child_box[i].lo[a], box.lo[a]), hi = bf16_hi_plane(child_box[i].hi[a], box.lo[a]);
+            w[a][i] = (hi << 16) | lo;
+            if (hi > hi_max) hi_max = hi;
         }
     }
-    const uint32_t e_imask = (uint32_t)((ex[0] + 127) & 0xFF) | ((uint32_t)((ex[1] + 127) & 0xFF) << 8) | ((uint32_t)((ex[2] + 127) & 0xFF) << 16) | (imask << 24);
+    const uint32_t e_imask = plane_bound_exponent(hi_max) | (imask << 24);
     node[0] = make_float4(box.lo[0], box.lo[1], box.lo[2], rt_uint_as_float(e_imask));
-    node[1] = make_float4(rt_uint_as_float(child_base), rt_uint_as_float(prim_base), rt_uint_as_float(pack4(meta)), rt_uint_as_float(pack4(meta + 4)));
-    node[2] = make_float4(rt_uint_as_float(pack4(qlo[0])), rt_uint_as_float(pack4(qlo[0] + 4)), rt_uint_as_float(pack4(qlo[1])), rt_uint_as_float(pack4(qlo[1] + 4)));
-    node[3] = make_float4(rt_uint_as_float(pack4(qlo[2])), rt_uint_as_float(pack4(qlo[2] + 4)), rt_uint_as_float(pack4(qhi[0])), rt_uint_as_float(pack4(qhi[0] + 4)));
-    node[4] = make_float4(rt_uint_as_float(pack4(qhi[1])), rt_uint_as_float(pack4(qhi[1] + 4)), rt_uint_as_float(pack4(qhi[2])), rt_uint_as_float(pack4(qhi[2] + 4)));
+    node[1] = make_float4(rt_uint_as_float(child_base), rt_uint_as_float(prim_base), rt_uint_as_float(meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24)),
+                          rt_uint_as_float(meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24)));
+    for (int a = 0; a < 3; ++a) {
+        node[2 + 2 * a] = make_float4(rt_uint_as_float(w[a][0]), rt_uint_as_float(w[a][1]), rt_uint_as_float(w[a][2]), rt_uint_as_float(w[a][3]));
+        node[3 + 2 * a] = make_float4(rt_uint_as_float(w[a][4]), rt_uint_as_float(w[a][5]), rt_uint_as_float(w[a][6]), rt_uint_as_float(w[a][7]));
+    }
 }
 
 // One collapse work item: binary subtree `bin` becomes wide node `wide`.
@@ -532,8 +525,7 @@ RT_D void refit_wide_node(float4* nodes, DAabb* node_box, const DAabb* leaf_boxe
 #ifndef RT_EMU
 // Warp-cooperative refit: 8 lanes per wide node (one per child slot), 4 nodes per warp.  Same arithmetic as
 // refit_wide_node / write_wide_node (identical node bytes), but the per-child work — fetching the child's box, the
-// "does it fit in 8 bits" test of the exponent search, the 6 quantisations — runs in parallel and the slot results are
-// combined with shuffles.  The one-thread-per-node version spent 384 us on the 150 k nodes of config 4's character
+// six conservative bfloat16 roundings — runs in parallel; every lane stores its own three plane words.  The one-thread-per-node version spent 384 us on the 150 k nodes of config 4's character
 // (a single lane per warp busy with ~2 k double-precision instructions per node).
 // Bottom-up order: groups start at nodes without inner children; the group that completes a parent's last pending
 // child (atomic counter) continues with the parent.
@@ -572,42 +564,23 @@ __global__ void __launch_bounds__(256) refit_nodes_kernel(float4* nodes, DAabb* 
         }
         const bool any = __ballot_sync(gmask, valid) != 0u;
         if (!any) for (int a = 0; a < 3; ++a) { blo[a] = 0.0f; bhi[a] = 0.0f; }
-        uint32_t q[6]; int ex[3];
+        // this slot's three plane words + the node's plane bound (same arithmetic as write_wide_node: identical bytes)
+        uint32_t hi_max = 0u;
+        uint32_t* words = reinterpret_cast<uint32_t*>(node);
         for (int a = 0; a < 3; ++a) {
-            const double ext = (double)bhi[a] - (double)blo[a];
-            int e = -100;
-            if (ext > 0.0) { int fe; frexp(ext / 255.0, &fe); e = fe; if (e < -100) e = -100; }
-            for (;;) {
-                const bool ok = !valid || !(ceil(((double)hi[a] - (double)blo[a]) / ldexp(1.0, e)) > 255.0);
-                if (__ballot_sync(gmask, !ok) == 0u) break;
-                ++e;
+            uint32_t wv = RT_PLANE_EMPTY;
+            if (valid) {
+                const uint32_t l = bf16_lo_plane(lo[a], blo[a]), h = bf16_hi_plane(hi[a], blo[a]);
+                wv = (h << 16) | l;
+                if (h > hi_max) hi_max = h;
             }
-            ex[a] = e;
-            if (!valid) { q[a] = 255u; q[3 + a] = 0u; }
-            else {
-                const double sc = ldexp(1.0, e);
-                double l = floor(((double)lo[a] - (double)blo[a]) / sc), h = ceil(((double)hi[a] - (double)blo[a]) / sc);
-                if (l < 0.0) l = 0.0; if (l > 255.0) l = 255.0;
-                if (h < 0.0) h = 0.0; if (h > 255.0) h = 255.0;
-                q[a] = (uint32_t)l; q[3 + a] = (uint32_t)h;
-            }
+            words[8 + 8 * a + slot] = wv;
         }
-        // pack: slots 0..3 -> word 0, slots 4..7 -> word 1 of each of the six byte planes
-        uint32_t w0[6], w1[6];
-        for (int k = 0; k < 6; ++k) {
-            uint32_t v = q[k] << (8u * (slot & 3u));
-            v |= __shfl_xor_sync(gmask, v, 1); v |= __shfl_xor_sync(gmask, v, 2);
-            const uint32_t other = __shfl_xor_sync(gmask, v, 4);
-            w0[k] = slot < 4u ? v : other; w1[k] = slot < 4u ? other : v;
-        }
+        for (int d = 1; d < 8; d <<= 1) { const uint32_t o = __shfl_xor_sync(gmask, hi_max, d); hi_max = o > hi_max ? o : hi_max; }
         if (slot == 0u) {
             DAabb box; for (int a = 0; a < 3; ++a) { box.lo[a] = blo[a]; box.hi[a] = bhi[a]; }
             node_box[w] = box;
-            const uint32_t e_imask = (uint32_t)((ex[0] + 127) & 0xFF) | ((uint32_t)((ex[1] + 127) & 0xFF) << 8) | ((uint32_t)((ex[2] + 127) & 0xFF) << 16) | (imask << 24);
-            node[0] = make_float4(blo[0], blo[1], blo[2], __uint_as_float(e_imask));
-            node[2] = make_float4(__uint_as_float(w0[0]), __uint_as_float(w1[0]), __uint_as_float(w0[1]), __uint_as_float(w1[1]));
-            node[3] = make_float4(__uint_as_float(w0[2]), __uint_as_float(w1[2]), __uint_as_float(w0[3]), __uint_as_float(w1[3]));
-            node[4] = make_float4(__uint_as_float(w0[4]), __uint_as_float(w1[4]), __uint_as_float(w0[5]), __uint_as_float(w1[5]));
+            node[0] = make_float4(blo[0], blo[1], blo[2], __uint_as_float(plane_bound_exponent(hi_max) | (imask << 24)));
         }
         const uint32_t p = parent[w];
         if (p == 0xFFFFFFFFu) return;

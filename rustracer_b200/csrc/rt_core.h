@@ -1276,7 +1276,7 @@ int RT_API(rt_scene_bvh_info)(rt_scene* s, rt_bvh_info* o) {
     for (auto& g : s->geo) if (g.needed) o->blas_nodes += g.n_nodes;
     o->blas_nodes += s->merged.n_nodes;
     o->blas_tris = s->total_tris; o->tlas_nodes = s->tlas_nodes;
-    o->bytes = o->blas_nodes * 80ull + o->blas_tris * 48ull + o->tlas_nodes * 80ull + (uint64_t)s->instances.size() * (64 + 48);
+    o->bytes = o->blas_nodes * (uint64_t)RT_NODE_BYTES + o->blas_tris * 48ull + o->tlas_nodes * (uint64_t)RT_NODE_BYTES + (uint64_t)s->instances.size() * (64 + 48);
     o->max_depth_blas = s->blas_depth; o->max_depth_tlas = s->tlas_depth;
     o->build_ms = s->build_ms; o->refit_ms = s->refit_ms; o->skin_ms = s->skin_ms; o->tlas_ms = s->tlas_ms;
     return 0;

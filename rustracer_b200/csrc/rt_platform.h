@@ -59,6 +59,7 @@ static inline uint32_t rt_float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4)
 static inline float rt_uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline float rt_byte_to_biased_float(uint32_t v, int i) { return rt_uint_as_float(0x4B000000u | ((v >> (8 * i)) & 0xFFu)); }
 static inline uint32_t rt_byte_of(uint32_t v, int i) { return (v >> (8 * i)) & 0xFFu; }
+static inline void rt_opaque(uint32_t&) {}
 static inline uint32_t rt_shl_wrap(uint32_t v, uint32_t amount) { return v << (amount & 31u); }
 static inline int rt_clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int rt_clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
@@ -133,6 +134,7 @@ RT_D float rt_rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : 
 //  the second operand ptxas rematerialised the selector into a register before every one of the 48 PRMTs of a node)
 RT_D float rt_byte_to_biased_float(uint32_t v, int i) { return __uint_as_float(__byte_perm(0x4B000000u, v, 0x3004u + (uint32_t)i)); }
 RT_D uint32_t rt_byte_of(uint32_t v, int i) { return __byte_perm(v, 0u, 0x4440u + (uint32_t)i); }          // one PRMT
+RT_D void rt_opaque(uint32_t& v) { asm("" : "+r"(v)); }   // hides a value's provenance from the optimiser (no instruction)
 RT_D uint32_t rt_shl_wrap(uint32_t v, uint32_t amount) { return __funnelshift_l(0u, v, amount); }            // SHF.L.W: low 5 bits of amount
 RT_D float rt_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 RT_D uint32_t rt_float_as_uint(float f) { return __float_as_uint(f); }

@@ -3,15 +3,22 @@
 #include "../../include/rt_b200.h"
 #include "rt_math.h"
 
-// 8-wide compressed BVH node, 80 bytes = 5 x float4 (Ylitie, Karras, Laine 2017 layout):
-//   n0: origin.xyz (f32)              | ex, ey, ez (int8 exponents), imask (bit i: slot i is an inner node)
+// 8-wide BVH node, 128 bytes = 8 x float4 = exactly one cache line (children of a node are contiguous, Ylitie-Karras-Laine
+// style, but the child planes are bfloat16 instead of 8-bit grid coordinates):
+//   n0: origin.xyz (f32, = the node box's low corner) | imask << 24 | E      (imask bit i: slot i is an inner node;
+//                                                                             2^(E-127) >= every plane value of the node)
 //   n1: child_base (u32) | prim_base (u32) | meta[0..3] | meta[4..7]
-//   n2: qlo_x[0..3] qlo_x[4..7] qlo_y[0..3] qlo_y[4..7]
-//   n3: qlo_z[0..3] qlo_z[4..7] qhi_x[0..3] qhi_x[4..7]
-//   n4: qhi_y[0..3] qhi_y[4..7] qhi_z[0..3] qhi_z[4..7]
+//   n2, n3: x planes of children 0..3, 4..7   n4, n5: y planes   n6, n7: z planes
+//           one 32-bit word per child and axis: (hi_bf16 << 16) | lo_bf16, planes relative to the origin (>= 0),
+//           lo rounded down, hi rounded up.  Read as a float the word IS the hi plane (the lo bits underneath only enlarge
+//           it by less than one bf16 ulp: conservative); word << 16 is the lo plane exactly.  So the slab test needs no
+//           byte permutes / int->float conversions at all (they saturated the alu pipe with the 8-bit layout, profiles/r02):
+//           an integer multiply by 1 or 65536 (fma pipe) picks the near / far plane by ray direction.
+//           Empty slot: lo = +inf, hi = 0.
 // meta[i]: 0 = empty; inner: 0b001_xxxxx with xxxxx = 24 + slot; leaf: top 3 bits = unary count (1 -> 001,
 // 2 -> 011, 3 -> 111), low 5 bits = first primitive offset (0..23) relative to prim_base.
-#define RT_NODE_F4 5
+#define RT_NODE_F4 8
+#define RT_NODE_BYTES (RT_NODE_F4 * 16)
 #define RT_O2W_F4 4
 #ifndef RT_LEAF_MAX
 #define RT_LEAF_MAX 3

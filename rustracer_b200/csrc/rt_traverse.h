@@ -71,25 +71,30 @@ RT_D uint32_t byte_of(uint32_t v, int i) { return (v >> (8 * i)) & 0xFFu; }
 RT_D float safe_rcp_dir(float d) { return rt_rcp_approx(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }   // slab test is padded: 1-ulp rcp is fine
 RT_D uint32_t octant_inv(f3 d) { return 7u - ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u)); }
 
-// Intersects the 8 quantised child boxes of one node.  Returns the hit mask: bits 24..31 inner children in
-// traversal priority order (slot ^ octinv), bits 0..23 leaf primitives.
-// The quantised byte q is turned into the float 2^23 + q by a byte permute (no int->float conversion: those run
-// on the quarter-rate XU pipe and dominated the first version of this kernel) and the 2^23 bias is folded into
-// the per-node plane constants.  Rounding of those constants costs at most half a quantisation step; the slab
-// distances are therefore padded by one full step plus the rounding error of the de-quantisation, so the test
-// never rejects a box the ray touches (conservative; ~1 % larger boxes).
-RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
+// Intersects the 8 child boxes of one node.  Returns the hit mask: bits 24..31 inner children in traversal priority
+// order (slot ^ octinv), bits 0..23 leaf primitives.
+// Child planes are bfloat16 pairs packed as (hi << 16 | lo) relative to the node origin (rt_scene_dev.h).  The word read as
+// a float is the hi plane (enlarged by < 1 bf16 ulp by the lo bits: conservative), word * 65536 is the lo plane; which of
+// the two is the near plane depends on the ray direction only, so the choice is an integer multiply by a per-ray constant
+// (1 or 65536): IMAD + FFMA on the fma pipe, no PRMT / SEL / I2F on the alu pipe, which the 8-bit layout saturated.
+// Rounding: c and the products carry a few ulp of their magnitudes; the slab distances are padded by EPS times those
+// magnitudes (2^(E-127) bounds the plane values), so the test never rejects a box the ray touches.
+RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 x03, const float4 x47, const float4 y03, const float4 y47, const float4 z03, const float4 z47,
                              f3 o, f3 idir, uint32_t octinv, float tmin, float tmax) {
     const uint32_t n0w = rt_float_as_uint(n0.w);
-    const float sx = rt_uint_as_float((((n0w >> 0) & 0xFFu)) << 23), sy = rt_uint_as_float((((n0w >> 8) & 0xFFu)) << 23), sz = rt_uint_as_float((((n0w >> 16) & 0xFFu)) << 23);
-    const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
-    const float ox = (n0.x - o.x) * idir.x, oy = (n0.y - o.y) * idir.y, oz = (n0.z - o.z) * idir.z;
+    const float bound = rt_uint_as_float((n0w & 0xFFu) << 23);
+    const float cx = (n0.x - o.x) * idir.x, cy = (n0.y - o.y) * idir.y, cz = (n0.z - o.z) * idir.z;
     const float EPS = 1.0e-6f;   // ~16 ulp of the magnitudes involved
-    const float px = fmaf(EPS, fabsf(ox) + 255.0f * fabsf(ax), fabsf(ax)), py = fmaf(EPS, fabsf(oy) + 255.0f * fabsf(ay), fabsf(ay)), pz = fmaf(EPS, fabsf(oz) + 255.0f * fabsf(az), fabsf(az));
-    const float BIAS = 8388608.0f;   // 2^23
-    const float cxn = fmaf(-BIAS, ax, ox - px), cxf = fmaf(-BIAS, ax, ox + px);
-    const float cyn = fmaf(-BIAS, ay, oy - py), cyf = fmaf(-BIAS, ay, oy + py);
-    const float czn = fmaf(-BIAS, az, oz - pz), czf = fmaf(-BIAS, az, oz + pz);
+    const float px = EPS * fmaf(bound, fabsf(idir.x), fabsf(cx)), py = EPS * fmaf(bound, fabsf(idir.y), fabsf(cy)), pz = EPS * fmaf(bound, fabsf(idir.z), fabsf(cz));
+    const float cxn = cx - px, cxf = cx + px, cyn = cy - py, cyf = cy + py, czn = cz - pz, czf = cz + pz;
+    // near / far plane multipliers from the sign bit of the direction: 1 (hi plane) / 65536 (lo plane).  Written as
+    // arithmetic on the sign bit so that the products below stay integer multiply-adds on the fma pipe (a select between
+    // the constants is strength-reduced to shifts on the alu pipe); recomputed per node: they cost less than the three
+    // registers they would occupy in the 64-register kernel
+    const uint32_t sx = rt_float_as_uint(idir.x) >> 31, sy = rt_float_as_uint(idir.y) >> 31, sz = rt_float_as_uint(idir.z) >> 31;
+    uint32_t mnx = 65536u - sx * 65535u, mny = 65536u - sy * 65535u, mnz = 65536u - sz * 65535u;
+    uint32_t mfx = 1u + sx * 65535u, mfy = 1u + sy * 65535u, mfz = 1u + sz * 65535u;
+    rt_opaque(mnx); rt_opaque(mny); rt_opaque(mnz); rt_opaque(mfx); rt_opaque(mfy); rt_opaque(mfz);
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -99,16 +104,15 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 n2, 
         const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
         const uint32_t bit_index4 = (meta4 ^ ((octinv * 0x01010101u) & inner_mask4 & 0x07070707u)) & 0x1F1F1F1Fu;
         const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = rt_float_as_uint(half ? n2.y : n2.x), qloy = rt_float_as_uint(half ? n2.w : n2.z), qloz = rt_float_as_uint(half ? n3.y : n3.x);
-        const uint32_t qhix = rt_float_as_uint(half ? n3.w : n3.z), qhiy = rt_float_as_uint(half ? n4.y : n4.x), qhiz = rt_float_as_uint(half ? n4.w : n4.z);
-        const uint32_t nx = idir.x < 0.0f ? qhix : qlox, fx = idir.x < 0.0f ? qlox : qhix;
-        const uint32_t ny = idir.y < 0.0f ? qhiy : qloy, fy = idir.y < 0.0f ? qloy : qhiy;
-        const uint32_t nz = idir.z < 0.0f ? qhiz : qloz, fz = idir.z < 0.0f ? qloz : qhiz;
+        const float4 xw = half ? x47 : x03, yw = half ? y47 : y03, zw = half ? z47 : z03;
+        const uint32_t xs[4] = {rt_float_as_uint(xw.x), rt_float_as_uint(xw.y), rt_float_as_uint(xw.z), rt_float_as_uint(xw.w)};
+        const uint32_t ys[4] = {rt_float_as_uint(yw.x), rt_float_as_uint(yw.y), rt_float_as_uint(yw.z), rt_float_as_uint(yw.w)};
+        const uint32_t zs[4] = {rt_float_as_uint(zw.x), rt_float_as_uint(zw.y), rt_float_as_uint(zw.z), rt_float_as_uint(zw.w)};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float tnx = fmaf(rt_byte_to_biased_float(nx, j), ax, cxn), tfx = fmaf(rt_byte_to_biased_float(fx, j), ax, cxf);
-            const float tny = fmaf(rt_byte_to_biased_float(ny, j), ay, cyn), tfy = fmaf(rt_byte_to_biased_float(fy, j), ay, cyf);
-            const float tnz = fmaf(rt_byte_to_biased_float(nz, j), az, czn), tfz = fmaf(rt_byte_to_biased_float(fz, j), az, czf);
+            const float tnx = fmaf(rt_uint_as_float(xs[j] * mnx), idir.x, cxn), tfx = fmaf(rt_uint_as_float(xs[j] * mfx), idir.x, cxf);
+            const float tny = fmaf(rt_uint_as_float(ys[j] * mny), idir.y, cyn), tfy = fmaf(rt_uint_as_float(ys[j] * mfy), idir.y, cyf);
+            const float tnz = fmaf(rt_uint_as_float(zs[j] * mnz), idir.z, czn), tfz = fmaf(rt_uint_as_float(zs[j] * mfz), idir.z, czf);
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
             // child_bits << bit_index: one PRMT for the byte, a wrapping shift that only looks at the low 5 bits of its amount
@@ -162,7 +166,7 @@ RT_D void trav_leave_blas(Trav& t, const DScene& S) {
 }
 
 // The traversal is a "while-while" loop (Aila & Laine 2009) over two kinds of steps:
-//   node step : precondition tgroup empty.  Visits the next inner child of ngroup (one 80-byte node, 8 box tests) or,
+//   node step : precondition tgroup empty.  Visits the next inner child of ngroup (one 128-byte node, 8 box tests) or,
 //               when ngroup holds no more inner children, leaves the BLAS / pops the stack.  Returns true when the
 //               ray has no work left.
 //   prim step : precondition tgroup non-empty.  Takes one primitive of tgroup: a triangle (watertight test, alpha
@@ -183,9 +187,9 @@ RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
         const uint32_t slot = (uint32_t)(child_bit - 24) ^ (t.octinv & 7u);
         const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
         const float4* np = (SINGLE ? S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4 : t.nodes) + (size_t)(child_base + rel) * RT_NODE_F4;
-        const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4);
+        const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4), n5 = rt_ld(np + 5), n6 = rt_ld(np + 6), n7 = rt_ld(np + 7);
         if (COUNT) c4[0]++;
-        const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, t.o, t.idir, t.octinv, t.tmin, t.hit.t);
+        const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, n5, n6, n7, t.o, t.idir, t.octinv, t.tmin, t.hit.t);
         t.ngroup.x = rt_float_as_uint(n1.x); t.tgroup.x = rt_float_as_uint(n1.y);
         t.ngroup.y = (hm & 0xFF000000u) | (rt_float_as_uint(n0.w) >> 24);
         t.tgroup.y = hm & 0x00FFFFFFu;

@@ -266,7 +266,7 @@ def case_skinning(api):
     # refit is idempotent: refitting with the pose the BVH was built from reproduces the built nodes byte for byte
     # (child boxes are exact min / max unions either way), and so does a rebuild (deterministic builder)
     built = sc.read_nodes(-1)
-    assert built.shape[0] >= 2 and built.shape[1] == 20
+    assert built.shape[0] >= 2 and built.shape[1] == 32
     sc.update_skins(pose(0.0), rebuild=False)
     assert (sc.read_nodes(-1) == built).all()
     # a rebuild allocates child / primitive ranges with atomics, so nodes may be numbered differently from run to run:
