@@ -143,22 +143,27 @@ RT_D void skin_transform(float4 (&r)[8], const float* skins, uint32_t n_skins) {
         const float* bones = skins + (size_t)skin_index * (RT_MAX_JOINTS * 16);
         const float w[4] = {r[4].x, r[4].y, r[4].z, r[4].w};
         const uint32_t j[4] = {rt_float_as_uint(r[5].x), rt_float_as_uint(r[5].y), rt_float_as_uint(r[5].z), rt_float_as_uint(r[5].w)};
+        // M = sum_k w_k * bones[joint_k], position / normal / tangent = M * v: every operation explicitly rounded, in the
+        // oracle's order (oracle.cpp::skin_vertices, g++ -ffp-contract=off) -> the skinned vertices are bit-identical
+        const float4* bm0 = reinterpret_cast<const float4*>(bones + (size_t)(j[0] & (RT_MAX_JOINTS - 1)) * 16);
+        const float4* bm1 = reinterpret_cast<const float4*>(bones + (size_t)(j[1] & (RT_MAX_JOINTS - 1)) * 16);
+        const float4* bm2 = reinterpret_cast<const float4*>(bones + (size_t)(j[2] & (RT_MAX_JOINTS - 1)) * 16);
+        const float4* bm3 = reinterpret_cast<const float4*>(bones + (size_t)(j[3] & (RT_MAX_JOINTS - 1)) * 16);
         float M[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) M[k] = 0.0f;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const float4* bm = reinterpret_cast<const float4*>(bones + (size_t)(j[b] & (RT_MAX_JOINTS - 1)) * 16);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float4 col = rt_ld(bm + c);
-                if (b == 0) { M[c * 4] = w[0] * col.x; M[c * 4 + 1] = w[0] * col.y; M[c * 4 + 2] = w[0] * col.z; M[c * 4 + 3] = w[0] * col.w; }
-                else { M[c * 4] += w[b] * col.x; M[c * 4 + 1] += w[b] * col.y; M[c * 4 + 2] += w[b] * col.z; M[c * 4 + 3] += w[b] * col.w; }
-            }
+        for (int c = 0; c < 4; ++c) {
+            const float4 c0 = rt_ld(bm0 + c), c1 = rt_ld(bm1 + c), c2 = rt_ld(bm2 + c), c3 = rt_ld(bm3 + c);
+            M[c * 4 + 0] = rt_fadd(rt_fadd(rt_fadd(rt_fmul(w[0], c0.x), rt_fmul(w[1], c1.x)), rt_fmul(w[2], c2.x)), rt_fmul(w[3], c3.x));
+            M[c * 4 + 1] = rt_fadd(rt_fadd(rt_fadd(rt_fmul(w[0], c0.y), rt_fmul(w[1], c1.y)), rt_fmul(w[2], c2.y)), rt_fmul(w[3], c3.y));
+            M[c * 4 + 2] = rt_fadd(rt_fadd(rt_fadd(rt_fmul(w[0], c0.z), rt_fmul(w[1], c1.z)), rt_fmul(w[2], c2.z)), rt_fmul(w[3], c3.z));
+            M[c * 4 + 3] = rt_fadd(rt_fadd(rt_fadd(rt_fmul(w[0], c0.w), rt_fmul(w[1], c1.w)), rt_fmul(w[2], c2.w)), rt_fmul(w[3], c3.w));
         }
-        const f4 pos = mat4_mul(M, mk4(r[0].x, r[0].y, r[0].z, 1.0f));
-        const f3 nn = normalize(xyz(mat4_mul(M, mk4(r[1].x, r[1].y, r[1].z, 0.0f))));
-        const f4 tt = normalize(mat4_mul(M, mk4(r[2].x, r[2].y, r[2].z, 0.0f)));
+        const f4 pos = mat4_mul_exact(M, mk4(r[0].x, r[0].y, r[0].z, 1.0f));
+        const f3 nn = normalize_exact(xyz(mat4_mul_exact(M, mk4(r[1].x, r[1].y, r[1].z, 0.0f))));
+        const f4 t4 = mat4_mul_exact(M, mk4(r[2].x, r[2].y, r[2].z, 0.0f));
+        // normalize(vec4): the w component of M * (t, 0) takes part in the length (AnimationCompute.comp:36), w itself is restored
+        const float tl = sqrtf(rt_fadd(rt_fadd(rt_fadd(rt_fmul(t4.x, t4.x), rt_fmul(t4.y, t4.y)), rt_fmul(t4.z, t4.z)), rt_fmul(t4.w, t4.w)));
+        const f3 tt = mk3(rt_fdiv(t4.x, tl), rt_fdiv(t4.y, tl), rt_fdiv(t4.z, tl));
         r[0].x = pos.x; r[0].y = pos.y; r[0].z = pos.z;
         r[1].x = nn.x; r[1].y = nn.y; r[1].z = nn.z;
         r[2].x = tt.x; r[2].y = tt.y; r[2].z = tt.z;   // w (handedness) kept

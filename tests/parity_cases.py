@@ -282,16 +282,44 @@ def case_skinning(api):
             mats = pose(phase)
             sc.update_skins(mats, rebuild=(k == 2)); o.update_skins(mats)
         vg, vo = sc.read_vertices(n), o.read_vertices(n)
-        # AnimationCompute.comp: positions within 1 ulp-ish (FMA contraction differs), skin_index etc. untouched
-        np.testing.assert_allclose(vg["position"], vo["position"], rtol=2e-6, atol=2e-6)
-        np.testing.assert_allclose(vg["normal"], vo["normal"], rtol=1e-5, atol=1e-5)
+        # AnimationCompute.comp: explicitly rounded operations in the oracle's order on both sides -> positions, normals and
+        # tangents bit-exact (SURVEY.md §8d "Skinning kernel: bit-exact vs oracle under the same fma policy")
+        for f in ("position", "normal", "tangent"):
+            assert (vg[f].view(np.uint32) == vo[f].view(np.uint32)).all(), (f, np.abs(vg[f] - vo[f]).max())
         assert (vg["joints"] == vo["joints"]).all() and (vg["skin_index"] == vo["skin_index"]).all()
-        # trace against an oracle scene built from the GPU's own skinned vertices would hide skinning errors;
-        # instead compare hit/miss agreement and t within 1e-4 (the vertex positions differ by rounding)
-        hg, ho = sc.trace_closest(rays, 1), o.trace_closest(rays, 1)
-        both = (hg["t"] > 0) & (ho["t"] > 0)
-        assert ((hg["t"] > 0) != (ho["t"] > 0)).mean() < 0.002
-        np.testing.assert_allclose(hg["t"][both], ho["t"][both], rtol=1e-3, atol=1e-4)
+        # identical vertices -> identical triangles: closest hits bit-exact through refit and rebuild alike
+        check_ids(sc, o, rays, 1, what=f"skinned pose {k}")
+
+
+def case_shadows_glb(api, d, z, frames=(0, 7, 23, 41, 59), size=128, n_rays=100000, spp=2):
+    """The reference's shadows.glb through its loader-produced animation (fixture tests/golden/shadows_glb_scene.npz):
+    per frame rt_scene_update_skins (skinning kernel + BLAS refit + TLAS refit, main.rs:384-395) then vertices, closest hits,
+    shadow-ray occlusion and a rendered image with NEE (point light on, textured base colour) against the oracle."""
+    o = orc.OracleScene(d)
+    ctx, sc = make(api, d, size, size)
+    rays, rng4 = util.random_rays(n_rays, seed=17, extent=5.0)
+    cam = host.Camera(size, size).set(position=(0.0, 0.0, 9.0)); gui = host.Gui(number_of_samples=spp, number_of_bounces=5, animation=1)
+    d1, d2 = host.FrameDriver(cam, gui, d.fully_opaque), host.FrameDriver(cam, gui, d.fully_opaque)
+    moved = 0.0
+    v0 = sc.read_vertices()
+    for f in frames:
+        mats = util.expand_skins(z["anim_skins"][f])
+        sc.update_skins(mats); o.update_skins(mats)
+        vg, vo = sc.read_vertices(), o.read_vertices(d.n_vertices)
+        for name in ("position", "normal", "tangent"):
+            assert (vg[name].view(np.uint32) == vo[name].view(np.uint32)).all(), (f, name)
+        moved = max(moved, float(np.abs(vg["position"] - v0["position"]).max()))
+        check_ids(sc, o, rays, 1, what=f"shadows.glb frame {f}")
+        u = d1.next_ubo(); ctx.render(sc, u); acc, out, st = o.render(d2.next_ubo(), size, size, None)
+        acc_g, out_g = ctx.readback()
+        mre, ps = util.mean_rel_err(acc_g, acc, spp), util.psnr(out_g[..., :3], out[..., :3])
+        assert mre < MRE_TOL and ps >= PSNR_TOL, (f, mre, ps)
+        sg = ctx.stats()
+        assert st.rays_shadow > 0 and abs(int(sg.rays_shadow) - int(st.rays_shadow)) <= 0.003 * st.rays_shadow + 2     # NEE is live
+        brays, brng, srays, srng = bounce_ray_sets(o, u, size, size, max_rays=20000, max_shadow=20000)
+        check_ids(sc, o, brays, 0, brng, what=f"shadows.glb bounce rays frame {f}")
+        check_any(sc, o, srays, 0, srng, what=f"shadows.glb shadow rays frame {f}")
+    assert moved > 0.05          # the animation really deforms the character
 
 
 def case_lucy_ids(api, n_rays=100000, rows=120, cols=121):

@@ -68,6 +68,66 @@ def test_lucy_scene_ids_and_image(api):
     assert abs(int(s.rays_extend) - int(st.rays_extend)) <= 0.002 * st.rays_extend
 
 
+def test_shadows_glb_loader_driven_animation(api):
+    """Real-asset animated path on the GPU (SURVEY.md §8d config 4 'small real-asset variant', §8f row 2): the committed
+    loader output of the reference's shadows.glb drives rt_scene_update_skins for five animation frames; vertices, ids,
+    shadow rays and NEE images against the oracle."""
+    d, z = util.load_scene_full(util.GOLDEN / "shadows_glb_scene.npz")
+    pc.case_shadows_glb(api, d, z)
+
+
+def _full_size_compare(api, d, o, W, H, frames, cam_pos, gui_kw, opaque, rows=None):
+    ctx = core.Context(W, H, api=api); sc = core.Scene(ctx, d)
+    cam = host.Camera(W, H).set(position=cam_pos); gui = host.Gui(**gui_kw)
+    d1, d2 = host.FrameDriver(cam, gui, opaque), host.FrameDriver(cam, gui, opaque)
+    acc = None
+    for _ in range(frames):
+        ctx.render(sc, d1.next_ubo()); acc, out, st = o.render(d2.next_ubo(), W, H, acc, rows=rows)
+    acc_g, out_g = ctx.readback()
+    r0, r1 = rows if rows else (0, H)
+    total = d1.total.value
+    mre = util.mean_rel_err(acc_g[r0:r1], acc[r0:r1], total); ps = util.psnr(out_g[r0:r1, :, :3], out[r0:r1, :, :3])
+    assert mre < pc.MRE_TOL and ps >= pc.PSNR_TOL, (mre, ps)
+    return ctx, sc, mre, ps
+
+
+def test_config1_full_size_image_and_debug_channels(api, cornell_desc, cornell_oracle):
+    """BASELINE configs[0] at its stated size: the bundled CornellBox (real asset fixture) 512x512, 64 frames x 1 spp, depth 8,
+    reference default camera (app/src/lib.rs:331-338) — converged image within MRE < 1 % / PSNR >= 40 dB of the oracle's,
+    and the deterministic debug channels at 512x512: instance / triangle ids exact, albedo / normal within 1 LSB."""
+    W = H = 512
+    ctx, sc, mre, ps = _full_size_compare(api, cornell_desc, cornell_oracle, W, H, 64, (0, 0, 1.0), dict(number_of_samples=1, number_of_bounces=8), cornell_desc.fully_opaque)
+    for mapping, tol in ((2, 0), (3, 0), (11, 0), (5, 1), (8, 1)):      # INSTANCE, TRIANGLE, GEO_ID exact; ALBEDO, NORMAL <= 1 LSB
+        ctx.resize(W, H)
+        cam = host.Camera(W, H); gui = host.Gui(number_of_samples=1, number_of_bounces=8, mapping=mapping, antialiasing=0)
+        u1 = host.FrameDriver(cam, gui, cornell_desc.fully_opaque).next_ubo(); u2 = host.FrameDriver(cam, gui, cornell_desc.fully_opaque).next_ubo()
+        ctx.render(sc, u1); acc, out, _ = cornell_oracle.render(u2, W, H, None)
+        acc_g, out_g = ctx.readback()
+        diff = np.abs(out_g.astype(int) - out.astype(int))
+        assert diff.max() <= 1, (mapping, int(diff.max()))                   # RGBA8 after the pow() of the tone map: 1 LSB
+        if tol == 0:    # id channels: the linear value (no transcendental involved) is bit-exact at every one of the 262 144 pixels
+            assert (acc_g.view(np.uint32) == acc.view(np.uint32)).all(), (mapping, int((acc_g != acc).sum()))
+
+
+def test_config2_full_size_image_vs_oracle(api):
+    """BASELINE configs[1] at its stated size: Lucy-in-Cornell stand-in (real shell + 448 868-triangle stand-in) 1920x1080,
+    16 frames x 1 spp accumulated, depth 8, reference default camera — the bench's exact workload — against the oracle."""
+    from oracle import orc
+    d = scenes.cornell_box(lucy=True, shell=util.GOLDEN / "cornell_box_scene.npz")
+    assert d.n_indices // 3 == 465588
+    o = orc.OracleScene(d)
+    _full_size_compare(api, d, o, 1920, 1080, 16, (0, 0, 1.0), dict(number_of_samples=1, number_of_bounces=8), True)
+
+
+def test_config5_crop_vs_oracle(api):
+    """BASELINE configs[4] (3840x2160, 64 glass / volume objects): a 96-row band of the 4K frame, 4 frames x 1 spp, against
+    the oracle rendering the same rows (the GPU renders the whole frame)."""
+    from oracle import orc
+    d = scenes.glass_box(n_objects=64)
+    o = orc.OracleScene(d)
+    _full_size_compare(api, d, o, 3840, 2160, 4, (0, 0, 14.0), dict(number_of_samples=1, number_of_bounces=8), bool(d.fully_opaque), rows=(1032, 1128))
+
+
 def test_full_size_properties(api):
     """1920x1080 depth 8 (BASELINE size), properties that need no oracle run: determinism, tile-partition identity,
     accumulation bookkeeping (acc == sum of per-frame radiance), alpha channel / finite output."""

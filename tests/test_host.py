@@ -165,6 +165,38 @@ def test_skinned_animated_glb_end_to_end():
     assert util.hits_equal(a, b).all()
 
 
+SHADOWS = util.GOLDEN / "shadows_glb_scene.npz"
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference assets only exist in the build container")
+def test_shadows_glb_fixture_is_what_the_loader_produces():
+    """tests/golden/shadows_glb_scene.npz (committed, drives the GPU-box tests) == the host loader's output for the
+    reference's shadows.glb, including the loader-driven animation frames (make_shadows_fixture.py)."""
+    d, z = util.load_scene_full(SHADOWS)
+    doc = host.load_file(REF / "shadows.glb"); ld = doc.scene_desc()
+    for name, ct in (("vertices", F.rt_vertex), ("instances", F.rt_instance), ("materials", F.rt_material), ("plights", F.rt_light), ("dlights", F.rt_light)):
+        assert util._arr(getattr(d, name), getattr(d, "n_" + name), ct) == util._arr(getattr(ld, name), getattr(ld, "n_" + name), ct), name
+    assert util._arr(d.indices, d.n_indices, F.c_u32) == util._arr(ld.indices, ld.n_indices, F.c_u32)
+    assert d.n_images == ld.n_images == 2 and C.string_at(d.images[1].rgba8, 1024 * 1024 * 4) == C.string_at(ld.images[1].rgba8, 1024 * 1024 * 4)
+    for f in (0, 13, 59):
+        doc.animate(float(z["anim_times"][f]))
+        assert (util.expand_skins(z["anim_skins"][f]) == doc.get_skins()).all(), f
+        assert z["anim_instances"][f].tobytes() == doc.get_instances().tobytes(), f
+
+
+def test_shadows_glb_fixture_animation_oracle_vs_emulation():
+    """The committed shadows.glb fixture (CesiumMan, 19 joints, textured, point light of intensity 20) animated by its
+    loader-produced skin matrices: skinned vertices bit-exact and closest hits bit-exact, CUDA sources (host emulation) vs
+    the oracle.  The same fixture drives rt_scene_update_skins on the B200 in tests/test_gpu_parity.py."""
+    from emu_lib import emu_api
+    from oracle import orc
+    from rustracer_b200 import core
+    import parity_cases as pc
+    d, z = util.load_scene_full(SHADOWS)
+    assert d.n_skins == 1 and d.n_plights == 1 and d.plights[0].intensity == 20.0 and z["anim_skins"].shape[:3] == (60, 1, 19)
+    pc.case_shadows_glb(emu_api(), d, z, frames=(7, 41), size=40, n_rays=3000)
+
+
 def _test_image(w, h, seed=1):
     rng = np.random.default_rng(seed)
     y, x = np.mgrid[0:h, 0:w]

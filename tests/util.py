@@ -122,3 +122,72 @@ def mean_rel_err(acc_a, acc_b, total_samples):
     la = (acc_a[..., :3].astype(np.float64) / total_samples) @ w
     lb = (acc_b[..., :3].astype(np.float64) / total_samples) @ w
     return float(np.mean(np.abs(la - lb) / (lb + 1e-3)))
+
+
+# ---- full scene fixtures (skinned + textured assets): every array of rt_scene_desc -------------------------------------
+def save_scene_full(d: F.rt_scene_desc, path, image_files=None, **extra):
+    """Writes every array of an rt_scene_desc.  image_files: {image index: encoded PNG/JPEG bytes} — those images are
+    stored in their file encoding (decoded again with the host decoder by load_scene_full) instead of raw RGBA8."""
+    image_files = image_files or {}
+    z = dict(extra)
+    z["vertices"] = np.frombuffer(_arr(d.vertices, d.n_vertices, F.rt_vertex), np.uint8)
+    z["indices"] = np.frombuffer(_arr(d.indices, d.n_indices, F.c_u32), np.uint32)
+    z["prim_infos"] = np.frombuffer(_arr(d.prim_infos, d.n_geometries, F.rt_prim_info), np.uint32).reshape(-1, 4)
+    z["geometries"] = np.frombuffer(_arr(d.geometries, d.n_geometries, F.rt_geometry), np.uint32).reshape(-1, 4)
+    z["materials"] = np.frombuffer(_arr(d.materials, d.n_materials, F.rt_material), np.uint8).reshape(-1, 256)
+    z["instances"] = np.frombuffer(_arr(d.instances, d.n_instances, F.rt_instance), F.INSTANCE_DTYPE)
+    z["dlights"] = np.frombuffer(_arr(d.dlights, d.n_dlights, F.rt_light), F.LIGHT_DTYPE)
+    z["plights"] = np.frombuffer(_arr(d.plights, d.n_plights, F.rt_light), F.LIGHT_DTYPE)
+    z["samplers"] = np.array([[s.mag_filter, s.min_filter, s.wrap_s, s.wrap_t] for s in d.samplers[:d.n_samplers]], np.uint32).reshape(-1, 4)
+    z["textures"] = np.array([[t.image_index, t.sampler_index] for t in d.textures[:d.n_textures]], np.uint32).reshape(-1, 2)
+    z["image_meta"] = np.array([[im.width, im.height, im.srgb, 1 if k in image_files else 0] for k, im in enumerate(d.images[:d.n_images])], np.uint32).reshape(-1, 4)
+    for k, im in enumerate(d.images[:d.n_images]):
+        z[f"image_{k}"] = np.frombuffer(image_files[k], np.uint8) if k in image_files else \
+            np.frombuffer(C.string_at(im.rgba8, im.width * im.height * 4), np.uint8)
+    if d.n_skins:
+        sk = np.frombuffer(_arr(d.skins, d.n_skins * 4096, F.c_f), np.float32).reshape(d.n_skins, 256, 16)
+        used = int(np.nonzero(np.abs(sk).sum(axis=(0, 2)))[0].max()) + 1
+        z["skins"] = sk[:, :used].copy(); z["n_skins"] = np.uint32(d.n_skins)
+    np.savez_compressed(path, **z)
+
+
+def expand_skins(sk: np.ndarray) -> np.ndarray:
+    """[n_skins, used_joints, 16] -> SkinRaw layout [n_skins, 256, 16] (unused joints zero, as the loader leaves them)."""
+    out = np.zeros((sk.shape[0], 256, 16), np.float32)
+    out[:, :sk.shape[1]] = sk
+    return out
+
+
+def load_scene_full(path):
+    """-> (rt_scene_desc, npz).  Encoded images are decoded with the host layer's own PNG / JPEG decoder."""
+    from rustracer_b200 import host
+    z = np.load(path)
+    keep = {k: np.ascontiguousarray(z[k]) for k in ("indices", "prim_infos", "geometries", "materials", "instances", "dlights", "plights")}
+    keep["v"] = np.frombuffer(z["vertices"].tobytes(), F.VERTEX_DTYPE).copy()
+    meta = z["image_meta"]; px = []
+    for k, (w, h, srgb, enc) in enumerate(meta):
+        a = z[f"image_{k}"]
+        img = host.decode_image(a.tobytes()) if enc else a.reshape(h, w, 4)
+        assert img.shape == (h, w, 4), (img.shape, w, h)
+        px.append(np.ascontiguousarray(img, np.uint8))
+    keep["px"] = px
+    keep["img"] = (F.rt_image_desc * max(1, len(px)))(*[F.rt_image_desc(p.ctypes.data_as(F.c_u8p), int(m[0]), int(m[1]), int(m[2]), 0) for p, m in zip(px, meta)])
+    keep["smp"] = (F.rt_sampler_desc * max(1, len(z["samplers"])))(*[F.rt_sampler_desc(*[int(x) for x in s]) for s in z["samplers"]])
+    keep["tex"] = (F.rt_texture_desc * max(1, len(z["textures"])))(*[F.rt_texture_desc(int(t[0]), int(t[1])) for t in z["textures"]])
+    d = F.rt_scene_desc()
+    d.vertices, d.n_vertices = F.as_ptr(keep["v"], F.rt_vertex), len(keep["v"])
+    d.indices, d.n_indices = F.as_ptr(keep["indices"], F.c_u32), len(keep["indices"])
+    d.prim_infos = keep["prim_infos"].ctypes.data_as(C.POINTER(F.rt_prim_info))
+    d.geometries, d.n_geometries = keep["geometries"].ctypes.data_as(C.POINTER(F.rt_geometry)), len(keep["geometries"])
+    d.materials, d.n_materials = keep["materials"].ctypes.data_as(C.POINTER(F.rt_material)), len(keep["materials"])
+    d.instances, d.n_instances = F.as_ptr(keep["instances"], F.rt_instance), len(keep["instances"])
+    d.images, d.n_images, d.samplers, d.n_samplers = keep["img"], len(px), keep["smp"], len(z["samplers"])
+    d.textures, d.n_textures = keep["tex"], len(z["textures"])
+    d.dlights, d.n_dlights = F.as_ptr(keep["dlights"], F.rt_light), len(keep["dlights"])
+    d.plights, d.n_plights = F.as_ptr(keep["plights"], F.rt_light), len(keep["plights"])
+    if "skins" in z.files:
+        keep["sk"] = expand_skins(z["skins"])
+        d.skins, d.n_skins = F.as_ptr(keep["sk"], F.c_f), int(z["n_skins"])
+    d._keep = keep
+    d.fully_opaque = bool((keep["materials"].view(np.uint32)[:, 0] == 1).all())
+    return d, z
