@@ -322,8 +322,14 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
     # sample-pass sharding (§8e B): global frame g = step * world + rank; every rank starts from a zero accumulation
     from rustracer_b200 import sharding
-    ubos = [frame_ubo(cam, gui, sharding.global_frame(s, rank, world), desc.fully_opaque) for s in range(Wm + K)]
-    final_ubo = frame_ubo(cam, gui, (Wm + K) * world - 1, desc.fully_opaque)
+    tiles = args.partition == "tiles" and world > 1
+    if tiles:      # strong scaling (§8e A): every rank renders its interleaved 8-row strips of the SAME global frame s
+        ubos = [frame_ubo(cam, gui, s, desc.fully_opaque) for s in range(Wm + K)]
+        final_ubo = ubos[-1]
+    else:          # weak scaling (§8e B): rank r renders whole global frames s * world + r into a private sum
+        ubos = [frame_ubo(cam, gui, sharding.global_frame(s, rank, world), desc.fully_opaque) for s in range(Wm + K)]
+        final_ubo = frame_ubo(cam, gui, (Wm + K) * world - 1, desc.fully_opaque)
+    combine_every = args.combine_every if args.combine_every >= 0 else (64 if CONFIG == 5 else 0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -337,14 +343,34 @@ def run_ours(args):
         if poses is not None:     # config 4: skin upload + skinning kernel + BLAS refit + TLAS refit belong to the step
             scene.update_skins(poses[s])
 
+    epoch = [0]
+    side = torch.cuda.Stream(device=local)      # periodic display refreshes run beside the frames (§8d config 5)
+
+    def combine(ubo, on_side=False):
+        """the exchange step, device-synchronised (rt_combine): no host-side wait, no barrier"""
+        if world == 1:
+            return
+        epoch[0] += 1
+        if tiles:      # rooted gather of the strips' RGBA8 (the frame is presented on rank 0)
+            ctx.combine(peers, ubo, epoch[0], tiles=(8, world, rank), gather_to=(F.RT_GATHER_NONE if rank == 0 else 0),
+                        n_senders=(world - 1 if rank == 0 else 0), stream=stream)
+        else:          # fused reduce + tonemap of this rank's band + all-gather: every rank ends up with the complete image
+            ctx.combine(peers, ubo, epoch[0], rows=(row0, row1), stream=(side.cuda_stream if on_side else stream))
+
+    def render_step(s, flags=0, exchange=True):
+        pre_step(s)
+        if tiles:
+            ctx.render(scene, ubos[s], flags=flags, strip_rows=8, n_parts=world, part=rank, stream=stream)
+            if exchange:
+                combine(ubos[s])
+        else:
+            ctx.render(scene, ubos[s], flags=flags, stream=stream)
+            if exchange and combine_every and (s + 1) % combine_every == 0 and s + 1 < Wm + K:
+                combine(frame_ubo(cam, gui, (s + 1) * world - 1, desc.fully_opaque), on_side=True)
+
     def frames(lo, hi, flags=0):
         for s in range(lo, hi):
-            pre_step(s)
-            ctx.render(scene, ubos[s], flags=flags, stream=stream)
-
-    def combine():
-        if world > 1:
-            ctx.api.check(ctx.api.rt_reduce_peers(ctx._h, peer_arr, len(peers), C.byref(final_ubo), row0, row1, stream))
+            render_step(s, flags, exchange=False)
 
     # ---- device-timed run: inputs resident, K frames (+ final cross-GPU reduce) ----
     # frames in flight (the reference's InFlightFrames, app/src/lib.rs:34): the path tracing of NF consecutive frames
@@ -358,17 +384,9 @@ def run_ours(args):
     # clears in place and a size change is refused while a handle is exported
     peers = []
     if world > 1:
-        handle = (C.c_uint8 * 64)()
-        ctx.api.check(ctx.api.rt_ipc_export(ctx._h, handle))
         gathered = [None] * world
-        dist.all_gather_object(gathered, bytes(handle))
-        for r, hb in enumerate(gathered):
-            if r == rank:
-                continue
-            p = C.c_void_p(); buf = (C.c_uint8 * 64).from_buffer_copy(hb)
-            ctx.api.check(ctx.api.rt_ipc_open(ctx._h, buf, C.byref(p)))
-            peers.append(p.value)
-    peer_arr = (C.c_void_p * max(1, len(peers)))(*peers)
+        dist.all_gather_object(gathered, ctx.ipc_handle())
+        peers = [ctx.ipc_open(hb) for r, hb in enumerate(gathered) if r != rank]     # accumulation blocks of the other ranks, in rank order
     row0, row1 = sharding.reduce_rows(rank, world, HEIGHT)
 
     frames(0, Wm)
@@ -380,22 +398,17 @@ def run_ours(args):
     e0.record()
     t_loop0 = time.perf_counter()
     for s in range(Wm, Wm + K):
-        pre_step(s)
-        ctx.render(scene, ubos[s], stream=stream)
-    t_sub = time.perf_counter()
-    t_enq = t_sub - t_loop0
-    if world > 1:
-        ctx.synchronize(); t_sync = time.perf_counter()
-        dist.barrier()                         # all ranks must have finished rendering before peers are read
-        t_bar = time.perf_counter()
-        combine()
-    ctx.join(stream)                           # the timing stream waits (on the device) for every frame in flight
+        render_step(s)
+    if not tiles:
+        combine(final_ubo)                     # all ranks' sums -> the complete tonemapped image on every rank; synchronised on the device
+    t_enq = time.perf_counter() - t_loop0
+    ctx.join(stream)                           # the timing stream waits (on the device) for every frame in flight and for the combine
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     if world > 1 and os.environ.get("BENCH_DEBUG"):
-        print(f"[rank {rank}] timed region {ms:.3f} ms; host: enqueue {1e3 * t_enq:.3f} ms, submit->sync {1e3 * (t_sync - t_sub):.3f} ms, barrier {1e3 * (t_bar - t_sync):.3f} ms; clocks {clocks}", file=sys.stderr, flush=True)
+        print(f"[rank {rank}] timed region {ms:.3f} ms; host enqueue {1e3 * t_enq:.3f} ms; clocks {clocks}", file=sys.stderr, flush=True)
     tmax = torch.tensor([ms], device="cuda")
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -408,8 +421,7 @@ def run_ours(args):
     tot = dict.fromkeys(COUNTER_KEYS, 0)
     ext_ms, launches, n_ext = 0.0, 0, 0
     for s in range(Wm, Wm + K):
-        pre_step(s)
-        ctx.render(scene, ubos[s], flags=1 | 4, stream=stream)
+        render_step(s, flags=1 | 4, exchange=False)
         st = ctx.stats()
         for k, v in stats_dict(st).items():
             tot[k] += v
@@ -420,8 +432,7 @@ def run_ours(args):
     stage = dict(raygen=0.0, extend=0.0, shade=0.0, shadow=0.0, accum=0.0)
     upd = dict(skin_ms=0.0, refit_ms=0.0, tlas_ms=0.0)
     for s in range(Wm, Wm + K):
-        pre_step(s)
-        ctx.render(scene, ubos[s], flags=4, stream=stream)
+        render_step(s, flags=4, exchange=False)
         st = ctx.stats()
         if poses is not None:      # update stages event-timed one frame at a time (nothing else runs on the GPU)
             bi = scene.bvh_info()
@@ -445,7 +456,7 @@ def run_ours(args):
     out_np = [p.numpy() for p in pinned]
     ctx.resize(WIDTH, HEIGHT)
     for s in range(0, Wm):
-        pre_step(s); ctx.render(scene, ubos[s], stream=stream); ctx.frame_wait(ctx.readback_async(out_np[s % HB]))
+        render_step(s, exchange=False); ctx.frame_wait(ctx.readback_async(out_np[s % HB]))
     ctx.synchronize()
     barrier()
     t0 = time.perf_counter()
@@ -455,8 +466,7 @@ def run_ours(args):
     for s in range(Wm, Wm + K):
         if len(tickets) >= HB:
             ctx.frame_wait(tickets[-HB])                   # the image of frame s-HB is in host memory; its buffer is reused now
-        pre_step(s)                                        # config 4: 256 mat4 (16 KB) host -> device per step
-        ctx.render(scene, ubos[s], stream=stream)
+        render_step(s, exchange=False)                     # config 4: 256 mat4 (16 KB) host -> device per step
         tickets.append(ctx.readback_async(out_np[s % HB]))  # device -> pinned host, 4 B/pixel, behind the frame
     for t in tickets[-HB:]:
         ctx.frame_wait(t)                                  # every step's result has reached the host inside the timed region
@@ -468,6 +478,37 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = rays_all / (float(t_e2e.item()) * 1e-3) / 1e6
+
+    # ---- the exchange step alone, two ways (outside the headline region): the fused peer-memory kernel vs NCCL ----
+    exchange = None
+    if world > 1 and not tiles:
+        ctx.set_frames_in_flight(NF); ctx.synchronize()
+        reps = 10
+
+        class _Cai:     # torch view of the RGBA32F accumulation image (zero copy) for the NCCL arm
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+        acc_ptr, _ = ctx.device_ptrs()
+        acc_t = torch.as_tensor(_Cai(acc_ptr, (HEIGHT, WIDTH, 4)), device=f"cuda:{local}")
+        scratch = acc_t.clone()
+        for arm in ("fused", "nccl"):
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(reps):
+                if arm == "fused":
+                    combine(final_ubo)
+                else:       # "NCCL accumulation reduce" (BASELINE.json): all-reduce of the sums, then every rank tonemaps the whole image
+                    dist.all_reduce(scratch)
+                    ctx.tonemap(final_ubo, stream=stream)
+            ctx.join(stream); c1.record(); torch.cuda.synchronize()
+            t = torch.tensor([c0.elapsed_time(c1) / reps], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            exchange = (exchange or {}) | {arm + "_ms": float(t.item())}
+        disp, _ = ctx.readback_display()
+        exchange |= {"fused": "rt_combine: snapshot + ONE kernel (peer loads of the other ranks' sums for this rank's band, tonemap, peer stores of the RGBA8 band into every rank's display) + device-side flags",
+                     "nccl": "torch.distributed all_reduce (NCCL) of the RGBA32F sums + rt_tonemap of the whole image on every rank",
+                     "bytes_rgba32f": WIDTH * HEIGHT * 16, "complete_image_on_this_rank": bool((disp[..., 3] == 255).all()),
+                     "periodic_every_steps": combine_every}
 
     # ---- second, labelled figure: the round-1 camera outside the box (not the headline; kept for continuity) ----
     alt = None
@@ -536,9 +577,11 @@ def run_ours(args):
             except Exception as ex:   # the oracle is test infrastructure; its absence must not break the GPU arm
                 cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(desc),      # identical keys / values in both arms
-                "engine": {"parallelism": f"sample-pass sharding x{world} (frames g = step*{world}+rank), fused peer-memory reduce+tonemap at the end",
+                "engine": {"parallelism": (f"tile partition x{world}: every frame split into interleaved 8-row strips, RGBA8 strips gathered on rank 0 every step (rt_combine, rooted)" if tiles else
+                                           f"sample-pass sharding x{world} (frames g = step*{world}+rank); rt_combine at the end: fused peer-memory reduce + tonemap + all-gather, device-side flags, no host barrier"),
+                           "exchange": exchange,
                            "frames_in_flight": NF,
                            "bvh": {"nodes": int(info.blas_nodes), "depth": int(info.max_depth_blas), "bytes": int(info.bytes), "build_s": build_s,
                                    "build_ms_device": float(info.build_ms), "tlas_ms_device": float(info.tlas_ms)}},
@@ -563,6 +606,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene-versions", type=int, default=3, help="config 4: copies of the buffers a skin update rewrites (2..4)")
+    ap.add_argument("--partition", default="samples", choices=["samples", "tiles"],
+                    help="N > 1: samples = whole frames per rank, private sums, fused combine (weak scaling, default); tiles = every frame split into interleaved 8-row strips (strong scaling)")
+    ap.add_argument("--combine-every", type=int, default=-1, help="sample passes: periodic display combine every N steps on a side stream (default: 64 for config 5, else off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-camera", action="store_true", help="skip the second (round-1 camera) figure of config 2")
     ap.add_argument("--size", default=None, help="WxH override (experiments only; the headline size is 1920x1080)")

@@ -353,6 +353,63 @@ int rt_ipc_close(rt_context* ctx, void* peer_acc);
 int rt_reduce_peers(rt_context* ctx, void* const* peer_acc, uint32_t n_peers, const rt_ubo* ubo,
                     uint32_t row0, uint32_t row1, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU combine, device-synchronised (supersedes rt_reduce_peers)
+ * ------------------------------------------------------------------------------------------
+ * Every context's accumulation image heads ONE device allocation, the "accumulation block":
+ *     [ acc RGBA32F | snap RGBA32F | display RGBA8 | sync words ]
+ * rt_ipc_export / rt_ipc_open (other processes) or rt_combine_ptrs (same process, peer access enabled) hand the block's
+ * base pointer to the other GPUs.  rt_combine then runs, on each rank and without any host-side wait:
+ *   snapshot acc -> snap; publish the epoch; wait (on the device) for the peers' snapshots of the same epoch;
+ *   ONE kernel: sum the peers' snap rows of this rank's band over NVLink peer loads, tonemap (RayTracing.rgen:132-166),
+ *   store the RGBA8 band into the own display AND (peer stores) into the peers' displays = reduce-scatter + tonemap +
+ *   all-gather fused; notify the peers; wait until the bands this rank receives have landed.
+ * acc is only read: frames keep accumulating while a combine is in flight (periodic display refresh on a side stream,
+ * §8d config 5 "reduce every 64 frames").  After the call has completed on `stream`, the display holds the complete
+ * tonemapped image (on every rank for RT_GATHER_ALL, on the root for a rooted gather) and snap holds the reduced RGBA32F
+ * band of this rank (the whole image on the root with gather_acc).  With n_parts > 1 (tile partition, §8e A) nothing is
+ * summed: each rank contributes the strips it rendered (bit-identical to the single-GPU image).
+ * A peer that never shows up makes the device-side waits give up after ~5 s; rt_readback_display then reports it. */
+enum { RT_GATHER_ALL = -1, RT_GATHER_NONE = -2 };
+typedef struct rt_combine_desc {
+    void* const* peer_blocks;   /* accumulation-block base pointers of the other ranks (rt_ipc_open / rt_combine_ptrs) */
+    uint32_t n_peers;           /* <= 8 */
+    uint32_t epoch;             /* 1, 2, 3, ... : the n-th combine; the same value on every rank */
+    uint32_t row0, row1;        /* sample passes: the row band this rank reduces and tonemaps */
+    uint32_t strip_rows, n_parts, part;   /* tiles (n_parts > 1): the strips this rank rendered (rt_render_opts) */
+    int32_t  gather_to;         /* who receives this rank's band: RT_GATHER_ALL, RT_GATHER_NONE or an index into peer_blocks */
+    uint32_t n_senders;         /* how many ranks store their band into THIS rank's display (n_peers for RT_GATHER_ALL / on the root, else 0) */
+    uint32_t gather_acc;        /* != 0 with a rooted gather: the reduced RGBA32F bands are assembled in the root's snap as well */
+} rt_combine_desc;
+int rt_combine(rt_context* ctx, const rt_combine_desc* desc, const rt_ubo* ubo, void* stream);
+/* synchronises, then copies the display image (and, optionally, snap = the reduced RGBA32F image / band) to the host */
+int rt_readback_display(rt_context* ctx, uint8_t* out_rgba8, float* sum_rgba32f);
+/* same-process peers: base pointer and size of the accumulation block, device pointer of the display image */
+int rt_combine_ptrs(rt_context* ctx, void** block, void** display, uint64_t* block_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * One process, several GPUs (SURVEY.md §8b last row: "rt_context_create with n > 1 devices => replicas; partition mode
+ * enum {TILES, SAMPLE_PASSES}").  The reference is a single process (app/src/lib.rs:133-252): rt_multi gives it N device
+ * replicas behind one handle — contexts with peer access enabled in every direction, one scene replica per device
+ * (deterministic builder: identical trees), frames partitioned by mode, rt_combine for the exchange.
+ * ---------------------------------------------------------------------------------------- */
+enum { RT_PARTITION_TILES = 0, RT_PARTITION_SAMPLE_PASSES = 1 };
+typedef struct rt_multi rt_multi;
+int  rt_multi_create(const int* devices, uint32_t n_devices, uint32_t width, uint32_t height, uint32_t mode, rt_multi** out);
+void rt_multi_destroy(rt_multi* m);
+/* replaces the scene upload + AS build on every replica */
+int  rt_multi_scene_create(rt_multi* m, const rt_scene_desc* desc);
+/* TILES: every device renders its interleaved 8-row strips of THIS frame (latency mode; image bit-identical to one GPU).
+   SAMPLE_PASSES: the frame goes, whole, to device (frames submitted so far) % n (throughput mode; private RGBA32F sums). */
+int  rt_multi_render(rt_multi* m, const rt_ubo* ubo);
+/* the exchange step: rt_combine on every device (rooted gather to device 0 incl. the RGBA32F sum), asynchronous */
+int  rt_multi_combine(rt_multi* m, const rt_ubo* ubo);
+/* rt_multi_combine if frames were submitted since the last one, then the complete image from device 0 (either may be NULL) */
+int  rt_multi_readback(rt_multi* m, const rt_ubo* ubo, float* acc_rgba32f, uint8_t* out_rgba8);
+int  rt_multi_synchronize(rt_multi* m);
+/* replica i, for calls this interface does not wrap (rt_scene_update_*, rt_last_frame_stats, ...) */
+int  rt_multi_replica(rt_multi* m, uint32_t i, rt_context** ctx, rt_scene** scene);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,16 @@ class rt_scene_desc(C.Structure):
     ]
 
 
+class rt_combine_desc(C.Structure):
+    _fields_ = [("peer_blocks", C.POINTER(C.c_void_p)), ("n_peers", c_u32), ("epoch", c_u32), ("row0", c_u32), ("row1", c_u32),
+                ("strip_rows", c_u32), ("n_parts", c_u32), ("part", c_u32), ("gather_to", C.c_int32), ("n_senders", c_u32),
+                ("gather_acc", c_u32)]
+
+
+RT_GATHER_ALL, RT_GATHER_NONE = -1, -2
+RT_PARTITION_TILES, RT_PARTITION_SAMPLE_PASSES = 0, 1
+
+
 class rt_ray(C.Structure):
     _fields_ = [("origin", c_f * 3), ("tmin", c_f), ("direction", c_f * 3), ("tmax", c_f)]
 
@@ -173,7 +183,14 @@ RT_EXPORTS = [
     "rt_trace_any", "rt_scene_read_vertices", "rt_scene_bvh_info", "rt_ipc_export", "rt_ipc_open",
     "rt_ipc_close", "rt_reduce_peers", "rt_context_set_frames_in_flight", "rt_join", "rt_readback_async",
     "rt_frame_wait", "rt_scene_read_nodes", "rt_scene_set_versions",
+    "rt_combine", "rt_readback_display", "rt_combine_ptrs",
+    "rt_multi_create", "rt_multi_destroy", "rt_multi_scene_create", "rt_multi_render", "rt_multi_combine",
+    "rt_multi_readback", "rt_multi_synchronize", "rt_multi_replica",
 ]
+# multi-GPU entry points: CUDA-only (the test-only host emulation has no peers to talk to)
+RT_CUDA_ONLY = ("rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_reduce_peers", "rt_combine", "rt_readback_display", "rt_combine_ptrs",
+                "rt_multi_create", "rt_multi_destroy", "rt_multi_scene_create", "rt_multi_render", "rt_multi_combine",
+                "rt_multi_readback", "rt_multi_synchronize", "rt_multi_replica")
 GV_EXPORTS = [
     "gv_last_error", "gv_load_file", "gv_doc_free", "gv_doc_scene_desc", "gv_doc_fully_opaque",
     "gv_doc_static_scene", "gv_doc_need_compute", "gv_doc_aabb_trans", "gv_doc_animate", "gv_doc_get_skins",
@@ -263,6 +280,17 @@ def bind_rt(lib: C.CDLL, rename=lambda n: n, optional=()) -> C.CDLL:
         "rt_frame_wait": ([vp, C.c_uint64], C.c_int),
         "rt_scene_set_versions": ([vp, c_u32], C.c_int),
         "rt_scene_read_nodes": ([vp, C.c_int, C.POINTER(c_f), c_u32, C.POINTER(c_u32)], C.c_int),
+        "rt_combine": ([vp, C.POINTER(rt_combine_desc), C.POINTER(rt_ubo), vp], C.c_int),
+        "rt_readback_display": ([vp, c_u8p, C.POINTER(c_f)], C.c_int),
+        "rt_combine_ptrs": ([vp, vpp, vpp, C.POINTER(C.c_uint64)], C.c_int),
+        "rt_multi_create": ([C.POINTER(C.c_int), c_u32, c_u32, c_u32, c_u32, vpp], C.c_int),
+        "rt_multi_destroy": ([vp], None),
+        "rt_multi_scene_create": ([vp, C.POINTER(rt_scene_desc)], C.c_int),
+        "rt_multi_render": ([vp, C.POINTER(rt_ubo)], C.c_int),
+        "rt_multi_combine": ([vp, C.POINTER(rt_ubo)], C.c_int),
+        "rt_multi_readback": ([vp, C.POINTER(rt_ubo), C.POINTER(c_f), c_u8p], C.c_int),
+        "rt_multi_synchronize": ([vp], C.c_int),
+        "rt_multi_replica": ([vp, c_u32, vpp, vpp], C.c_int),
     }
     assert set(sigs) == set(RT_EXPORTS)
     for name, (args, res) in sigs.items():

@@ -104,6 +104,39 @@ class Context:
         self.api.check(self.api.rt_device_ptrs(self._h, C.byref(a), C.byref(o)))
         return a.value, o.value
 
+    # ---- multi-GPU combine (include/rt_b200.h "Multi-GPU combine, device-synchronised") ----
+    def ipc_handle(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self.api.check(self.api.rt_ipc_export(self._h, h))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self.api.check(self.api.rt_ipc_open(self._h, (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(p)))
+        return p.value
+
+    def combine_ptrs(self):
+        b, d, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self.api.check(self.api.rt_combine_ptrs(self._h, C.byref(b), C.byref(d), C.byref(n)))
+        return b.value, d.value, int(n.value)
+
+    def combine(self, peers, ubo: F.rt_ubo, epoch: int, rows=(0, 0), tiles=None, gather_to=F.RT_GATHER_ALL, n_senders=None,
+                gather_acc=False, stream=None):
+        """rt_combine: fused peer-memory reduce + tonemap + gather of this rank's band.  peers: accumulation-block pointers of
+        the other ranks.  tiles = (strip_rows, n_parts, part) for the tile partition."""
+        arr = (C.c_void_p * max(1, len(peers)))(*peers)
+        d = F.rt_combine_desc(arr, len(peers), epoch, rows[0], rows[1], 0, 0, 0, gather_to,
+                              (len(peers) if gather_to == F.RT_GATHER_ALL else 0) if n_senders is None else n_senders, int(gather_acc))
+        if tiles:
+            d.strip_rows, d.n_parts, d.part = tiles
+        self.api.check(self.api.rt_combine(self._h, C.byref(d), C.byref(ubo), stream))
+
+    def readback_display(self, want_sum: bool = False):
+        out = np.empty((self.height, self.width, 4), np.uint8)
+        acc = np.empty((self.height, self.width, 4), np.float32) if want_sum else None
+        self.api.check(self.api.rt_readback_display(self._h, out.ctypes.data_as(F.c_u8p), F.as_ptr(acc, F.c_f) if want_sum else None))
+        return out, acc
+
     def stats(self) -> F.rt_stats:
         st = F.rt_stats()
         self.api.check(self.api.rt_last_frame_stats(self._h, C.byref(st)))
@@ -189,3 +222,40 @@ class Scene:
         info = F.rt_bvh_info()
         self.api.check(self.api.rt_scene_bvh_info(self._h, C.byref(info)))
         return info
+
+
+class Multi:
+    """rt_multi: one process, several GPUs (SURVEY.md §8b last row).  mode: F.RT_PARTITION_TILES (every device renders its
+    strips of each frame; bit-identical to one GPU) or F.RT_PARTITION_SAMPLE_PASSES (whole frames round-robin)."""
+
+    def __init__(self, devices, width: int, height: int, mode: int, api: Api | None = None):
+        self.api = api or Api()
+        self.width, self.height, self.n = width, height, len(devices)
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        self.api.check(self.api.rt_multi_create(arr, len(devices), width, height, mode, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.api.rt_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def scene(self, desc: F.rt_scene_desc):
+        self.api.check(self.api.rt_multi_scene_create(self._h, C.byref(desc)))
+
+    def render(self, ubo: F.rt_ubo):
+        self.api.check(self.api.rt_multi_render(self._h, C.byref(ubo)))
+
+    def combine(self, ubo: F.rt_ubo):
+        self.api.check(self.api.rt_multi_combine(self._h, C.byref(ubo)))
+
+    def synchronize(self):
+        self.api.check(self.api.rt_multi_synchronize(self._h))
+
+    def readback(self, ubo: F.rt_ubo):
+        acc = np.empty((self.height, self.width, 4), np.float32); out = np.empty((self.height, self.width, 4), np.uint8)
+        self.api.check(self.api.rt_multi_readback(self._h, C.byref(ubo), F.as_ptr(acc, F.c_f), out.ctypes.data_as(F.c_u8p)))
+        return acc, out

@@ -93,6 +93,13 @@ struct rt_context {
     rt_stream_t last_stream = nullptr;   // stream of the most recent rt_render / rt_tonemap (may be caller-provided)
     uint32_t width = 0, height = 0;
     float4* acc = nullptr;               // RGBA32F accumulation image shared by all slots (RayTracing.rgen:18)
+    // multi-GPU combine (rt_combine): the accumulation image is the head of ONE allocation [acc | snap | display | sync]
+    // so that a single CUDA IPC handle (or peer pointer) gives the other GPUs everything they touch:
+    float4* snap = nullptr;              //   snapshot of acc a combine works on (frames keep accumulating meanwhile)
+    uint32_t* display = nullptr;         //   combined, tonemapped RGBA8 image (every rank's band lands here: all-gather)
+    uint32_t* sync = nullptr;            //   RT_SYNC_* words written / polled across GPUs (device-side flags, no host barrier)
+    rt_event ev_combine; bool combine_pending = false; rt_stream_t combine_stream = nullptr;   // the last rt_combine (possibly on a side stream)
+    uint32_t combine_epoch = 0, recv_expected = 0;   // combines issued so far / display bands expected so far (RT_SYNC_RECV)
     FrameSlot slot[RT_MAX_FRAMES_IN_FLIGHT];
     uint32_t n_slots = 1, cur = 0;       // cur: slot of the most recently submitted frame
     uint64_t frame_seq = 0;              // frames submitted so far (ticket of the next frame)
@@ -162,8 +169,13 @@ static void free_slot(FrameSlot* f) {
 static void free_frame(rt_context* c) {
     for (uint32_t k = 0; k < RT_MAX_FRAMES_IN_FLIGHT; ++k) free_slot(&c->slot[k]);
     if (c->acc) rt_free(c->acc);
-    c->acc = nullptr;
+    c->acc = nullptr; c->snap = nullptr; c->display = nullptr; c->sync = nullptr;
 }
+// byte offsets inside the accumulation block (the same arithmetic locates a peer's snap / display / sync from its base)
+static inline size_t acc_block_snap(size_t n) { return n * sizeof(float4); }
+static inline size_t acc_block_display(size_t n) { return 2 * n * sizeof(float4); }
+static inline size_t acc_block_sync(size_t n) { return 2 * n * sizeof(float4) + ((n * 4 + 255) & ~(size_t)255); }
+static inline size_t acc_block_bytes(size_t n) { return acc_block_sync(n) + 256; }
 
 static int alloc_slot(rt_context* c, FrameSlot* f, size_t n) {
     int e = 0;
@@ -185,8 +197,12 @@ static int alloc_slot(rt_context* c, FrameSlot* f, size_t n) {
 static int alloc_frame(rt_context* c, uint32_t w, uint32_t h) {
     free_frame(c);
     const size_t n = (size_t)w * h;
-    if (dev_alloc(&c->acc, n)) return 1;
-    rt_memset(c->acc, 0, n * sizeof(float4), c->stream);
+    if (rt_malloc((void**)&c->acc, acc_block_bytes(n))) return 1;
+    c->snap = reinterpret_cast<float4*>(reinterpret_cast<char*>(c->acc) + acc_block_snap(n));
+    c->display = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->acc) + acc_block_display(n));
+    c->sync = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->acc) + acc_block_sync(n));
+    c->combine_epoch = 0; c->recv_expected = 0;
+    rt_memset(c->acc, 0, acc_block_bytes(n), c->stream);
     for (uint32_t k = 0; k < c->n_slots; ++k) if (alloc_slot(c, &c->slot[k], n)) { free_frame(c); return 1; }
     c->width = w; c->height = h; c->cur = 0; c->acc_pending = false; c->consumer_pending = false;
     return rt_stream_sync(c->stream);
@@ -507,6 +523,7 @@ static uint32_t owned_rows(const TilePart& tp) {
 
 static int sync_all(rt_context* c) {
     int e = 0;
+    if (c->combine_pending) { e |= c->ev_combine.sync(); c->combine_pending = false; }    // a combine on a caller's side stream
     if (c->last_stream && c->last_stream != c->stream) e |= rt_stream_sync(c->last_stream);
     if (c->n_slots > 1) for (uint32_t k = 0; k < c->n_slots; ++k) if (c->slot[k].stream) e |= rt_stream_sync(c->slot[k].stream);
     e |= rt_stream_sync(c->stream);
@@ -519,7 +536,6 @@ static void join_frames(rt_context* c, rt_stream_t st) {
 }
 // a consumer of the accumulation image ran on `st`: later frames must not accumulate before it
 static void consumer_ran(rt_context* c, rt_stream_t st) {
-    if (c->n_slots <= 1) return;
     c->ev_consumer.record(st); c->consumer_pending = true;
 }
 
@@ -689,7 +705,7 @@ int RT_API(rt_context_create)(int device, uint32_t width, uint32_t height, rt_co
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("rt_context_create: stream creation failed"); }
     c->timers = true;
 #endif
-    c->ev_submit.create(); c->ev_acc.create(); c->ev_consumer.create();
+    c->ev_submit.create(); c->ev_acc.create(); c->ev_consumer.create(); c->ev_combine.create();
     for (auto& e : c->ticket_done) e.create();
     if (alloc_frame(c, width, height)) { RT_API(rt_context_destroy)(c); return fail(std::string("rt_context_create: allocation failed: ") + rt_platform_error()); }
     *out = c;
@@ -707,7 +723,7 @@ void RT_API(rt_context_destroy)(rt_context* c) {
         f.ev_begin.destroy(); f.ev_end.destroy(); f.done.destroy();
         rt_stream_destroy(f.stream);
     }
-    c->ev_submit.destroy(); c->ev_acc.destroy(); c->ev_consumer.destroy();
+    c->ev_submit.destroy(); c->ev_acc.destroy(); c->ev_consumer.destroy(); c->ev_combine.destroy();
     for (auto& e : c->ticket_done) e.destroy();
 #ifndef RT_EMU
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -726,7 +742,7 @@ int RT_API(rt_frame_resize)(rt_context* c, uint32_t width, uint32_t height) {
         // same size: drop the accumulation in place.  The allocation (and with it any CUDA IPC mapping a peer holds on the
         // accumulation image, rt_ipc_export) stays valid.
         const size_t n = (size_t)width * height;
-        rt_memset(c->acc, 0, n * sizeof(float4), c->stream);
+        rt_memset(c->acc, 0, n * sizeof(float4), c->stream);     // (snap / display / sync keep their combine state: peers may be mid-protocol)
         for (uint32_t k = 0; k < c->n_slots; ++k) {
             FrameSlot& f = c->slot[k];
             rt_memset(f.fb.out, 0, n * 4, c->stream); rt_memset(f.fb.rad, 0, n * sizeof(float4), c->stream); rt_memset(f.fb.aux, 0, n * sizeof(float2), c->stream);
@@ -1065,9 +1081,9 @@ int RT_API(rt_render)(rt_context* c, rt_scene* s, const rt_ubo* ubo, const rt_re
     FrameSlot* f = &c->slot[k];
     if (c->n_slots > 1) {
         c->ev_submit.record(st); c->ev_submit.wait(f->stream);
-        if (c->consumer_pending) c->ev_consumer.wait(f->stream);
         st = f->stream;
     }
+    if (c->consumer_pending) c->ev_consumer.wait(st);   // (a no-op when the consumer ran on this very stream)
     if (s->update_pending) s->ev_updated.wait(st);     // asynchronous skin update queued on the scene's stream
 #ifndef RT_EMU
     f->launches_before = g_rt_launch_count;
@@ -1135,7 +1151,9 @@ int RT_API(rt_device_ptrs)(rt_context* c, void** acc, void** out) {
 
 int RT_API(rt_join)(rt_context* c, void* stream) {
     if (!c) return fail("rt_join: null context");
-    join_frames(c, stream ? (rt_stream_t)stream : c->stream);
+    rt_stream_t st = stream ? (rt_stream_t)stream : c->stream;
+    join_frames(c, st);
+    if (c->combine_pending && c->combine_stream != st) c->ev_combine.wait(st);      // a combine queued on a side stream
     return 0;
 }
 

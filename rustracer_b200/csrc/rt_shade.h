@@ -483,6 +483,11 @@ RT_D uint32_t to_unorm8(float v) {
     if (v >= 1.0f) return 255u;
     return (uint32_t)rintf(v * 255.0f);
 }
+// RGBA8 of an accumulated radiance sum (RayTracing.rgen:150-166 without the debug overrides): used by the multi-GPU combine
+RT_D uint32_t tonemap_rgba8(const rt_ubo& ubo, f3 sum) {
+    const f3 color = tonemap(ubo.tone_mapping_mode, sum / (float)ubo.total_number_of_samples);
+    return to_unorm8(color.x) | (to_unorm8(color.y) << 8) | (to_unorm8(color.z) << 16) | 0xFF000000u;
+}
 // frame_rad: radiance gathered this frame (all samples).  last_t / n_traces feed the DISTANCE / HEAT mappings.
 RT_D void accumulate_pixel(const rt_ubo& ubo, float4* acc, uint32_t* out, size_t pixel, f3 frame_rad, float last_t, uint32_t n_traces) {
     const bool accumulate = ubo.number_of_samples != ubo.total_number_of_samples;

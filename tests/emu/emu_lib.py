@@ -11,7 +11,7 @@ from rustracer_b200.core import Api
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "_build" / "librt_emu.so"
-IPC = ("rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_reduce_peers")
+IPC = F.RT_CUDA_ONLY      # multi-GPU entry points exist in the CUDA library only
 _api = None
 
 

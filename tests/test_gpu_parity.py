@@ -255,6 +255,41 @@ def test_baseline_sized_configs_properties(api):
     assert (a0 == a1).all() and (o0 == o1).all() and np.isfinite(a0).all() and (o0[..., 3] == 255).all()
 
 
+def test_multi_device_interface_and_combine(api, cornell_desc):
+    """rt_multi (one process, n devices, {TILES, SAMPLE_PASSES}) and the device-synchronised rt_combine it
+    drives.  The GPU-test box has one B200, so the replicas are contexts on device 0 — the partition, the fused
+    reduce + tonemap + gather kernel and the flag protocol are the ones the 8-GPU runs use (tests/multigpu_check.py).
+    TILES: image and accumulation bit-identical to a single context.  SAMPLE_PASSES: sums agree within fp32 reassociation."""
+    W, H, K = 320, 192, 6
+    cam = host.Camera(W, H); gui = host.Gui(number_of_samples=1, number_of_bounces=6)
+    drv = host.FrameDriver(cam, gui, cornell_desc.fully_opaque)
+    ubos = [drv.next_ubo() for _ in range(K)]
+    ref = core.Context(W, H, api=api); rsc = core.Scene(ref, cornell_desc)
+    for u in ubos:
+        ref.render(rsc, u)
+    racc, rout = ref.readback()
+    for n in (1, 2, 3):
+        m = core.Multi([0] * n, W, H, F.RT_PARTITION_TILES, api=api); m.scene(cornell_desc)
+        for u in ubos:
+            m.render(u)
+        acc, out = m.readback(ubos[-1])
+        assert (acc == racc).all() and (out == rout).all(), ("tiles", n)
+        acc2, out2 = m.readback(ubos[-1])                      # nothing submitted since: same image, no second combine needed
+        assert (acc2 == racc).all() and (out2 == rout).all()
+        m.close()
+        m = core.Multi([0] * n, W, H, F.RT_PARTITION_SAMPLE_PASSES, api=api); m.scene(cornell_desc)
+        for k, u in enumerate(ubos):
+            m.render(u)
+            if k == 2:
+                m.combine(u)                                   # a periodic display refresh mid-way must not disturb the sums
+        acc, out = m.readback(ubos[-1])
+        np.testing.assert_allclose(acc, racc, rtol=2e-6, atol=1e-6)
+        assert np.abs(out.astype(int) - rout.astype(int)).max() <= 1, ("sample passes", n)
+        m.close()
+    with pytest.raises(core.RtError):
+        core.Multi([0, 99], W, H, F.RT_PARTITION_TILES, api=api)
+
+
 def test_errors_are_reported_not_swallowed(api, cornell_desc):
     ctx = core.Context(32, 32, api=api); sc = core.Scene(ctx, cornell_desc)
     u = F.rt_ubo()   # total_number_of_samples == 0
