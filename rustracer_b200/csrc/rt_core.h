@@ -501,6 +501,7 @@ static void compute_has_nee(rt_scene* s, const rt_light* pl, uint32_t n) {
         const float lum = 0.2126f * pl[i].color[0] * pl[i].intensity + 0.7152f * pl[i].color[1] * pl[i].intensity + 0.0722f * pl[i].color[2] * pl[i].intensity;
         if (!(lum < 0.1f)) s->has_nee = true;
     }
+    s->ds.nee_plights = s->has_nee ? n : 0u;
 }
 
 static int upload_sky(rt_scene* s, const uint8_t* const faces[6], uint32_t w, uint32_t h, uint32_t srgb) {

@@ -534,51 +534,73 @@ RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" :
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 8
 #endif
+#ifndef RT_SHADE_SORT
+#define RT_SHADE_SORT 1       // 1: material-sorted shading (CTA-local counting sort of each 128-path tile), 0: queue order
+#endif
+#define RT_SHADE_CLASSES 32   // class 0 = miss, 1..30 = material id (mod 30), 31 = no path (tail of the last tile)
+
+// Material-sorted closest-hit shading (north_star: "a material-sorted ... closest-hit shading pass").  The reference's
+// ubershader (RayTracing.rchit:136-477) branches on workflow / transmission / volume / texture bits per material; in queue
+// order a warp holds a random mix of them (18-19 of 32 lanes active after the first bounce, profiles/r02).  Each CTA
+// therefore takes a tile of 128 consecutive paths, reads only what the sort key needs (hit distance + instance ->
+// material id, two coalesced loads and one L1-resident gather), counting-sorts the tile by (miss | material) in shared
+// memory — warp-level match + a 128-entry block scan, ~70 instructions per path against ~1500 of shading — and thread t
+// then shades the t-th path of the sorted order.  Paths are independent, so the image is bit-identical to queue order;
+// only the order of the compacted next-bounce queue changes.
 template <bool SIMPLE, bool COUNT>
 __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene S, FrameParams P, FrameBuffers fb, DQueue qin, DHits hits, DQueue qout, DShadowQueue sq,
                                                     const uint32_t* count_ptr, uint32_t* out_count, uint32_t* shadow_count, uint32_t* hit_count, uint32_t bounce, RtCounters* cnt) {
     const uint32_t count = *count_ptr;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    // all lanes of a warp iterate together so the ballots below are convergent
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
-        const uint32_t i = base + lane;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#if RT_SHADE_SORT
+    __shared__ uint32_t s_hist[RT_SHADE_CLASSES * 4];     // [class][warp] counts, then exclusive offsets
+    __shared__ uint32_t s_wsum[4];
+    __shared__ uint8_t s_perm[128];
+#endif
+    // all threads of a CTA iterate together (barriers / ballots below are convergent)
+    for (uint32_t tile = blockIdx.x * 128u; tile < count; tile += gridDim.x * 128u) {
+        uint32_t i = tile + threadIdx.x;
 #if RT_SHADE_PREFETCH
-        {   // stream the next iteration's path state and hit record towards the SM while this one is shaded
-            const uint32_t nx = i + stride;
+        {   // stream the next tile's path state and hit records towards the SM while this one is shaded
+            const uint32_t nx = i + gridDim.x * 128u;
             if (nx < count) {
                 rt_prefetch(qin.o_tmin + nx); rt_prefetch(qin.d_tmax + nx); rt_prefetch(qin.thr_pix + nx); rt_prefetch(qin.rng + nx);
                 rt_prefetch(hits.tuvp + nx); rt_prefetch(hits.inst + nx);
             }
         }
 #endif
+#if RT_SHADE_SORT
+        {
+            uint32_t cls = RT_SHADE_CLASSES - 1u;
+            if (i < count) {
+                const float t = hits.tuvp[i].x;
+                cls = 0u;
+                if (!(t < 0.0f)) cls = 1u + rt_float_as_uint(rt_ld(S.inst_o2w + (size_t)hits.inst[i] * RT_O2W_F4 + 3).z) % (RT_SHADE_CLASSES - 2u);
+            }
+            s_hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+            const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            if (rank == 0u) s_hist[cls * 4u + warp] = (uint32_t)__popc(peers);
+            __syncthreads();
+            // exclusive scan of the 128 (class-major, warp-minor) counts: one entry per thread
+            const uint32_t v = s_hist[threadIdx.x];
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+            if (lane == 31u) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t base = 0u;
+            for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
+            s_hist[threadIdx.x] = base + incl - v;
+            __syncthreads();
+            s_perm[s_hist[cls * 4u + warp] + rank] = (uint8_t)threadIdx.x;
+            __syncthreads();
+            i = tile + s_perm[threadIdx.x];      // (paths beyond count sort last: a thread with i >= count idles as before)
+        }
+#endif
         ShadeResult r; r.alive = false; r.has_shadow = false; r.hit = false;
         if (i < count) r = shade_item<SIMPLE, COUNT>(S, P, fb, qin, hits, i, bounce, cnt);
-        {   // closest hits actually shaded (rt_stats::shaded_hits; misses run the miss stage only)
-            const uint32_t hit_mask = __ballot_sync(0xFFFFFFFFu, r.hit);
-            if (hit_mask && lane == 0) atomicAdd(hit_count, (uint32_t)__popc(hit_mask));
-        }
-        const uint32_t alive_mask = __ballot_sync(0xFFFFFFFFu, r.alive);
-        if (alive_mask) {
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(out_count, (uint32_t)__popc(alive_mask));
-            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-            if (r.alive) store_path(qout, slot0 + (uint32_t)__popc(alive_mask & ((1u << lane) - 1u)), r.next);
-        }
-        const uint32_t sh_mask = __ballot_sync(0xFFFFFFFFu, r.has_shadow);
-        if (sh_mask) {
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(shadow_count, (uint32_t)__popc(sh_mask));
-            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-            if (r.has_shadow) {
-                const uint32_t s = slot0 + (uint32_t)__popc(sh_mask & ((1u << lane) - 1u));
-                sq.o_tmax[s] = make_float4(r.shadow.origin.x, r.shadow.origin.y, r.shadow.origin.z, r.shadow.tmax);
-                sq.d_pix[s] = make_float4(r.shadow.dir.x, r.shadow.dir.y, r.shadow.dir.z, rt_uint_as_float(r.shadow.pixel));
-                sq.contrib[s] = make_float4(r.shadow.contrib.x, r.shadow.contrib.y, r.shadow.contrib.z, rt_uint_as_float(r.shadow.path_w));
-            }
-        }
-    }
-}
 
 // rt_trace_closest / rt_trace_any (default path): the caller's ray set goes through the SAME persistent traversal as the
 // frame kernels above (persistent_trace + coop_round: dynamic fetch, deferred warp-cooperative triangle rounds, 64-bit

@@ -62,6 +62,7 @@ struct DScene {
     const DImage* images;
     const rt_light* dlights; uint32_t n_dlights;
     const rt_light* plights; uint32_t n_plights;
+    uint32_t nee_plights;          // n_plights if a point light of the first min(n,3) slots is bright enough for RIS (RayTracing.rchit:86), else 0
     const float* srgb_lut;         // 256 entries
     DImage sky[6]; uint32_t has_sky_faces;
 };

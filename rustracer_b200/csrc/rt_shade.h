@@ -371,7 +371,7 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     u4 rng = path_stream(P, st.pixel, st.path_w);
     const uint32_t entry_w = st.path_w;
     // NEE: sampleLightRIS :77-122 + castShadowRay :35-59 (resolved by the shadow pass)
-    if (S.n_plights) {
+    if (S.nee_plights) {      // (0 when no candidate slot can pass the luminance test below: the loop would draw nothing)
         float totalWeights = 0.0f, samplePdfG = 0.0f; uint32_t sel = 0;
         const uint32_t ncand = S.n_plights < 3u ? S.n_plights : 3u;
         for (uint32_t i = 0; i < ncand; i++) {

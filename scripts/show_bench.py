@@ -1,12 +1,11 @@
-import sys, json
-for l in sys.stdin:
-    l = l.strip()
-    if l.startswith('{'):
-        d = json.loads(l)
-        print('value', round(d['value'], 1), 'ms/step', round(d['ms_per_step'], 3), 'e2e', round(d['e2e']['value'], 1), 'launches', d.get('gpu_launches'),
-              'cpu', round(d['cpu_baseline']['value'], 1) if d.get('cpu_baseline') and d['cpu_baseline'].get('value') else None)
-        r = d['roofline']
-        print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k not in ('stage_ms_per_step', 'kernel', 'peak_source')})
-        print({k: round(v, 3) for k, v in r['stage_ms_per_step'].items()}, d['clocks'])
-    elif not l.startswith('[gpurun] sending'):
-        print(l)
+"""prints the headline fields of a bench.py JSON line (stdin)"""
+import json, sys
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); r = d.get("roofline") or {}
+print("  value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "ms/step", round(d["ms_per_step"], 3), "gpus", d["n_gpus"], d["scaling"],
+      "frac", r.get("frac") and round(r["frac"], 3), "whole", r.get("whole_frame_frac") and round(r["whole_frame_frac"], 3),
+      "stages", {k: round(v, 3) for k, v in (r.get("stage_ms_per_step") or {}).items()})
+ex = (d.get("engine") or {}).get("exchange")
+if ex:
+    print("  exchange: fused", round(ex["fused_ms"], 4), "ms  nccl", round(ex["nccl_ms"], 4), "ms  complete image:", ex["complete_image_on_this_rank"])
+if d.get("alt_camera"):
+    print("  alt camera", round(d["alt_camera"]["value"], 1))
