@@ -601,6 +601,31 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
 #endif
         ShadeResult r; r.alive = false; r.has_shadow = false; r.hit = false;
         if (i < count) r = shade_item<SIMPLE, COUNT>(S, P, fb, qin, hits, i, bounce, cnt);
+        {   // closest hits actually shaded (rt_stats::shaded_hits; misses run the miss stage only)
+            const uint32_t hit_mask = __ballot_sync(0xFFFFFFFFu, r.hit);
+            if (hit_mask && lane == 0) atomicAdd(hit_count, (uint32_t)__popc(hit_mask));
+        }
+        const uint32_t alive_mask = __ballot_sync(0xFFFFFFFFu, r.alive);
+        if (alive_mask) {
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(out_count, (uint32_t)__popc(alive_mask));
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            if (r.alive) store_path(qout, slot0 + (uint32_t)__popc(alive_mask & ((1u << lane) - 1u)), r.next);
+        }
+        const uint32_t sh_mask = __ballot_sync(0xFFFFFFFFu, r.has_shadow);
+        if (sh_mask) {
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(shadow_count, (uint32_t)__popc(sh_mask));
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            if (r.has_shadow) {
+                const uint32_t s = slot0 + (uint32_t)__popc(sh_mask & ((1u << lane) - 1u));
+                sq.o_tmax[s] = make_float4(r.shadow.origin.x, r.shadow.origin.y, r.shadow.origin.z, r.shadow.tmax);
+                sq.d_pix[s] = make_float4(r.shadow.dir.x, r.shadow.dir.y, r.shadow.dir.z, rt_uint_as_float(r.shadow.pixel));
+                sq.contrib[s] = make_float4(r.shadow.contrib.x, r.shadow.contrib.y, r.shadow.contrib.z, rt_uint_as_float(r.shadow.path_w));
+            }
+        }
+    }
+}
 
 // rt_trace_closest / rt_trace_any (default path): the caller's ray set goes through the SAME persistent traversal as the
 // frame kernels above (persistent_trace + coop_round: dynamic fetch, deferred warp-cooperative triangle rounds, 64-bit
