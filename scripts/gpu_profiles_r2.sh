@@ -1,0 +1,32 @@
+#!/bin/bash
+# Round-2 evidence run for profiles/ (one B200): the driver's bench command, its ncu launch list, full ncu captures of the
+# two dominant kernels over one steady-state frame (8 extend + 8 shade launches), the other BASELINE configs, sanitizers.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+echo "== bench (driver command)"
+timeout 900 python bench.py --steps 50 --warmup 5 2>&1 | tail -1 | tee gpurun_out/bench.log | python scripts/show_bench.py
+echo "== reference arm"
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_reference.log | cut -c1-200
+echo "== launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-alt-camera > gpurun_out/ncu_bench.log 2>&1
+tail -1 gpurun_out/ncu_bench.log | cut -c1-120
+for K in extend_kernel shade_kernel; do
+  echo "== ncu full $K"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 24 -c 8 -f -o gpurun_out/prof_$K \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-alt-camera --frames-in-flight 1 > gpurun_out/ncu_full_$K.log 2>&1
+  tail -1 gpurun_out/ncu_full_$K.log
+done
+echo "== configs"
+for c in 1 3 4 5; do
+  timeout 900 python bench.py --config $c --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/config_$c.json | python scripts/show_bench.py
+done
+if [ "${SANITIZE:-1}" = "1" ]; then
+echo "== sanitizers"
+for tool in memcheck racecheck; do
+  ( timeout 600 compute-sanitizer --tool $tool python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -E "smoke:|ERROR SUMMARY|RACECHECK SUMMARY|=========  *(Invalid|Race|Error)" | head -10
+    timeout 900 compute-sanitizer --tool $tool python -m pytest tests -x -q -m gpu -k "multi_device or skinning_refit or shadows_glb or lifecycle or frames_in_flight_bit" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY|=========  *(Invalid|Race)" | head -10 ) | tee gpurun_out/sanitizer_$tool.txt
+done
+fi
+ls gpurun_out | head -50
