@@ -375,7 +375,7 @@ def run_ours(args):
     # ---- device-timed run: inputs resident, K frames (+ final cross-GPU reduce) ----
     # frames in flight (the reference's InFlightFrames, app/src/lib.rs:34): the path tracing of NF consecutive frames
     # overlaps on the GPU, the accumulation stays in submission order (bit-identical images, tests/parity_cases.py)
-    NF = max(1, min(4, args.frames_in_flight))
+    NF = max(1, min(8, args.frames_in_flight))
     ctx.set_frames_in_flight(NF)
     if POSE is not None:
         scene.set_versions(max(2, min(4, args.scene_versions)))   # skin updates write the next copy while frames read the previous ones

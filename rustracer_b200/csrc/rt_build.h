@@ -314,6 +314,77 @@ inline int builder_kind() {
     return kind;
 }
 
+#ifndef RT_EMU
+// Last PLOC rounds in ONE launch: once at most RT_PLOC_FINISH_MAX clusters are left (the long tail of the algorithm: most of
+// its ~110 rounds for 465 k triangles), a single 1024-thread CTA runs the remaining rounds back to back — the same three
+// phases (nearest neighbour, survivor flags + exclusive scan, merge + order-preserving compaction) with __syncthreads()
+// between them instead of 5 launches per round and a host read every few rounds.  Same arithmetic and the same id
+// assignment as the per-round kernels below: the tree is identical.
+#define RT_PLOC_FINISH_MAX 4096
+__global__ void __launch_bounds__(1024) ploc_finish_kernel(int n, int2* bin_children, DAabb* bin_box, uint32_t* bin_count, uint32_t* cl_in, uint32_t* cl_out,
+                                                          uint32_t* nn, uint32_t* valid, uint32_t* pos, const uint32_t* cur) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t c = cur[0], merged_before = cur[1];
+    while (c > 1u) {
+        const int ci = (int)c;
+        for (uint32_t i = tid; i < c; i += 1024u) {
+            const DAabb a = bin_box[cl_in[i]];
+            const int lo = (int)i - RT_PLOC_RADIUS < 0 ? 0 : (int)i - RT_PLOC_RADIUS;
+            const int hi = (int)i + RT_PLOC_RADIUS > ci - 1 ? ci - 1 : (int)i + RT_PLOC_RADIUS;
+            float best = 3.0e38f; int bj = -1;
+            for (int j = lo; j <= hi; ++j) {
+                if (j == (int)i) continue;
+                const float d = aabb_half_area(aabb_union(a, bin_box[cl_in[j]]));
+                if (d < best || bj < 0) { best = d; bj = j; }
+            }
+            nn[i] = (uint32_t)bj;
+        }
+        __syncthreads();
+        // survivor flags + exclusive scan: thread t owns the entries [t * per, t * per + per)
+        const uint32_t per = (c + 1023u) / 1024u, first = tid * per;
+        uint32_t local = 0u;
+        for (uint32_t k = 0; k < per; ++k) {
+            const uint32_t i = first + k;
+            if (i < c) { const uint32_t j = nn[i]; const uint32_t v = (nn[j] == i && j < i) ? 0u : 1u; valid[i] = v; local += v; }
+        }
+        uint32_t incl = local;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+        if (lane == 31u) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0u) {
+            uint32_t w = s_warp[lane], wi = w;
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)lane >= d) wi += o; }
+            s_warp[lane] = wi - w;
+            if (lane == 31u) s_total = wi;
+        }
+        __syncthreads();
+        uint32_t run = s_warp[warp] + incl - local;
+        for (uint32_t k = 0; k < per; ++k) { const uint32_t i = first + k; if (i < c) { pos[i] = run; run += valid[i]; } }
+        const uint32_t c_new = s_total;
+        __syncthreads();
+        for (uint32_t i = tid; i < c; i += 1024u) {
+            if (!valid[i]) continue;
+            const uint32_t j = nn[i];
+            uint32_t id = cl_in[i];
+            if (nn[j] == i) {
+                const uint32_t rank = j - pos[j];   // absorbed entries before j == merges before this one
+                const uint32_t a = id, b = cl_in[j];
+                id = (uint32_t)(n - 2) - (merged_before + rank);
+                bin_children[id] = make_int2((int)a, (int)b);
+                bin_box[id] = aabb_union(bin_box[a], bin_box[b]);
+                bin_count[id] = (a >= (uint32_t)(n - 1) ? 1u : bin_count[a]) + (b >= (uint32_t)(n - 1) ? 1u : bin_count[b]);
+            }
+            cl_out[pos[i]] = id;
+        }
+        merged_before += c - c_new; c = c_new;
+        uint32_t* t = cl_in; cl_in = cl_out; cl_out = t;
+        __syncthreads();
+    }
+}
+#endif
+
 inline int ploc_build(const DAabb* prim_boxes, int n, BuildScratch& sc, rt_stream_t stream) {
     int2* bin_children = sc.bin_children; DAabb* bin_box = sc.bin_box; uint32_t* bin_count = sc.bin_count;
     const uint32_t* vals = sc.vals; uint32_t *nn = sc.nn, *valid = sc.valid, *pos = sc.pos, *counters = sc.counters;
@@ -332,7 +403,17 @@ inline int ploc_build(const DAabb* prim_boxes, int n, BuildScratch& sc, rt_strea
     uint32_t c_ub = (uint32_t)n, rounds = 0;
     { const uint32_t init[4] = {(uint32_t)n, 0u, (uint32_t)n, 0u}; if (rt_h2d(&counters[4], init, sizeof init, stream)) return 1; }
     while (c_ub > 1) {
-        for (int r = 0; r < RT_PLOC_BATCH; ++r, ++rounds) {
+#ifndef RT_EMU
+        if (c_ub <= RT_PLOC_FINISH_MAX) {     // the long tail of the algorithm: one launch, no further host reads
+            ploc_finish_kernel<<<1, 1024, 0, stream>>>(n, bin_children, bin_box, bin_count, cl_in, cl_out, nn, valid, pos, counters + 4 + 2 * (rounds & 1u));
+            ++g_rt_launch_count;
+            break;
+        }
+#endif
+        // launches are sized for the cluster count at the start of a batch: short batches while the list is long (a round
+        // removes 30-45 % of it), longer ones later
+        const int batch = c_ub > 65536u ? 2 : (c_ub > 16384u ? 3 : RT_PLOC_BATCH);
+        for (int r = 0; r < batch; ++r, ++rounds) {
             const uint32_t* cl = cl_in; uint32_t* co = cl_out;
             const uint32_t* cur = counters + 4 + 2 * (rounds & 1u); uint32_t* nxt = counters + 4 + 2 * ((rounds + 1u) & 1u);
             rt_launch(c_ub, stream, RT_LAMBDA(size_t i) {

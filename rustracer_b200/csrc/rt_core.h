@@ -63,9 +63,11 @@ using namespace rtcore;
 #ifndef RT_MIN_RAYS_PER_CTA
 #define RT_MIN_RAYS_PER_CTA 0
 #endif
+#ifndef RT_MAX_FRAMES_IN_FLIGHT
 #define RT_MAX_FRAMES_IN_FLIGHT 4
+#endif
 #define RT_MAX_SCENE_VERSIONS 4
-#define RT_TICKET_RING 12
+#define RT_TICKET_RING 24      // a multiple of every slot count (1..8 with RT_MAX_FRAMES_IN_FLIGHT raised)
 
 // One frame in flight: everything a frame writes except the shared accumulation image.  Mirrors the reference's
 // InFlightFrames (app/src/lib.rs:34,329,400-401: IN_FLIGHT_FRAMES = 2, one fence per frame) and its per-swapchain-image
@@ -709,6 +711,27 @@ int RT_API(rt_context_create)(int device, uint32_t width, uint32_t height, rt_co
     c->ev_submit.create(); c->ev_acc.create(); c->ev_consumer.create(); c->ev_combine.create();
     for (auto& e : c->ticket_done) e.create();
     if (alloc_frame(c, width, height)) { RT_API(rt_context_destroy)(c); return fail(std::string("rt_context_create: allocation failed: ") + rt_platform_error()); }
+#ifndef RT_EMU
+    {   // CUDA loads a kernel's code on its first launch: run the builder once over a few thousand dummy boxes so that the first
+        // real scene build (and its build_ms) does not pay ~7 ms of lazy module loading.  Once per process and device.
+        static bool warmed[64] = {false};
+        if (device < 64 && !warmed[device]) {
+            warmed[device] = true;
+            const uint32_t n = 6000;       // > RT_PLOC_FINISH_MAX: per-round kernels and the finishing kernel both run
+            DAabb* boxes = nullptr; BuildScratch sc; WideOut wo{}; WideBvhInfo info;
+            int e = dev_alloc(&boxes, n); e |= dev_alloc(&wo.nodes, (size_t)n * RT_NODE_F4); e |= dev_alloc(&wo.prim_order, n); e |= dev_alloc(&wo.node_box, n); e |= dev_alloc(&wo.node_parent, n);
+            wo.max_nodes = n;
+            if (!e) {
+                DAabb* b = boxes;
+                rt_launch(n, c->stream, RT_LAMBDA(size_t i) { DAabb x; const float f = (float)(i % 97u), g = (float)(i / 97u); x.lo[0] = f; x.lo[1] = g; x.lo[2] = 0.0f; x.hi[0] = f + 0.9f; x.hi[1] = g + 0.9f; x.hi[2] = 0.5f; b[i] = x; });
+                build_wide_bvh(boxes, n, sc, wo, c->stream, &info);
+                rt_stream_sync(c->stream);
+            }
+            scratch_free(sc);
+            rt_free(boxes); rt_free(wo.nodes); rt_free(wo.prim_order); rt_free(wo.node_box); rt_free(wo.node_parent);
+        }
+    }
+#endif
     *out = c;
     return 0;
 }
@@ -759,7 +782,7 @@ int RT_API(rt_frame_resize)(rt_context* c, uint32_t width, uint32_t height) {
 
 int RT_API(rt_context_set_frames_in_flight)(rt_context* c, uint32_t n) {
     if (!c) return fail("rt_context_set_frames_in_flight: null context");
-    if (n < 1 || n > RT_MAX_FRAMES_IN_FLIGHT) return fail("rt_context_set_frames_in_flight: n must be 1..4");
+    if (n < 1 || n > RT_MAX_FRAMES_IN_FLIGHT || RT_TICKET_RING % n) return fail("rt_context_set_frames_in_flight: n must be 1.." + std::to_string(RT_MAX_FRAMES_IN_FLIGHT));
     if (n == c->n_slots) return 0;
 #ifndef RT_EMU
     cudaSetDevice(c->device);
@@ -913,6 +936,8 @@ int RT_API(rt_scene_create)(rt_context* c, const rt_scene_desc* d, rt_scene** ou
     e |= dev_alloc(&s->d_inst_root, ninst + 1); e |= dev_alloc(&s->d_entry_rec, ninst + 1);
     if (e) return bail(std::string("rt_scene_create: BVH allocation failed: ") + rt_platform_error());
 
+    // builder scratch is reserved up front: the build below then runs without allocating (and build_ms times the build, not cudaMalloc)
+    if (scratch_reserve(s->scratch, (size_t)(max_tris > ninst + 1 ? max_tris : ninst + 1))) return bail(std::string("rt_scene_create: scratch allocation failed: ") + rt_platform_error());
     rt_timer t0, t1, t2; t0.create(); t1.create(); t2.create();
     t0.record(st);
     run_skinning(s);   // initial ComputeUnit::dispatch (main.rs:85-91); copy-through when nothing is skinned
