@@ -621,7 +621,7 @@ template <bool ALPHA, bool COUNT>
 static int render_frame(rt_context* ctx, FrameSlot* c, rt_scene* s, const FrameParams& P0, const TilePart& tp, uint32_t flags, rt_stream_t st) {
     FrameParams P = P0;
     const uint32_t S = P.ubo.number_of_samples, B = P.ubo.number_of_bounces;
-    const uint32_t n_local = owned_rows(tp) * tp.width;
+    const uint32_t n_rows = owned_rows(tp), n_local = n_rows * tp.width;
     const size_t per = (size_t)(S ? S : 1) * (B + 1);
     if (per * 5 > c->counters_cap) {
         if (c->counters) rt_free(c->counters);
@@ -641,7 +641,7 @@ static int render_frame(rt_context* ctx, FrameSlot* c, rt_scene* s, const FrameP
         StageEvent* ev = stage_begin(c, timing, 0, st);
         rt_launch(n_local, st, RT_LAMBDA(size_t i) {
             if (i == 0) *qc0 = n_local;
-            raygen_item(Pk, tp, fb, q0, (uint32_t)i);
+            raygen_item(Pk, tp, fb, q0, (uint32_t)i, n_rows);
         });
         stage_end(ev, st);
         for (uint32_t b = 0; b < B; ++b) {

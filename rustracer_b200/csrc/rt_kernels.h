@@ -28,6 +28,23 @@ RT_D uint32_t local_to_pixel(const TilePart& tp, uint32_t i) {
     return y * tp.width + x;
 }
 
+// Queue order of the primary rays: 8x4-pixel tiles instead of 32x1 row segments, so that the 32 rays a warp fetches together
+// (and, through the order-preserving compaction, their descendants) start closer to each other.  A bijection of the local
+// index space; paths carry their pixel, so nothing else depends on it.  n_rows = rows this context renders.
+#ifndef RT_PRIMARY_TILES
+#define RT_PRIMARY_TILES 1
+#endif
+RT_D uint32_t primary_order(uint32_t i, uint32_t width, uint32_t n_rows) {
+#if RT_PRIMARY_TILES
+    if ((width & 7u) == 0u && (n_rows & 3u) == 0u) {
+        const uint32_t tiles_x = width >> 3, t = i >> 5, in = i & 31u;
+        const uint32_t tx = t % tiles_x, ty = t / tiles_x;
+        return (ty * 4u + (in >> 3)) * width + tx * 8u + (in & 7u);
+    }
+#endif
+    return i;
+}
+
 RT_D void store_path(const DQueue& q, uint32_t slot, const PathState& s) {
     q.o_tmin[slot] = make_float4(s.origin.x, s.origin.y, s.origin.z, s.tmin);
     q.d_tmax[slot] = make_float4(s.dir.x, s.dir.y, s.dir.z, s.tmax);
@@ -44,8 +61,8 @@ RT_D PathState load_path(const DQueue& q, uint32_t slot) {
 }
 
 // ---- per-item bodies ----------------------------------------------------------------------------------
-RT_D void raygen_item(const FrameParams& P, const TilePart& tp, const FrameBuffers& fb, const DQueue& q, uint32_t i) {
-    const uint32_t pixel = local_to_pixel(tp, i);
+RT_D void raygen_item(const FrameParams& P, const TilePart& tp, const FrameBuffers& fb, const DQueue& q, uint32_t i, uint32_t n_rows) {
+    const uint32_t pixel = local_to_pixel(tp, primary_order(i, tp.width, n_rows));
     uint4 pr = make_uint4(0u, 0u, 0u, 0u);
     if (P.sample != 0) pr = fb.pixrng[pixel];
     else { fb.rad[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); fb.aux[pixel] = make_float2(0.0f, 0.0f); }
