@@ -448,14 +448,18 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             // queue positions from one shared-memory atomic per pushing lane (item order inside the queue is irrelevant:
             // hit resolution is order-independent) instead of a 5-step shuffle scan
             if (k) {
-                uint32_t pos = atomicAdd(&sh.tail, k);
+                uint32_t slot = atomicAdd(&sh.tail, k) & (RT_TQ_CAP - 1u);
                 outstanding += k;
-                while (leaf_mask) {
-                    const int bit = 31 - __clz((int)leaf_mask);
-                    leaf_mask &= ~(1u << bit);
-                    sh.items[pos & (RT_TQ_CAP - 1u)] = (lane << RT_TQ_TRI_BITS) | (leaf_base + (uint32_t)bit);
-                    ++pos;
-                }
+                // (this loop runs with few lanes: keep it short — owner | first triangle folded into one base, a wrapped slot
+                //  counter instead of masking a position; leaf_base + bit < 2^27 cannot carry into the owner bits)
+                const uint32_t item_base = (lane << RT_TQ_TRI_BITS) | leaf_base;
+                uint32_t off = slot * 4u;                                 // byte offset into the ring
+                do {
+                    uint32_t bit; asm("bfind.u32 %0, %1;" : "=r"(bit) : "r"(leaf_mask));
+                    leaf_mask ^= 1u << bit;
+                    *reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sh.items) + off) = item_base + bit;
+                    off = (off + 4u) & (RT_TQ_CAP * 4u - 1u);
+                } while (leaf_mask);
             }
             __syncwarp();
             q_count = sh.tail - q_head;
