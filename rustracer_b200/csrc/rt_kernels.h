@@ -271,6 +271,12 @@ __global__ void __launch_bounds__(RT_SKIN_TILE) skin_kernel(const rt_vertex* vin
 #define RT_TQ_CAP 512u         // per-warp triangle queue capacity (power of two, >= 31 + 32 * RT_TQ_PUSH_MAX * RT_NODE_STEPS)
 #endif
 #define RT_TQ_TRI_BITS 27      // item = owner lane << 27 | absolute triangle index
+#ifndef RT_ENTER_BATCH
+#define RT_ENTER_BATCH 8        // two-level scenes: instance entries wait for this many lanes ...
+#endif
+#ifndef RT_ENTER_MAX_WAIT
+#define RT_ENTER_MAX_WAIT 3     // ... or this many node steps
+#endif
 
 #ifdef RT_PROBE
 // developer probe (variant builds only, scripts/gpu_probe.py): per-warp start / queue-exhausted / exit times, rays, iterations
@@ -376,6 +382,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
     bool active = false, exhausted = false;
     uint32_t idx = 0, outstanding = 0;          // outstanding: this lane's items still in the queue
     uint32_t q_head = 0, q_count = 0;           // warp-uniform queue cursor
+    int enter_wait = 0;                         // two-level scenes: steps the pending instance entries have been postponed (warp-uniform)
     if (lane == 0) sh.tail = 0u;
     __syncwarp();
 #ifdef RT_PROBE
@@ -421,8 +428,25 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                     const uint2 e = stack[--tv.sp];
                     if (e.y > 0x00FFFFFFu) tv.ngroup = e; else { tv.tgroup = e; tv.ngroup = make_uint2(0u, 0u); }
                 }
-                if (active && !want_flush) {
-                    if (!SINGLE && tv.tgroup.y != 0u && tv.blas_sp < 0) {
+            }
+            // Two-level scenes: entering an instance (ray transform, shear setup, record fetch: ~180 instructions) is per-lane
+            // work that few lanes reach in the same step — alone it ran at 2-3 of 32 lanes and cost 13 % of the kernel's
+            // instructions (config 3, profiles/r02_extend_config3_ncu.txt).  Lanes that reach a TLAS leaf therefore wait until
+            // RT_ENTER_BATCH of them can enter together, nobody else has a node to visit, or RT_ENTER_MAX_WAIT steps have
+            // passed: a waiting lane only forgoes its share of a node step (~12 warp instructions).
+            bool do_work = active && !want_flush, enter = false;
+            if constexpr (!SINGLE) {
+                enter = do_work && tv.tgroup.y != 0u && tv.blas_sp < 0;
+                const uint32_t em = __ballot_sync(0xFFFFFFFFu, enter);
+                if (em) {
+                    const uint32_t others = __ballot_sync(0xFFFFFFFFu, do_work && !enter);
+                    if (__popc(em) >= RT_ENTER_BATCH || others == 0u || ++enter_wait >= RT_ENTER_MAX_WAIT) enter_wait = 0;
+                    else { if (enter) do_work = false; enter = false; }
+                }
+            }
+            {
+                if (do_work) {
+                    if (!SINGLE && enter) {
                         // TLAS level: parked instances
                         trav_enter_instance<ALPHA, COUNT>(tv, S, stack, c4);
                         coop_publish_ray<ALPHA, SINGLE>(tv, sh, lane);
