@@ -20,11 +20,13 @@ ncu -i gpurun_out/prof_extend_kernel.ncu-rep --page source --csv --print-source 
   python scripts/ncu_summary.py gpurun_out/prof_shade_kernel.ncu-rep 8 25; } > profiles/${R}_shade_kernel_ncu.txt 2>&1
 for c in 1 3 4 5; do if [ -f gpurun_out/config_$c.json ]; then tail -1 gpurun_out/config_$c.json > profiles/${R}_config_$c.json; fi; done
 for t in memcheck racecheck; do cp gpurun_out/sanitizer_$t.txt profiles/${R}_sanitizer_$t.txt; done
-for n in 2 8; do
-  [ -f gpurun_out/multigpu_check_${n}gpu.txt ] && cp gpurun_out/multigpu_check_${n}gpu.txt profiles/${R}_multigpu_check_${n}gpu.txt
+for n in 2 4 8; do
+  true; [ -f gpurun_out/multigpu_check_${n}gpu.txt ] && cp gpurun_out/multigpu_check_${n}gpu.txt profiles/${R}_multigpu_check_${n}gpu.txt
   [ -f gpurun_out/bench_${n}gpu.json ] && cp gpurun_out/bench_${n}gpu.json profiles/${R}_bench_${n}gpu.json
   [ -f gpurun_out/bench_${n}gpu_tiles.json ] && cp gpurun_out/bench_${n}gpu_tiles.json profiles/${R}_bench_${n}gpu_tiles.json
+  for c in 3 5; do [ -f gpurun_out/config_${c}_${n}gpu.json ] && cp gpurun_out/config_${c}_${n}gpu.json profiles/${R}_config_${c}_${n}gpu.json; done
 done
+python scripts/results_table.py > profiles/${R}_results_table.md
 if [ -f gpurun_out/prof_extend_c3.ncu-rep ]; then
   ncu -i gpurun_out/prof_extend_c3.ncu-rep --page source --csv --print-source sass,cuda > /tmp/r2_c3_src.csv 2>/dev/null
   { echo "# config 3 (10k instances x 100k triangles, alpha MASK): extend_kernel<ALPHA=1,COUNT=0,SINGLE=0>, ncu --set full, bounces 0..3 of one frame"
