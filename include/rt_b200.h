@@ -262,7 +262,7 @@ int rt_frame_resize(rt_context* ctx, uint32_t width, uint32_t height);
    tails of one frame's late bounces fill with the next frame's rays) while the accumulate+tonemap steps
    run in submission order on the one shared accumulation image, so the images are bit-identical to n = 1.
    A frame starts after everything queued on rt_render's `stream` at the time of the call.  The library's
-   own consumers (rt_readback, rt_tonemap, rt_reduce_peers, rt_last_frame_stats, rt_synchronize, the
+   own consumers (rt_readback, rt_tonemap, rt_combine, rt_last_frame_stats, rt_synchronize, the
    rt_scene_update_* calls, rt_frame_resize) wait for the frames in flight; work of your own on another
    stream must call rt_join first.  Keeps the accumulation image; synchronises. */
 int rt_context_set_frames_in_flight(rt_context* ctx, uint32_t n);
@@ -343,18 +343,15 @@ typedef struct rt_bvh_info {
 } rt_bvh_info;
 int rt_scene_bvh_info(rt_scene* scene, rt_bvh_info* info);
 
-/* multi-GPU (new): cross-process peer access to the accumulation image.
-   rt_ipc_export writes a 64-byte cudaIpcMemHandle; rt_ipc_open maps a peer's handle and returns
-   the device pointer in this process; rt_reduce_peers sums peers' accumulation images into this
-   context's rows [row0,row1) and tonemaps them (fused reduce + tonemap over NVLink peer loads). */
+/* multi-GPU (new): cross-process peer access to a context's accumulation block (see rt_combine below).
+   rt_ipc_export writes a 64-byte cudaIpcMemHandle of the block; rt_ipc_open maps a peer's handle and returns the block's
+   device pointer in this process (close it with rt_ipc_close before the peer resizes). */
 int rt_ipc_export(rt_context* ctx, void* handle64);
-int rt_ipc_open(rt_context* ctx, const void* handle64, void** peer_acc);
-int rt_ipc_close(rt_context* ctx, void* peer_acc);
-int rt_reduce_peers(rt_context* ctx, void* const* peer_acc, uint32_t n_peers, const rt_ubo* ubo,
-                    uint32_t row0, uint32_t row1, void* stream);
+int rt_ipc_open(rt_context* ctx, const void* handle64, void** peer_block);
+int rt_ipc_close(rt_context* ctx, void* peer_block);
 
 /* ------------------------------------------------------------------------------------------
- * Multi-GPU combine, device-synchronised (supersedes rt_reduce_peers)
+ * Multi-GPU combine, device-synchronised
  * ------------------------------------------------------------------------------------------
  * Every context's accumulation image heads ONE device allocation, the "accumulation block":
  *     [ acc RGBA32F | snap RGBA32F | display RGBA8 | sync words ]

@@ -181,14 +181,14 @@ RT_EXPORTS = [
     "rt_scene_update_lights", "rt_scene_set_skybox", "rt_render", "rt_tonemap", "rt_synchronize",
     "rt_readback", "rt_upload_accumulation", "rt_device_ptrs", "rt_last_frame_stats", "rt_trace_closest",
     "rt_trace_any", "rt_scene_read_vertices", "rt_scene_bvh_info", "rt_ipc_export", "rt_ipc_open",
-    "rt_ipc_close", "rt_reduce_peers", "rt_context_set_frames_in_flight", "rt_join", "rt_readback_async",
+    "rt_ipc_close", "rt_context_set_frames_in_flight", "rt_join", "rt_readback_async",
     "rt_frame_wait", "rt_scene_read_nodes", "rt_scene_set_versions",
     "rt_combine", "rt_readback_display", "rt_combine_ptrs",
     "rt_multi_create", "rt_multi_destroy", "rt_multi_scene_create", "rt_multi_render", "rt_multi_combine",
     "rt_multi_readback", "rt_multi_synchronize", "rt_multi_replica",
 ]
 # multi-GPU entry points: CUDA-only (the test-only host emulation has no peers to talk to)
-RT_CUDA_ONLY = ("rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_reduce_peers", "rt_combine", "rt_readback_display", "rt_combine_ptrs",
+RT_CUDA_ONLY = ("rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_combine", "rt_readback_display", "rt_combine_ptrs",
                 "rt_multi_create", "rt_multi_destroy", "rt_multi_scene_create", "rt_multi_render", "rt_multi_combine",
                 "rt_multi_readback", "rt_multi_synchronize", "rt_multi_replica")
 GV_EXPORTS = [
@@ -273,7 +273,6 @@ def bind_rt(lib: C.CDLL, rename=lambda n: n, optional=()) -> C.CDLL:
         "rt_ipc_export": ([vp, vp], C.c_int),
         "rt_ipc_open": ([vp, vp, vpp], C.c_int),
         "rt_ipc_close": ([vp, vp], C.c_int),
-        "rt_reduce_peers": ([vp, vpp, c_u32, C.POINTER(rt_ubo), c_u32, c_u32, vp], C.c_int),
         "rt_context_set_frames_in_flight": ([vp, c_u32], C.c_int),
         "rt_join": ([vp, vp], C.c_int),
         "rt_readback_async": ([vp, c_u8p, C.POINTER(C.c_uint64)], C.c_int),

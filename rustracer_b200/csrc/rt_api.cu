@@ -51,22 +51,6 @@ int rt_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void** tm
 
 // ---- multi-GPU: peer access to the accumulation image across processes ----------------
 #define RT_MAX_PEERS 8
-struct PeerPtrs { const float4* p[RT_MAX_PEERS]; };
-
-// Sums the peers' accumulation rows into this GPU's image over NVLink peer loads and tonemaps the result in
-// the same pass (reduce fused with RayTracing.rgen:132-166).
-__global__ void __launch_bounds__(256) reduce_peers_kernel(float4* acc, uint32_t* out, PeerPtrs peers, uint32_t n_peers, rt_ubo ubo, size_t begin, size_t end) {
-    for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x) {
-        float4 a = acc[i];
-        for (uint32_t k = 0; k < n_peers; ++k) {
-            const float4 b = __ldcv(peers.p[k] + i);   // volatile load: peer memory, never cached stale
-            a.x += b.x; a.y += b.y; a.z += b.z;
-        }
-        acc[i] = make_float4(a.x, a.y, a.z, 0.0f);
-        rt_ubo u = ubo; u.number_of_samples = 0;
-        accumulate_pixel(u, acc, out, i, mk3(0.0f), 0.0f, 0u);
-    }
-}
 
 // ---- multi-GPU combine with device-side synchronisation (rt_combine, include/rt_b200.h) ---------------------------
 // One kernel per rank sums the peers' accumulation snapshots over NVLink peer loads for its band of the image, tonemaps
@@ -359,24 +343,6 @@ int rt_ipc_close(rt_context* c, void* peer_acc) {
     if (!c || !peer_acc) return fail("rt_ipc_close: null argument");
     for (size_t i = 0; i < c->ipc_opened.size(); ++i) if (c->ipc_opened[i] == peer_acc) { c->ipc_opened.erase(c->ipc_opened.begin() + i); break; }
     if (chk(cudaIpcCloseMemHandle(peer_acc))) return fail(std::string("rt_ipc_close: ") + rt_platform_error());
-    return 0;
-}
-int rt_reduce_peers(rt_context* c, void* const* peer_acc, uint32_t n_peers, const rt_ubo* ubo, uint32_t row0, uint32_t row1, void* stream) {
-    if (!c || !ubo || (n_peers && !peer_acc)) return fail("rt_reduce_peers: null argument");
-    if (n_peers > RT_MAX_PEERS) return fail("rt_reduce_peers: too many peers");
-    if (row1 > c->height || row0 > row1) return fail("rt_reduce_peers: bad row range");
-    if (ubo->total_number_of_samples == 0) return fail("rt_reduce_peers: total_number_of_samples must be > 0");
-    cudaSetDevice(c->device);
-    PeerPtrs pp; for (uint32_t k = 0; k < RT_MAX_PEERS; ++k) pp.p[k] = k < n_peers ? (const float4*)peer_acc[k] : nullptr;
-    const size_t begin = (size_t)row0 * c->width, end = (size_t)row1 * c->width;
-    if (end == begin) return 0;
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    size_t blocks = (end - begin + 255) / 256; const size_t cap = (size_t)g_rt_sm_count * 8; if (blocks > cap) blocks = cap;
-    join_frames(c, st);          // frames still in flight on this context accumulate first
-    reduce_peers_kernel<<<(unsigned)blocks, 256, 0, st>>>(c->acc, c->slot[c->cur].fb.out, pp, n_peers, *ubo, begin, end);
-    ++g_rt_launch_count;
-    c->last_stream = st; consumer_ran(c, st);
-    if (cudaPeekAtLastError() != cudaSuccess) return fail(std::string("rt_reduce_peers: ") + rt_platform_error());
     return 0;
 }
 

@@ -3,7 +3,7 @@
 Partition A — tiles: rows are cut into strips of `strip_rows`; rank r owns strips with strip % world == r
 (rt_render_opts).  Bit-identical to the single-GPU image.
 Partition B — sample passes: rank r renders global frames g with g % world == r into a private RGBA32F sum; the sums
-are combined once (fused peer-memory reduce + tonemap, rt_reduce_peers) — fp32 sum order differs from 1 GPU, so the
+are combined by rt_combine (fused peer-memory reduce + tonemap + all-gather, device-synchronised) — fp32 sum order differs from 1 GPU, so the
 result is compared within tolerance.
 """
 from __future__ import annotations
