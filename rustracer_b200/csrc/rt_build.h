@@ -158,7 +158,7 @@ RT_D void write_wide_node(float4* node, const DAabb& box, const DAabb* child_box
 // One collapse work item: binary subtree `bin` becomes wide node `wide`.
 // Binary node ids: internal k -> k (root 0), leaf at sorted position k -> n-1+k.
 RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, const uint32_t* bin_count, const uint32_t* vals,
-                        uint32_t bin, uint32_t wide, uint32_t parent_wide, WideOut out, uint32_t* counters, uint2* q_out) {
+                        uint32_t bin, uint32_t wide, uint32_t parent_wide, WideOut out, uint32_t* counters, uint2* q_out, uint32_t* q_out_count) {
     auto count_of = [&](uint32_t c) -> uint32_t { return c >= (uint32_t)(n - 1) ? 1u : bin_count[c]; };
     uint32_t ch[8]; int nch = 0;
     if (n == 1 || count_of(bin) <= RT_LEAF_MAX) { ch[nch++] = bin; }
@@ -238,7 +238,7 @@ RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, c
         } else {
             const uint32_t w = child_base + inner_rank;
             if (w < out.max_nodes) {
-                const uint32_t qi = rt_atomic_add(&counters[2], 1u);
+                const uint32_t qi = rt_atomic_add(q_out_count, 1u);
                 q_out[qi] = make_uint2(c, w);
                 out.node_parent[w] = wide;
             }
@@ -304,6 +304,9 @@ inline void emu_sah_binary_build(const DAabb* boxes, int n, uint32_t* vals, int2
 // on the Lucy stand-in.  Internal ids are handed out downwards from n-2 so that the last merge is the root, id 0.
 #ifndef RT_PLOC_RADIUS
 #define RT_PLOC_RADIUS 16
+#endif
+#ifndef RT_COLLAPSE_BATCH
+#define RT_COLLAPSE_BATCH 8     // collapse levels launched between two host reads of the queue size
 #endif
 #ifndef RT_PLOC_BATCH
 #define RT_PLOC_BATCH 16     // rounds between two host reads of the cluster count (465 k triangles: 113 rounds, ~10 ms)
@@ -544,30 +547,41 @@ inline int build_wide_bvh(const DAabb* prim_boxes, uint32_t n, BuildScratch& sc,
     } else {
         rt_launch(1, stream, RT_LAMBDA(size_t) { bin_box[0] = prim_boxes[vals[0]]; });
     }
-    // collapse, level by level
+    // collapse, level by level.  The size of a level's work queue lives on the device ([8] / [9], ping-pong): the level
+    // kernels are launched blind, sized by an upper bound (8x the previous one, at most max_nodes), and a thread beyond the real
+    // queue size leaves at once — the host reads the counters back once per RT_COLLAPSE_BATCH levels instead of synchronising
+    // after every one of the ~15 levels (an empty level costs a ~2 us launch).
+    // counters: [0] wide nodes, [1] primitives emitted, [3] depth, [8] / [9] queue sizes
     uint32_t* counters = sc.counters;
-    const uint32_t init_counters[3] = {1u, 0u, 0u};
-    rt_h2d(counters, init_counters, sizeof init_counters, stream);
+    {
+        uint32_t init[16] = {0}; init[0] = 1u; init[8] = 1u;
+        rt_h2d(counters, init, sizeof init, stream);
+    }
     const uint2 root_item = make_uint2(0u, 0u);
     rt_h2d(sc.q_a, &root_item, sizeof root_item, stream);
     uint2 *q_in = sc.q_a, *q_out = sc.q_b;
-    uint32_t q_count = 1, depth = 0;
-    while (q_count) {
-        ++depth;
-        const uint32_t zero = 0; rt_h2d(&counters[2], &zero, 4, stream);
-        const uint2* qi = q_in; uint2* qo = q_out; const bool is_root = depth == 1;
-        rt_launch(q_count, stream, RT_LAMBDA(size_t i) {
-            const uint2 it = qi[i];
-            collapse_node(ni, bin_children, bin_box, bin_count, vals, it.x, it.y, is_root ? 0xFFFFFFFFu : 0u, out, counters, qo);
-        });
-        uint32_t host_counters[3];
+    uint32_t depth = 0, level = 0; size_t ub = 1;
+    for (;;) {
+        for (int k = 0; k < RT_COLLAPSE_BATCH; ++k, ++level) {
+            const uint32_t* cin = counters + 8 + (level & 1u); uint32_t* cout = counters + 8 + ((level + 1u) & 1u);
+            rt_memset(cout, 0, 4, stream);
+            const uint2* qi = q_in; uint2* qo = q_out; const bool is_root = level == 0; const uint32_t lv = level;
+            rt_launch(ub, stream, RT_LAMBDA(size_t i) {
+                if (i >= (size_t)cin[0]) return;
+                if (i == 0) counters[3] = lv + 1u;
+                const uint2 it = qi[i];
+                collapse_node(ni, bin_children, bin_box, bin_count, vals, it.x, it.y, is_root ? 0xFFFFFFFFu : 0u, out, counters, qo, cout);
+            });
+            uint2* t = q_in; q_in = q_out; q_out = t;
+            ub = ub * 8 < (size_t)out.max_nodes ? ub * 8 : (size_t)out.max_nodes;
+        }
+        uint32_t host_counters[16];
         if (rt_d2h(host_counters, counters, sizeof host_counters, stream)) return 1;
         if (rt_stream_sync(stream)) return 1;
         if (host_counters[0] > out.max_nodes) return 2;
-        q_count = host_counters[2];
-        info->n_nodes = host_counters[0]; info->n_prims = host_counters[1];
-        uint2* t = q_in; q_in = q_out; q_out = t;
-        if (depth > 512) return 3;
+        info->n_nodes = host_counters[0]; info->n_prims = host_counters[1]; depth = host_counters[3];
+        if (host_counters[8 + (level & 1u)] == 0u) break;      // nothing queued for the next level
+        if (level > 512) return 3;
     }
     info->depth = depth;
     return 0;
