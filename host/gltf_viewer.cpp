@@ -4,7 +4,11 @@
 //
 //   gltf_viewer -f scene.gltf [-o out.png] [--width W --height H] [--spp N] [--samples-per-frame K] [--bounces B]
 //               [--skybox DIR] [--mapping M] [--tone-map T] [--animate SECONDS] [--camera X Y Z] [--device D]
-//               [--frames-in-flight N]
+//               [--frames-in-flight N] [--gpus N [--same-device]]
+//
+// --gpus N renders every frame on N GPUs of this one process through rt_multi (tile partition: interleaved 8-row strips per
+// device, gathered on device 0 by the fused peer-memory combine) — the image is bit-identical to one GPU.  --same-device puts
+// all replicas on --device (single-GPU boxes, tests).
 //
 // The window, swapchain and imgui panel are out of scope; GUI defaults (gui_state.rs:303-332)
 // stand in for everything not given on the command line.  The draw loop keeps IN_FLIGHT_FRAMES = 2 frames in flight
@@ -52,7 +56,8 @@ static int die_gv(const char* what) { fprintf(stderr, "gltf_viewer: %s: %s\n", w
 int main(int argc, char** argv) {
     std::string file, output = "render.png", skybox;
     uint32_t width = 1920, height = 1080, spp = 64, per_frame = 3, bounces = 5, mapping = 0, tone_map = 0, in_flight = 2;
-    int device = 0; bool animate = false, have_cam = false; float anim_t = 0.0f, cam[3] = {0, 0, 0};
+    int device = 0; bool animate = false, have_cam = false, same_device = false; float anim_t = 0.0f, cam[3] = {0, 0, 0};
+    uint32_t gpus = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](int n) { if (i + n >= argc) { fprintf(stderr, "gltf_viewer: %s needs %d value(s)\n", a.c_str(), n); exit(2); } };
@@ -70,6 +75,8 @@ int main(int argc, char** argv) {
         else if (a == "--camera") { need(3); have_cam = true; for (int k = 0; k < 3; ++k) cam[k] = (float)atof(argv[++i]); }
         else if (a == "--device") { need(1); device = atoi(argv[++i]); }
         else if (a == "--frames-in-flight") { need(1); in_flight = (uint32_t)atoi(argv[++i]); }
+        else if (a == "--gpus") { need(1); gpus = (uint32_t)atoi(argv[++i]); }
+        else if (a == "--same-device") { same_device = true; }
         else { fprintf(stderr, "gltf_viewer: unknown argument %s\n", a.c_str()); return 2; }
     }
     if (file.empty()) { fprintf(stderr, "usage: gltf_viewer -f <file> [-o out.png] ...\n"); return 2; }
@@ -87,23 +94,31 @@ int main(int argc, char** argv) {
     rt_scene_desc desc;
     if (gv_doc_scene_desc(doc, &desc)) return die_gv("scene_desc");
 
-    rt_context* ctx = nullptr; rt_scene* scene = nullptr;
-    if (rt_context_create(device, width, height, &ctx)) return die_rt("rt_context_create");
-    if (rt_scene_create(ctx, &desc, &scene)) return die_rt("rt_scene_create");
-    if (animate) {           // GltfViewer::state_change animation branch (main.rs:377-410)
-        if (gv_doc_animate(doc, anim_t)) return die_gv("animate");
-        if (gv_doc_need_compute(doc)) {
-            const float* mats = nullptr; uint32_t n_skins = 0;
-            if (gv_doc_get_skins(doc, &mats, &n_skins)) return die_gv("get_skins");
-            if (rt_scene_update_skins(scene, mats, n_skins, 0)) return die_rt("rt_scene_update_skins");
-        }
-        const rt_instance* inst = nullptr; uint32_t n = 0;
-        if (gv_doc_get_instances(doc, &inst, &n)) return die_gv("get_instances");
-        if (rt_scene_update_instances(scene, inst, n)) return die_rt("rt_scene_update_instances");
-    }
+    if (gpus < 1 || gpus > 8) { fprintf(stderr, "gltf_viewer: --gpus must be 1..8\n"); return 2; }
+    // one replica (context + scene) per GPU behind rt_multi; a single GPU is the n = 1 case of the same interface
+    rt_multi* multi = nullptr;
+    std::vector<int> devices;
+    for (uint32_t g = 0; g < gpus; ++g) devices.push_back(same_device ? device : device + (int)g);
+    if (rt_multi_create(devices.data(), gpus, width, height, RT_PARTITION_TILES, &multi)) return die_rt("rt_multi_create");
+    if (rt_multi_scene_create(multi, &desc)) return die_rt("rt_multi_scene_create");
     if (in_flight < 1) in_flight = 1;
     if (in_flight > 4) in_flight = 4;
-    if (rt_context_set_frames_in_flight(ctx, in_flight)) return die_rt("rt_context_set_frames_in_flight");
+    if (animate && gv_doc_animate(doc, anim_t)) return die_gv("animate");     // GltfViewer::state_change animation branch (main.rs:377-410)
+    for (uint32_t g = 0; g < gpus; ++g) {
+        rt_context* ctx = nullptr; rt_scene* scene = nullptr;
+        if (rt_multi_replica(multi, g, &ctx, &scene)) return die_rt("rt_multi_replica");
+        if (animate) {
+            if (gv_doc_need_compute(doc)) {
+                const float* mats = nullptr; uint32_t n_skins = 0;
+                if (gv_doc_get_skins(doc, &mats, &n_skins)) return die_gv("get_skins");
+                if (rt_scene_update_skins(scene, mats, n_skins, 0)) return die_rt("rt_scene_update_skins");
+            }
+            const rt_instance* inst = nullptr; uint32_t n = 0;
+            if (gv_doc_get_instances(doc, &inst, &n)) return die_gv("get_instances");
+            if (rt_scene_update_instances(scene, inst, n)) return die_rt("rt_scene_update_instances");
+        }
+        if (rt_context_set_frames_in_flight(ctx, in_flight)) return die_rt("rt_context_set_frames_in_flight");
+    }
 
     gv_camera camera; gv_camera_default(&camera, width, height);
     if (have_cam) memcpy(camera.position, cam, sizeof cam);
@@ -112,21 +127,28 @@ int main(int argc, char** argv) {
     gui.mapping = mapping; gui.selected_tone_map_mode = tone_map;
     const uint32_t opaque = (uint32_t)gv_doc_fully_opaque(doc);
     uint32_t total = 0, frames = 0;
+    rt_ubo ubo, last_ubo; memset(&last_ubo, 0, sizeof last_ubo);
     for (;;) {               // GltfViewer::update + record_raytracing_commands (main.rs:189-270)
-        rt_ubo ubo;
         gv_build_ubo(&camera, &gui, &total, frames, opaque, 3u, &ubo);
         if (ubo.number_of_samples == 0) break;
-        if (rt_render(ctx, scene, &ubo, nullptr, nullptr)) return die_rt("rt_render");
-        ++frames;
+        if (rt_multi_render(multi, &ubo)) return die_rt("rt_multi_render");
+        last_ubo = ubo; ++frames;
         if (mapping != 0) break;
     }
+    if (!frames) { fprintf(stderr, "gltf_viewer: nothing to render (--spp 0?)\n"); return 2; }
     std::vector<uint8_t> rgba((size_t)width * height * 4);
-    if (rt_readback(ctx, nullptr, rgba.data())) return die_rt("rt_readback");
-    rt_stats st;
-    if (rt_last_frame_stats(ctx, &st)) return die_rt("rt_last_frame_stats");
+    rt_context* ctx0 = nullptr;
+    if (rt_multi_replica(multi, 0, &ctx0, nullptr)) return die_rt("rt_multi_replica");
+    rt_stats st; memset(&st, 0, sizeof st);
+    if (gpus == 1) {         // the storage image of the last frame (debug mappings such as HEAT / DISTANCE live there)
+        if (rt_readback(ctx0, nullptr, rgba.data())) return die_rt("rt_readback");
+    } else {                 // strips of every device gathered on device 0 (rt_combine over peer memory)
+        if (rt_multi_readback(multi, &last_ubo, nullptr, rgba.data())) return die_rt("rt_multi_readback");
+    }
+    if (rt_last_frame_stats(ctx0, &st)) return die_rt("rt_last_frame_stats");
     if (!write_png(output.c_str(), rgba.data(), width, height)) { fprintf(stderr, "gltf_viewer: cannot write %s\n", output.c_str()); return 1; }
-    printf("%s: %ux%u, %u spp in %u frames, last frame %.2f ms\n", output.c_str(), width, height, total, frames, st.ms_total);
-    rt_scene_destroy(scene); rt_context_destroy(ctx); gv_doc_free(doc);
+    printf("%s: %ux%u, %u spp in %u frames on %u GPU(s), last frame %.2f ms\n", output.c_str(), width, height, total, frames, gpus, st.ms_total);
+    rt_multi_destroy(multi); gv_doc_free(doc);
     for (uint8_t* f : faces) gv_free(f);
     return 0;
 }

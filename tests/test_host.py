@@ -358,6 +358,13 @@ def test_cpp_gltf_viewer_matches_python_viewer(tmp_path):
     gltf_viewer.main([*common, "-o", str(tmp_path / "py.png")])
     a, b = np.asarray(Image.open(tmp_path / "cpp.png")), np.asarray(Image.open(tmp_path / "py.png"))
     assert a.shape == (64, 96, 3) and (a == b).all() and a.std() > 0
+    # the same frames split over three replicas in ONE process (rt_multi, tile partition; the box has one GPU, so all replicas
+    # sit on device 0): gathered image identical to the single-GPU one
+    r = subprocess.run([str(VIEWER), *common, "--gpus", "3", "--same-device", "-o", str(tmp_path / "multi.png")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "on 3 GPU(s)" in r.stdout
+    c = np.asarray(Image.open(tmp_path / "multi.png"))
+    assert (c == a).all()
 
 
 def test_malformed_gltf_is_an_error_not_a_crash(tmp_path):
