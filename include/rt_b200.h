@@ -332,8 +332,8 @@ int rt_trace_any(rt_scene* scene, const rt_ray* rays, uint32_t n, uint32_t flags
                  const uint32_t* rng4, uint8_t* occluded);
 /* read back the (skinned) vertex buffer the BLASes were built from (AnimationCompute.comp output) */
 int rt_scene_read_vertices(rt_scene* scene, rt_vertex* out, uint32_t n);
-/* diagnostics / tests: the 128-byte wide nodes (8 x float4: header, child meta, bfloat16 child planes) of one BLAS (geo >= 0: that geometry's own BLAS, geo < 0: the
-   merged world-space BLAS).  *n_nodes receives the node count; out may be NULL to query it. */
+/* diagnostics / tests: the 128-byte wide nodes (8 x float4: header, child meta, bfloat16 child planes) of one BLAS (geo >= 0: that geometry's own BLAS, geo == -1: the
+   merged world-space BLAS, geo == -2: the TLAS).  *n_nodes receives the node count; out may be NULL to query it. */
 int rt_scene_read_nodes(rt_scene* scene, int geo, float* out, uint32_t max_nodes, uint32_t* n_nodes);
 /* BVH statistics for DESIGN/bench: nodes, max depth, bytes */
 typedef struct rt_bvh_info {

@@ -452,7 +452,10 @@ static int build_tlas(rt_scene* s) {
     const uint32_t n = (uint32_t)s->instances.size();
     std::vector<uint32_t> entry_rec, entry_root;
     for (uint32_t i = 0; i < n; ++i) if (!s->baked[i]) { entry_rec.push_back(i); entry_root.push_back(s->geo[s->instances[i].geo_id].node_off); }
-    if (s->merged.n_tris) { entry_rec.push_back(n); entry_root.push_back(s->merged.node_off); }
+    // the merged BLAS is a TLAS entry only when it is the whole scene (SINGLE kernels); next to real instances rays start in it
+    const bool only_merged = s->merged.n_tris && entry_rec.empty();
+    s->ds.merged_first = (s->merged.n_tris && !only_merged && !getenv("RT_B200_NO_MERGED_FIRST")) ? 1u : 0u;   // (env: A/B knob)
+    if (s->merged.n_tris && !s->ds.merged_first) { entry_rec.push_back(n); entry_root.push_back(s->merged.node_off); }
     const uint32_t ne = (uint32_t)entry_rec.size();
     if (ne) {
         RT_CHECK(rt_h2d(s->d_inst_root, entry_root.data(), (size_t)ne * 4, st), "upload TLAS entries");
@@ -467,7 +470,7 @@ static int build_tlas(rt_scene* s) {
     uint32_t* tp = s->d_tlas_prims; uint32_t* le = s->d_tlas_leaf_entry;
     rt_launch(ne, st, RT_LAMBDA(size_t k) { le[k] = tp[k]; tp[k] = recd[tp[k]]; });   // TLAS leaf -> entry (kept for refits) -> instance record index
     s->tlas_nodes = info.n_nodes; s->tlas_depth = info.depth; s->tlas_entries = ne;
-    s->ds.single_merged = (ne == 1 && s->merged.n_tris) ? 1u : 0u;
+    s->ds.single_merged = only_merged ? 1u : 0u;
     s->ds.merged_node_off = s->merged.node_off; s->ds.merged_tri_off = s->merged.tri_off;
     uint32_t bd = s->merged.depth;
     for (auto& g : s->geo) if (g.needed && g.depth > bd) bd = g.depth;
@@ -1303,12 +1306,14 @@ int RT_API(rt_scene_read_vertices)(rt_scene* s, rt_vertex* out, uint32_t n) {
 int RT_API(rt_scene_read_nodes)(rt_scene* s, int geo, float* out, uint32_t max_nodes, uint32_t* n_nodes) {
     if (!s || !n_nodes) return fail("rt_scene_read_nodes: null argument");
     if (geo >= (int)s->geo.size()) return fail("rt_scene_read_nodes: geometry index out of range");
-    const GeoRecord& gr = geo < 0 ? s->merged : s->geo[geo];
+    GeoRecord tl{}; tl.needed = true; tl.n_nodes = s->tlas_nodes;          // geo == -2: the TLAS
+    const GeoRecord& gr = geo == -2 ? tl : (geo < 0 ? s->merged : s->geo[geo]);
     *n_nodes = gr.needed ? gr.n_nodes : 0u;
     if (!out || !*n_nodes) return 0;
     if (max_nodes < *n_nodes) return fail("rt_scene_read_nodes: buffer too small");
     sync_all(s->ctx);
-    RT_CHECK(rt_d2h(out, s->d_blas_nodes + (size_t)gr.node_off * RT_NODE_F4, (size_t)gr.n_nodes * RT_NODE_F4 * sizeof(float4), s->ctx->stream), "rt_scene_read_nodes");
+    const float4* src = geo == -2 ? s->d_tlas_nodes : s->d_blas_nodes + (size_t)gr.node_off * RT_NODE_F4;
+    RT_CHECK(rt_d2h(out, src, (size_t)gr.n_nodes * RT_NODE_F4 * sizeof(float4), s->ctx->stream), "rt_scene_read_nodes");
     rt_stream_sync(s->ctx->stream);
     return 0;
 }

@@ -418,8 +418,11 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                 // acquire the next node group: leave the BLAS / pop until ngroup holds an inner child or instances are parked
                 while (tv.ngroup.y <= 0x00FFFFFFu && tv.tgroup.y == 0u) {
                     if (!SINGLE && tv.blas_sp >= 0 && tv.sp == tv.blas_sp) {
-                        if (outstanding) { want_flush = true; break; }     // queued triangles refer to the object-space ray
+                        // queued triangles refer to the object-space ray; after an identity BLAS the published ray stays
+                        // valid, the flush is postponed to the next instance entry
+                        if (outstanding && !tv.identity) { want_flush = true; break; }
                         trav_leave_blas(tv, S);
+                        if (tv.ngroup.y > 0x00FFFFFFu) break;              // merged-first scenes: the TLAS root is next
                     }
                     if (tv.sp == 0) {
                         if (outstanding) { want_flush = true; break; }
@@ -437,6 +440,7 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
             bool do_work = active && !want_flush, enter = false;
             if constexpr (!SINGLE) {
                 enter = do_work && tv.tgroup.y != 0u && tv.blas_sp < 0;
+                if (enter && outstanding) { want_flush = true; do_work = false; enter = false; }   // entering republishes the lane's ray
                 const uint32_t em = __ballot_sync(0xFFFFFFFFu, enter);
                 if (em) {
                     const uint32_t others = __ballot_sync(0xFFFFFFFFu, do_work && !enter);

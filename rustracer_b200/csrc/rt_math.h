@@ -16,6 +16,9 @@ RT_D f4 mk4(float4 v) { return mk4(v.x, v.y, v.z, v.w); }
 RT_D f3 xyz(f4 v) { return mk3(v.x, v.y, v.z); }
 RT_D f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
 RT_D float comp(f3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+// a / b for a finite b > 0: the same bits as the IEEE division (0 / b keeps the sign of the zero).  A zero numerator (ior 1,
+// no transmission: every material of the Cornell scenes) sends the hardware division down its ~35-instruction slow path.
+RT_D float div_pos(float a, float b) { return a == 0.0f ? a : a / b; }
 
 RT_D f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 RT_D f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }

@@ -53,6 +53,9 @@ struct DScene {
     uint32_t n_instances;
     // when the TLAS holds nothing but the merged world-space BLAS, rays start inside it (no TLAS visit, no instance entry)
     uint32_t single_merged, merged_node_off, merged_tri_off;
+    // merged BLAS next to real instances: rays also start inside it (it is not a TLAS entry) and continue at the TLAS
+    // root when it is exhausted — one instance entry less per ray, the world-space shear is set up with the ray
+    uint32_t merged_first;
     // shading inputs in the reference's layouts
     const rt_vertex* vertices;     // skinned output (AnimationCompute.comp) == BLAS build input
     const uint32_t* indices;

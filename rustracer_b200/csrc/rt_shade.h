@@ -78,7 +78,7 @@ RT_D LobeProb brdf_probability(const Surface& m, f3 V, f3 N) {   // getBrdfProba
     float p = clampf(specular / sum, 0.001f, 0.9f);
     float d = (1.0f - p) * (1.0f - m.transmission), t = (1.0f - p) * m.transmission;
     sum = p + d + t;
-    LobeProb r; r.specular = p / sum; r.diffuse = d / sum; r.transmission = t / sum;
+    LobeProb r; r.specular = p / sum; r.diffuse = div_pos(d, sum); r.transmission = div_pos(t, sum);    // sum >= p >= 0.001
     return r;
 }
 RT_D f4 rotation_to_z(f3 v) {   // getRotationToZAxis :362-368
@@ -357,7 +357,7 @@ RT_D void shade_hit(const DScene& S, const FrameParams& P, const RtHit& hit, Pat
     m.roughness = roughness; m.ior = mat.volume_exists ? mat.ior : 1.0f;   // :320
     m.transmission = transmission; m.specular_factor = spec_factor; m.front_face = front_face;
     {   // matBuild :195-206
-        const float f = (m.ior - 1.0f) / (m.ior + 1.0f);
+        const float f = m.ior + 1.0f > 0.0f ? div_pos(m.ior - 1.0f, m.ior + 1.0f) : (m.ior - 1.0f) / (m.ior + 1.0f);
         const f3 dF0 = min3(f * f * spec_color, mk3(1.0f)) * spec_factor;
         m.F0 = mix3(dF0, color, metallic); m.F90 = mix3(spec_color, mk3(1.0f), metallic); m.c_diff = mix3(color, mk3(0.0f), metallic);
     }

@@ -56,7 +56,10 @@ RT_D float blend_random(u4 s, uint32_t instance_id, uint32_t primitive_id) {
 
 // ---- textures ----------------------------------------------------------------------------------------
 RT_D int wrap_coord(int i, int n, uint32_t mode) {
-    if (mode == RT_WRAP_REPEAT) { int m = i % n; return m < 0 ? m + n : m; }
+    if (mode == RT_WRAP_REPEAT) {
+        if ((n & (n - 1)) == 0) return i & (n - 1);      // power-of-two sizes: the same non-negative remainder without an integer division
+        int m = i % n; return m < 0 ? m + n : m;
+    }
     if (mode == RT_WRAP_MIRROR) {
         int m = i % (2 * n); if (m < 0) m += 2 * n;
         int k = m - n; k = k >= 0 ? k : -(1 + k);
@@ -64,11 +67,19 @@ RT_D int wrap_coord(int i, int n, uint32_t mode) {
     }
     return min(max(i, 0), n - 1);
 }
+// byte / 255.0f, bit for bit (the sequence is checked for the 256 inputs in tests/test_host.py, the textured parity cases
+// compare it with the oracle's division): product with the rounded reciprocal plus one residual correction.  The IEEE division it replaces takes its ~30-instruction slow path whenever the byte is 0 (a fully
+// transparent texel of a MASK texture: most of the any-hit taps in foliage).
+RT_D float unorm8(uint32_t b) {
+    const float x = (float)b, c = 0.0039215688593685626984f;
+    const float q0 = rt_fmul(x, c);
+    return rt_fma(rt_fma(-q0, 255.0f, x), c, q0);
+}
 RT_D f4 fetch_texel(const DScene& S, const DImage& im, int x, int y) {
     const uint32_t p = rt_ld(reinterpret_cast<const uint32_t*>(im.px) + ((size_t)y * im.w + x));
     const uint32_t r = p & 0xFF, g = (p >> 8) & 0xFF, b = (p >> 16) & 0xFF, a = p >> 24;
-    if (im.srgb) return mk4(rt_ld(S.srgb_lut + r), rt_ld(S.srgb_lut + g), rt_ld(S.srgb_lut + b), a / 255.0f);
-    return mk4(r / 255.0f, g / 255.0f, b / 255.0f, a / 255.0f);
+    if (im.srgb) return mk4(rt_ld(S.srgb_lut + r), rt_ld(S.srgb_lut + g), rt_ld(S.srgb_lut + b), unorm8(a));
+    return mk4(unorm8(r), unorm8(g), unorm8(b), unorm8(a));
 }
 RT_D f4 sample_image(const DScene& S, const DImage& im, uint32_t filter, uint32_t ws, uint32_t wt, f2 uv) {
     if (!(isfinite(uv.x) && isfinite(uv.y)) || im.w == 0) return mk4(0, 0, 0, 0);

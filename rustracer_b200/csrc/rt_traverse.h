@@ -123,6 +123,10 @@ RT_D uint32_t node_intersect(const float4 n0, const float4 n1, const float4 x03,
 }
 
 enum { RT_MODE_CLOSEST = 0, RT_MODE_ANY = 1 };
+#ifdef RT_EMU_PROFILE
+static unsigned long long g_emu_prof[8];   // developer probe (host emulation only): node visits per level, triangle tests per BLAS kind
+extern "C" unsigned long long* emu_prof() { return g_emu_prof; }
+#endif
 
 // Resumable traversal state: init() then step() until it returns true.  The persistent extend kernel keeps one of
 // these per lane and refills finished lanes with new rays (dynamic fetch); trace_ray() below simply loops.
@@ -151,8 +155,8 @@ RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tm
     t.nodes = S.tlas_nodes; t.tri_off = 0; t.blas_sp = -1; t.cur_inst = 0; t.cur_geo = 0; t.cur_alpha = false; t.merged = false; t.identity = false;
     t.ngroup = make_uint2(0u, 0x80000000u); t.tgroup = make_uint2(0u, 0u); t.sp = 0;
     t.hit.t = tmax; t.hit.u = 0.0f; t.hit.v = 0.0f; t.hit.inst = 0xFFFFFFFFu; t.hit.prim = 0xFFFFFFFFu; t.found = false;
-    if (SINGLE || S.single_merged) {
-        // the whole scene is the merged world-space BLAS: start inside it
+    if (SINGLE || S.single_merged || S.merged_first) {
+        // the whole scene is the merged world-space BLAS, or it is traversed first: start inside it
         t.nodes = S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4; t.tri_off = S.merged_tri_off;
         t.blas_sp = 0; t.identity = true; t.merged = true; t.cur_inst = S.n_instances;
         t.sh = shear_init(dw);
@@ -163,6 +167,8 @@ RT_D void trav_init(Trav& t, const DScene& S, f3 ow, f3 dw, float tmin, float tm
 RT_D void trav_leave_blas(Trav& t, const DScene& S) {
     t.blas_sp = -1; t.nodes = S.tlas_nodes;
     if (!t.identity) trav_set_level_ray(t, t.ow, t.dw);
+    // DScene::merged_first: the merged BLAS was the start of the ray, not a TLAS entry; the TLAS root comes next
+    if (t.merged && S.merged_first) { t.merged = false; t.ngroup = make_uint2(0u, 0x80000000u); }
 }
 
 // The traversal is a "while-while" loop (Aila & Laine 2009) over two kinds of steps:
@@ -189,13 +195,19 @@ RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
         const float4* np = (SINGLE ? S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4 : t.nodes) + (size_t)(child_base + rel) * RT_NODE_F4;
         const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4), n5 = rt_ld(np + 5), n6 = rt_ld(np + 6), n7 = rt_ld(np + 7);
         if (COUNT) c4[0]++;
+#ifdef RT_EMU_PROFILE
+        g_emu_prof[t.blas_sp < 0 ? 0 : (t.merged ? 1 : 2)]++;
+#endif
         const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, n5, n6, n7, t.o, t.idir, t.octinv, t.tmin, t.hit.t);
         t.ngroup.x = rt_float_as_uint(n1.x); t.tgroup.x = rt_float_as_uint(n1.y);
         t.ngroup.y = (hm & 0xFF000000u) | (rt_float_as_uint(n0.w) >> 24);
         t.tgroup.y = hm & 0x00FFFFFFu;
         return false;
     }
-    if (t.blas_sp >= 0 && t.sp == t.blas_sp) trav_leave_blas(t, S);
+    if (t.blas_sp >= 0 && t.sp == t.blas_sp) {
+        trav_leave_blas(t, S);
+        if (t.ngroup.y > 0x00FFFFFFu) return false;        // merged-first scenes: the TLAS root
+    }
     if (t.sp == 0) return true;
     const uint2 e = stack[--t.sp];
     if (e.y > 0x00FFFFFFu) { t.ngroup = e; } else { t.tgroup = e; t.ngroup = make_uint2(0u, 0u); }
@@ -213,6 +225,9 @@ RT_D void trav_enter_instance(Trav& t, const DScene& S, uint2* stack, unsigned l
     const float4* ip = S.inst_w2o + (size_t)inst * RT_INST_F4;
     const float4 r0 = rt_ld(ip), r1 = rt_ld(ip + 1), r2 = rt_ld(ip + 2), meta = rt_ld(ip + 3);
     if (COUNT) c4[2]++;
+#ifdef RT_EMU_PROFILE
+    g_emu_prof[5]++;
+#endif
     const uint32_t flags = rt_float_as_uint(meta.z);
     t.identity = (flags & RT_INST_IDENTITY) != 0u; t.merged = (flags & RT_INST_MERGED) != 0u;
     if (t.identity) {
@@ -260,6 +275,9 @@ RT_D bool trav_prim_step(Trav& t, const DScene& S, uint2* stack, unsigned long l
     const float4* tp = S.tris + (size_t)(t.tri_off + t.tgroup.x + bit) * RT_TRI_F4;
     const float4 a = rt_ld(tp), b = rt_ld(tp + 1), c = rt_ld(tp + 2);
     if (COUNT) c4[1]++;
+#ifdef RT_EMU_PROFILE
+    g_emu_prof[t.merged ? 3 : 4]++;
+#endif
     float tt, bu, bv;
     if (!tri_test(t.sh, t.o, xyz(a), xyz(b), xyz(c), t.tmin, t.tmax, tt, bu, bv)) return false;
     const uint32_t prim = rt_float_as_uint(a.w);

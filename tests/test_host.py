@@ -405,3 +405,16 @@ def test_malformed_gltf_is_an_error_not_a_crash(tmp_path):
         raw = bytearray(base64.b64decode(g["buffers"][0]["uri"].split(",", 1)[1])); raw[64:76] = idx_bad
         g["buffers"][0]["uri"] = "data:application/octet-stream;base64," + base64.b64encode(bytes(raw)).decode()
     broken(bad_index)                                                                           # vertex index beyond the vertex count
+
+
+def test_unorm8_sequence_equals_division():
+    """rt_surface.h unorm8(): x * rn(1/255) plus one fused residual correction is byte / 255.0f for every byte (the product
+    alone differs for 126 of them).  The fused multiply-adds are evaluated exactly in float64 and rounded once."""
+    x = np.arange(256, dtype=np.float32)
+    c = np.float32(0.0039215688593685626984)
+    assert c == np.float32(1) / np.float32(255)
+    q0 = (x * c).astype(np.float32)
+    r = (x.astype(np.float64) - q0.astype(np.float64) * 255.0).astype(np.float32)
+    q = (r.astype(np.float64) * np.float64(c) + q0.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(q, x / np.float32(255))
+    assert np.count_nonzero(q0 != x / np.float32(255)) > 0
