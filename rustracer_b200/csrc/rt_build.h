@@ -118,6 +118,8 @@ struct WideOut {
     DAabb* node_box;        // unquantised box per wide node (refit / TLAS input)
     uint32_t* node_parent;  // parent wide node (0xFFFFFFFF for the root)
     uint32_t max_nodes;
+    uint32_t leaf_max = RT_LEAF_MAX;   // primitives a leaf slot may hold (<= RT_LEAF_MAX).  The TLAS uses 1: entering an
+                                       // instance costs ~200 instructions, so every instance gets its own box test first
 };
 
 // ---- bfloat16 child planes (rt_scene_dev.h: node layout) ----------------------------------------------------
@@ -161,13 +163,13 @@ RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, c
                         uint32_t bin, uint32_t wide, uint32_t parent_wide, WideOut out, uint32_t* counters, uint2* q_out, uint32_t* q_out_count) {
     auto count_of = [&](uint32_t c) -> uint32_t { return c >= (uint32_t)(n - 1) ? 1u : bin_count[c]; };
     uint32_t ch[8]; int nch = 0;
-    if (n == 1 || count_of(bin) <= RT_LEAF_MAX) { ch[nch++] = bin; }
+    if (n == 1 || count_of(bin) <= out.leaf_max) { ch[nch++] = bin; }
     else { ch[nch++] = (uint32_t)bin_children[bin].x; ch[nch++] = (uint32_t)bin_children[bin].y; }
     // greedy: open the child with the largest surface area until 8 children or nothing left to open
     while (nch < 8) {
         int best = -1; float best_area = -1.0f;
         for (int i = 0; i < nch; ++i) {
-            if (count_of(ch[i]) <= RT_LEAF_MAX) continue;
+            if (count_of(ch[i]) <= out.leaf_max) continue;
             const float a = aabb_half_area(bin_box[ch[i]]);
             if (a > best_area) { best_area = a; best = i; }
         }
@@ -180,7 +182,7 @@ RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, c
     while (nch < 8) {
         int best = -1; float best_area = -1.0f;
         for (int i = 0; i < nch; ++i) {
-            if (ch[i] >= (uint32_t)(n - 1) || count_of(ch[i]) > RT_LEAF_MAX) continue;   // single primitive / inner child
+            if (ch[i] >= (uint32_t)(n - 1) || count_of(ch[i]) > out.leaf_max) continue;   // single primitive / inner child
             const float a = aabb_half_area(bin_box[ch[i]]);
             if (a > best_area) { best_area = a; best = i; }
         }
@@ -213,7 +215,7 @@ RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, c
     for (int s = 0; s < 8; ++s) {
         if (slot_child[s] < 0) continue;
         const uint32_t c = ch[slot_child[s]], cnt = count_of(c);
-        if (cnt <= RT_LEAF_MAX) n_prims += cnt; else n_inner++;
+        if (cnt <= out.leaf_max) n_prims += cnt; else n_inner++;
     }
     const uint32_t child_base = n_inner ? rt_atomic_add(&counters[0], n_inner) : 0u;
     const uint32_t prim_base = n_prims ? rt_atomic_add(&counters[1], n_prims) : 0u;
@@ -223,8 +225,8 @@ RT_D void collapse_node(int n, const int2* bin_children, const DAabb* bin_box, c
         if (slot_child[s] < 0) continue;
         const uint32_t c = ch[slot_child[s]], cnt = count_of(c);
         cbox[s] = (n == 1) ? bin_box[0] : bin_box[c];
-        if (cnt <= RT_LEAF_MAX) {
-            // gather the (<= RT_LEAF_MAX) primitives below c, left to right
+        if (cnt <= out.leaf_max) {
+            // gather the (<= out.leaf_max <= RT_LEAF_MAX) primitives below c, left to right
             uint32_t stack[RT_LEAF_MAX]; int sp = 0; uint32_t cur = c, k = 0;
             for (;;) {
                 if (cur >= (uint32_t)(n - 1) || n == 1) {

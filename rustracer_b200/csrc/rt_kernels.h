@@ -456,7 +456,8 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
                         coop_publish_ray<ALPHA, SINGLE>(tv, sh, lane);
                     } else {
                         // BLAS level with leftover leaf triangles parked: queue those first; else visit the next node
-                        if (tv.tgroup.y == 0u) trav_node_step<COUNT, SINGLE>(tv, S, stack, c4);
+                        // (the acquire loop above left an inner child in ngroup unless primitives are parked)
+                        if (tv.tgroup.y == 0u) trav_visit_child<COUNT, SINGLE>(tv, S, stack, c4);
                         if ((SINGLE || tv.blas_sp >= 0) && tv.tgroup.y != 0u) {
                             leaf_base = (SINGLE ? S.merged_tri_off : tv.tri_off) + tv.tgroup.x;
                             leaf_mask = tv.tgroup.y;

@@ -182,28 +182,31 @@ RT_D void trav_leave_blas(Trav& t, const DScene& S) {
 // phases execute with most lanes active instead of interleaving per lane.
 // MODE: closest / any (terminate on first accepted hit).  ALPHA: run the alpha test on non-opaque geometry
 // (false == gl_RayFlagsOpaqueEXT / the reference's `fully_opaque` pipeline without any-hit shaders).
+// visits the next inner child of ngroup (precondition: ngroup holds one): one 128-byte node, 8 box tests
+template <bool COUNT, bool SINGLE = false>
+RT_D void trav_visit_child(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
+    const uint32_t hits = t.ngroup.y, imask = t.ngroup.y;
+    const int child_bit = rt_bfind(hits);
+    const uint32_t child_base = t.ngroup.x;
+    t.ngroup.y &= ~(1u << child_bit);
+    if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
+    const uint32_t slot = (uint32_t)(child_bit - 24) ^ (t.octinv & 7u);
+    const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+    const float4* np = (SINGLE ? S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4 : t.nodes) + (size_t)(child_base + rel) * RT_NODE_F4;
+    const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4), n5 = rt_ld(np + 5), n6 = rt_ld(np + 6), n7 = rt_ld(np + 7);
+    if (COUNT) c4[0]++;
+#ifdef RT_EMU_PROFILE
+    g_emu_prof[t.blas_sp < 0 ? 0 : (t.merged ? 1 : 2)]++;
+#endif
+    const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, n5, n6, n7, t.o, t.idir, t.octinv, t.tmin, t.hit.t);
+    t.ngroup.x = rt_float_as_uint(n1.x); t.tgroup.x = rt_float_as_uint(n1.y);
+    t.ngroup.y = (hm & 0xFF000000u) | (rt_float_as_uint(n0.w) >> 24);
+    t.tgroup.y = hm & 0x00FFFFFFu;
+}
+
 template <bool COUNT, bool SINGLE = false>
 RT_D bool trav_node_step(Trav& t, const DScene& S, uint2* stack, unsigned long long* c4) {
-    if (t.ngroup.y > 0x00FFFFFFu) {
-        const uint32_t hits = t.ngroup.y, imask = t.ngroup.y;
-        const int child_bit = rt_bfind(hits);
-        const uint32_t child_base = t.ngroup.x;
-        t.ngroup.y &= ~(1u << child_bit);
-        if (t.ngroup.y > 0x00FFFFFFu) stack[t.sp++] = t.ngroup;
-        const uint32_t slot = (uint32_t)(child_bit - 24) ^ (t.octinv & 7u);
-        const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-        const float4* np = (SINGLE ? S.blas_nodes + (size_t)S.merged_node_off * RT_NODE_F4 : t.nodes) + (size_t)(child_base + rel) * RT_NODE_F4;
-        const float4 n0 = rt_ld(np), n1 = rt_ld(np + 1), n2 = rt_ld(np + 2), n3 = rt_ld(np + 3), n4 = rt_ld(np + 4), n5 = rt_ld(np + 5), n6 = rt_ld(np + 6), n7 = rt_ld(np + 7);
-        if (COUNT) c4[0]++;
-#ifdef RT_EMU_PROFILE
-        g_emu_prof[t.blas_sp < 0 ? 0 : (t.merged ? 1 : 2)]++;
-#endif
-        const uint32_t hm = node_intersect(n0, n1, n2, n3, n4, n5, n6, n7, t.o, t.idir, t.octinv, t.tmin, t.hit.t);
-        t.ngroup.x = rt_float_as_uint(n1.x); t.tgroup.x = rt_float_as_uint(n1.y);
-        t.ngroup.y = (hm & 0xFF000000u) | (rt_float_as_uint(n0.w) >> 24);
-        t.tgroup.y = hm & 0x00FFFFFFu;
-        return false;
-    }
+    if (t.ngroup.y > 0x00FFFFFFu) { trav_visit_child<COUNT, SINGLE>(t, S, stack, c4); return false; }
     if (t.blas_sp >= 0 && t.sp == t.blas_sp) {
         trav_leave_blas(t, S);
         if (t.ngroup.y > 0x00FFFFFFu) return false;        // merged-first scenes: the TLAS root

@@ -34,4 +34,9 @@ if [ -f gpurun_out/prof_extend_c3.ncu-rep ]; then
     echo "# basic-block breakdown, launch 1: the instance entry (rt_traverse.h trav_enter_instance), the leaf pushes and the any-hit evaluation run at 2-3 lanes"
     python scripts/ncu_sass_flow.py /tmp/r2_c3_src.csv 1 > /tmp/r2_flow.txt; head -1 /tmp/r2_flow.txt; python scripts/ncu_blocks.py /tmp/r2_flow.txt 0.9 | cut -c1-190; } > profiles/${R}_extend_config3_ncu.txt 2>&1
 fi
+if [ -f gpurun_out/prof_skin_c4.ncu-rep ]; then
+  { echo "# config 4 (1 M-triangle skinned character): skin_kernel and refit_nodes_kernel, ncu --set full --clock-control none, one steady-state update"
+    echo "# (bench.py --config 4 --steps 2 --warmup 3 --frames-in-flight 1).  Algorithmic bytes of skinning: 256 B per vertex (128 B in + 128 B out)."
+    python scripts/ncu_summary.py gpurun_out/prof_skin_c4.ncu-rep 4 0 2>&1 | grep -v "^total\|inst  " ; } > profiles/${R}_skin_refit_config4_ncu.txt 2>&1
+fi
 echo "profiles/${R}_* refreshed"; ls -la profiles | grep r02

@@ -18,6 +18,14 @@ for K in extend_kernel shade_kernel; do
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-alt-camera --frames-in-flight 1 > gpurun_out/ncu_full_$K.log 2>&1
   tail -1 gpurun_out/ncu_full_$K.log
 done
+echo "== ncu full, config 3 two-level extend kernel (bounces 0..3 of one steady-state frame)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:extend_kernel -s 24 -c 4 -f -o gpurun_out/prof_extend_c3 \
+    python bench.py --config 3 --steps 2 --warmup 3 --no-cpu-baseline --frames-in-flight 1 > gpurun_out/ncu_full_c3.log 2>&1
+tail -1 gpurun_out/ncu_full_c3.log | cut -c1-150
+echo "== ncu full, config 4 skinning + refit kernels (one steady-state update)"
+timeout 900 ncu --set full --clock-control none -k regex:"skin_kernel|refit_nodes_kernel" -s 6 -c 4 -f -o gpurun_out/prof_skin_c4 \
+    python bench.py --config 4 --steps 2 --warmup 3 --no-cpu-baseline --frames-in-flight 1 > gpurun_out/ncu_full_c4.log 2>&1
+tail -1 gpurun_out/ncu_full_c4.log | cut -c1-150
 echo "== configs"
 for c in 1 3 4 5; do
   timeout 900 python bench.py --config $c --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/config_$c.json | python scripts/show_bench.py

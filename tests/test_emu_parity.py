@@ -63,3 +63,27 @@ def test_emu_textured_materials():
 
 def test_emu_lifecycle_in_flight(cornell_desc):
     pc.case_lifecycle_in_flight(emu_api(), cornell_desc, size=16)
+
+
+def test_flat_scene_morton_cells_stay_cubic(monkeypatch):
+    """A flat field of instances + baked foliage cards (config 3 in small): normalising the Morton codes per axis stretches the
+    thin axis until its bits are noise (round 1).  The builder clamps the per-axis stretch (RT_MORTON_MAX_ASPECT): the same
+    frame must need clearly fewer node visits than with the round-1 normalisation, and the two images must be identical."""
+    import numpy as np
+    from rustracer_b200 import core, host, scenes, _ffi as F
+    d = scenes.instanced_foliage(n_side=48, tris_per_mesh=1000, cards=32, tex_size=64, sky=scenes.procedural_sky(16))
+    cam = host.Camera(96, 54).set(position=(0, 1.2, 7.0))
+    gui = host.Gui(number_of_samples=1, number_of_bounces=4, sky=1)
+    import ctypes as C
+    u = F.rt_ubo(); total = F.c_u32(0)
+    F.load_host().gv_build_ubo(C.byref(cam.c), C.byref(gui.g), C.byref(total), 0, 0, 3, C.byref(u))
+    out = {}
+    for name, env in (("cubic", None), ("per_axis", "1e30")):
+        if env: monkeypatch.setenv("RT_B200_MORTON_ASPECT", env)
+        ctx = core.Context(96, 54, api=emu_api()); sc = core.Scene(ctx, d)
+        ctx.render(sc, u, flags=1)          # RT_RENDER_COUNTERS
+        ctx.synchronize()
+        st = ctx.stats()
+        out[name] = (st.nodes / max(st.rays_extend, 1), ctx.readback()[0].copy())
+    assert np.array_equal(out["cubic"][1], out["per_axis"][1])
+    assert out["cubic"][0] < 0.9 * out["per_axis"][0], (out["cubic"][0], out["per_axis"][0])
