@@ -514,7 +514,8 @@ RT_D void persistent_trace(const DScene& S, const uint32_t count, uint32_t* fetc
 #endif
         } while (holding && (exhausted || __popc(holding) >= RT_REFILL_BELOW));
         // lanes whose any-hit ray retired early may still own queued items: drain so they can be refilled
-        if (__any_sync(0xFFFFFFFFu, !active && outstanding != 0u)) {
+        // (a closest-hit lane only retires with an empty queue share: no second copy of the round in those kernels)
+        if constexpr (MODE == RT_MODE_ANY) if (__any_sync(0xFFFFFFFFu, !active && outstanding != 0u)) {
             while (q_count) {
                 const uint32_t n = q_count < 32u ? q_count : 32u;
                 bool terminated = false;
