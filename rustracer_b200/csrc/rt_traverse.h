@@ -27,14 +27,25 @@ RT_D RayShear shear_init(f3 d) {
 
 // Woop/Benthin/Wald watertight test; every operation is an explicitly rounded IEEE op (no FMA contraction),
 // so the result is bit-identical to the oracle's.
+// (kx, ky, kz) is always a cyclic rotation of (0, 1, 2) (shear_init): v rotated so that .z is the kz component.  Bitwise
+// selects on two masks: the chained ?: of comp() compiled to nine divergent branches per triangle in the cooperative
+// round, where the 32 lanes test triangles against rays of different major axes.
+RT_D f3 rotate_to_shear(f3 v, uint32_t m0, uint32_t m1) {      // m0 = all ones if kz == 0, m1 = all ones if kz == 1
+    const uint32_t x = rt_float_as_uint(v.x), y = rt_float_as_uint(v.y), z = rt_float_as_uint(v.z);
+    const uint32_t rx = (y & m0) | (((z & m1) | (x & ~m1)) & ~m0);       // kz 0: y   kz 1: z   kz 2: x
+    const uint32_t ry = (z & m0) | (((x & m1) | (y & ~m1)) & ~m0);       //       z         x         y
+    const uint32_t rz = (x & m0) | (((y & m1) | (z & ~m1)) & ~m0);       //       x         y         z
+    return mk3(rt_uint_as_float(rx), rt_uint_as_float(ry), rt_uint_as_float(rz));
+}
 RT_D bool tri_test(const RayShear& r, f3 o, f3 v0, f3 v1, f3 v2, float tmin, float tmax, float& t, float& bu, float& bv) {
-    const f3 A = mk3(rt_fsub(v0.x, o.x), rt_fsub(v0.y, o.y), rt_fsub(v0.z, o.z));
-    const f3 B = mk3(rt_fsub(v1.x, o.x), rt_fsub(v1.y, o.y), rt_fsub(v1.z, o.z));
-    const f3 C = mk3(rt_fsub(v2.x, o.x), rt_fsub(v2.y, o.y), rt_fsub(v2.z, o.z));
-    const float Akz = comp(A, r.kz), Bkz = comp(B, r.kz), Ckz = comp(C, r.kz);
-    const float Ax = rt_fsub(comp(A, r.kx), rt_fmul(r.Sx, Akz)), Ay = rt_fsub(comp(A, r.ky), rt_fmul(r.Sy, Akz));
-    const float Bx = rt_fsub(comp(B, r.kx), rt_fmul(r.Sx, Bkz)), By = rt_fsub(comp(B, r.ky), rt_fmul(r.Sy, Bkz));
-    const float Cx = rt_fsub(comp(C, r.kx), rt_fmul(r.Sx, Ckz)), Cy = rt_fsub(comp(C, r.ky), rt_fmul(r.Sy, Ckz));
+    const uint32_t m0 = r.kz == 0 ? 0xFFFFFFFFu : 0u, m1 = r.kz == 1 ? 0xFFFFFFFFu : 0u;
+    const f3 A = rotate_to_shear(mk3(rt_fsub(v0.x, o.x), rt_fsub(v0.y, o.y), rt_fsub(v0.z, o.z)), m0, m1);
+    const f3 B = rotate_to_shear(mk3(rt_fsub(v1.x, o.x), rt_fsub(v1.y, o.y), rt_fsub(v1.z, o.z)), m0, m1);
+    const f3 C = rotate_to_shear(mk3(rt_fsub(v2.x, o.x), rt_fsub(v2.y, o.y), rt_fsub(v2.z, o.z)), m0, m1);
+    const float Akz = A.z, Bkz = B.z, Ckz = C.z;
+    const float Ax = rt_fsub(A.x, rt_fmul(r.Sx, Akz)), Ay = rt_fsub(A.y, rt_fmul(r.Sy, Akz));
+    const float Bx = rt_fsub(B.x, rt_fmul(r.Sx, Bkz)), By = rt_fsub(B.y, rt_fmul(r.Sy, Bkz));
+    const float Cx = rt_fsub(C.x, rt_fmul(r.Sx, Ckz)), Cy = rt_fsub(C.y, rt_fmul(r.Sy, Ckz));
     float U = rt_fsub(rt_fmul(Cx, By), rt_fmul(Cy, Bx));
     float V = rt_fsub(rt_fmul(Ax, Cy), rt_fmul(Ay, Cx));
     float W = rt_fsub(rt_fmul(Bx, Ay), rt_fmul(By, Ax));
