@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(RT_SKIN_TILE) skin_kernel(const rt_vertex* vin
 //    outstanding items before it leaves a BLAS or retires its ray.
 // MODE selects closest-hit (extend) or any-hit (shadow) semantics.
 #ifndef RT_REFILL_BELOW
-#define RT_REFILL_BELOW 22     // refill when fewer than this many lanes still hold a ray
+#define RT_REFILL_BELOW 16     // refill when fewer than this many lanes still hold a ray (sweep 6..32 on config 2: flat optimum at 14-18; a refill costs ~150 instructions at few lanes)
 #endif
 #define RT_WARPS_PER_BLOCK (RT_EXTEND_THREADS / 32)
 #ifndef RT_NODE_STEPS

@@ -10,23 +10,6 @@ struct RtHit { float t, u, v; uint32_t inst, prim; };
 
 struct RayShear { int kx, ky, kz; float Sx, Sy, Sz; };
 
-RT_D RayShear shear_init(f3 d) {
-    RayShear r;
-    int kz = 0; float m = fabsf(d.x);
-    if (fabsf(d.y) > m) { kz = 1; m = fabsf(d.y); }
-    if (fabsf(d.z) > m) { kz = 2; }
-    int kx = kz + 1; if (kx == 3) kx = 0;
-    int ky = kx + 1; if (ky == 3) ky = 0;
-    const float dz = comp(d, kz);
-    // (the paper swaps kx/ky when d[kz] < 0 to preserve winding; for a two-sided test the swap negates U, V, W, det
-    //  and T together and leaves t, u, v bit-identical, so it is omitted here and in the oracle)
-    r.kx = kx; r.ky = ky; r.kz = kz;
-    r.Sx = rt_fdiv(comp(d, kx), dz); r.Sy = rt_fdiv(comp(d, ky), dz); r.Sz = rt_fdiv(1.0f, dz);
-    return r;
-}
-
-// Woop/Benthin/Wald watertight test; every operation is an explicitly rounded IEEE op (no FMA contraction),
-// so the result is bit-identical to the oracle's.
 // (kx, ky, kz) is always a cyclic rotation of (0, 1, 2) (shear_init): v rotated so that .z is the kz component.  Bitwise
 // selects on two masks: the chained ?: of comp() compiled to nine divergent branches per triangle in the cooperative
 // round, where the 32 lanes test triangles against rays of different major axes.
@@ -37,6 +20,24 @@ RT_D f3 rotate_to_shear(f3 v, uint32_t m0, uint32_t m1) {      // m0 = all ones 
     const uint32_t rz = (x & m0) | (((y & m1) | (z & ~m1)) & ~m0);       //       x         y         z
     return mk3(rt_uint_as_float(rx), rt_uint_as_float(ry), rt_uint_as_float(rz));
 }
+RT_D RayShear shear_init(f3 d) {
+    RayShear r;
+    int kz = 0; float m = fabsf(d.x);
+    if (fabsf(d.y) > m) { kz = 1; m = fabsf(d.y); }
+    if (fabsf(d.z) > m) { kz = 2; }
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    const f3 ds = rotate_to_shear(d, kz == 0 ? 0xFFFFFFFFu : 0u, kz == 1 ? 0xFFFFFFFFu : 0u);    // (d[kx], d[ky], d[kz])
+    const float dz = ds.z;
+    // (the paper swaps kx/ky when d[kz] < 0 to preserve winding; for a two-sided test the swap negates U, V, W, det
+    //  and T together and leaves t, u, v bit-identical, so it is omitted here and in the oracle)
+    r.kx = kx; r.ky = ky; r.kz = kz;
+    r.Sx = rt_fdiv(ds.x, dz); r.Sy = rt_fdiv(ds.y, dz); r.Sz = rt_fdiv(1.0f, dz);
+    return r;
+}
+
+// Woop/Benthin/Wald watertight test; every operation is an explicitly rounded IEEE op (no FMA contraction),
+// so the result is bit-identical to the oracle's.
 RT_D bool tri_test(const RayShear& r, f3 o, f3 v0, f3 v1, f3 v2, float tmin, float tmax, float& t, float& bu, float& bv) {
     const uint32_t m0 = r.kz == 0 ? 0xFFFFFFFFu : 0u, m1 = r.kz == 1 ? 0xFFFFFFFFu : 0u;
     const f3 A = rotate_to_shear(mk3(rt_fsub(v0.x, o.x), rt_fsub(v0.y, o.y), rt_fsub(v0.z, o.z)), m0, m1);
