@@ -252,7 +252,7 @@ static int run_skinning(rt_scene* s) {
     const rt_vertex* vin = s->d_vin; rt_vertex* vout = s->d_vout; const float* skins = s->d_skins; const uint32_t ns = s->n_skins;
 #ifndef RT_EMU
     if (s->n_vertices) {
-        size_t blocks = ((size_t)s->n_vertices + RT_SKIN_TILE - 1) / RT_SKIN_TILE; const size_t cap = (size_t)g_rt_sm_count * 12;
+        size_t blocks = ((size_t)s->n_vertices + RT_SKIN_TILE - 1) / RT_SKIN_TILE; const size_t cap = (size_t)g_rt_sm_count * RT_SKIN_CTAS_PER_SM;   // persistent: every CTA streams several double-buffered tiles
         if (blocks > cap) blocks = cap;
         skin_kernel<<<(unsigned)blocks, RT_SKIN_TILE, 0, st>>>(vin, vout, skins, ns, s->n_vertices);
         ++g_rt_launch_count;

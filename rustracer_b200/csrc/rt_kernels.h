@@ -214,27 +214,47 @@ RT_D DAabb tri_box_of(const rt_vertex* verts, const uint32_t* indices, uint32_t 
 // Skinning as a streaming kernel: a CTA stages 128 vertices (16 KB) through shared memory so that every global access is
 // a fully coalesced 16-byte-per-lane stream (one thread per vertex reading its own 128-byte record touches 32 cache
 // lines per load instruction); each thread then transforms its vertex out of shared memory.  Rows are padded to 9
-// float4 so the per-vertex accesses of a quarter warp fall into distinct banks.
+// float4 so the per-vertex accesses of a quarter warp fall into distinct banks.  The tiles are double-buffered: the
+// asynchronous copies (cp.async, 16 B per lane, global -> shared without a register round trip) of the CTA's next tile are
+// in flight while the current one is transformed and stored, so the load latency is no longer exposed once per tile
+// (ncu, config 4: 54 % of the stall samples were long-scoreboard waits of the staging loads).
 #define RT_SKIN_TILE 128
+#define RT_SKIN_CTAS_PER_SM 6      // 2 x 18 KB of shared memory per CTA
+RT_D void skin_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 __global__ void __launch_bounds__(RT_SKIN_TILE) skin_kernel(const rt_vertex* vin, rt_vertex* vout, const float* skins, uint32_t n_skins, uint32_t n) {
-    __shared__ float4 tile[RT_SKIN_TILE * 9];
+    __shared__ float4 tile[2][RT_SKIN_TILE * 9];
     const float4* src = reinterpret_cast<const float4*>(vin); float4* dst = reinterpret_cast<float4*>(vout);
-    for (uint32_t base = blockIdx.x * RT_SKIN_TILE; base < n; base += gridDim.x * RT_SKIN_TILE) {
-        const uint32_t cnt = n - base < RT_SKIN_TILE ? n - base : RT_SKIN_TILE;
-        for (uint32_t f = threadIdx.x; f < cnt * 8u; f += RT_SKIN_TILE) tile[(f >> 3) * 9u + (f & 7u)] = __ldcs(src + (size_t)base * 8u + f);
+    const uint32_t stride = gridDim.x * RT_SKIN_TILE;
+    auto stage = [&](uint32_t base, int buf) {           // issues this thread's copies of tile `base` (possibly none) as one group
+        if (base < n) {
+            const uint32_t cnt = n - base < RT_SKIN_TILE ? n - base : RT_SKIN_TILE;
+            for (uint32_t f = threadIdx.x; f < cnt * 8u; f += RT_SKIN_TILE) skin_cp_async16(&tile[buf][(f >> 3) * 9u + (f & 7u)], src + (size_t)base * 8u + f);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t base = blockIdx.x * RT_SKIN_TILE; int buf = 0;
+    stage(base, 0);
+    for (; base < n; base += stride, buf ^= 1) {
+        stage(base + stride, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the newest group: the current tile has landed
         __syncthreads();
+        const uint32_t cnt = n - base < RT_SKIN_TILE ? n - base : RT_SKIN_TILE;
+        float4* t = tile[buf];
         if (threadIdx.x < cnt) {
             float4 r[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = tile[threadIdx.x * 9u + k];
+            for (int k = 0; k < 8; ++k) r[k] = t[threadIdx.x * 9u + k];
             skin_transform(r, skins, n_skins);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) tile[threadIdx.x * 9u + k] = r[k];      // only position / normal / tangent change
+            for (int k = 0; k < 3; ++k) t[threadIdx.x * 9u + k] = r[k];      // only position / normal / tangent change
         }
         __syncthreads();
-        for (uint32_t f = threadIdx.x; f < cnt * 8u; f += RT_SKIN_TILE) dst[(size_t)base * 8u + f] = tile[(f >> 3) * 9u + (f & 7u)];
-        __syncthreads();
+        for (uint32_t f = threadIdx.x; f < cnt * 8u; f += RT_SKIN_TILE) __stcs(dst + (size_t)base * 8u + f, t[(f >> 3) * 9u + (f & 7u)]);
+        __syncthreads();                                          // the buffer is staged again at the top of the next iteration but one
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 #define RT_EXTEND_THREADS 128
 #ifndef RT_EXTEND_MIN_BLOCKS
