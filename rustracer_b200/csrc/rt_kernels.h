@@ -608,6 +608,9 @@ RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" :
 #ifndef RT_SHADE_SORT
 #define RT_SHADE_SORT 1       // 1: material-sorted shading (CTA-local counting sort of each 128-path tile), 0: queue order
 #endif
+#ifndef RT_SHADE_OCTSORT
+#define RT_SHADE_OCTSORT 1    // next-bounce queue grouped by direction octant inside each 128-path tile
+#endif
 #define RT_SHADE_CLASSES 32   // class 0 = miss, 1..30 = material id (mod 30), 31 = no path (tail of the last tile)
 
 // Material-sorted closest-hit shading (north_star: "a material-sorted ... closest-hit shading pass").  The reference's
@@ -676,6 +679,32 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
             const uint32_t hit_mask = __ballot_sync(0xFFFFFFFFu, r.hit);
             if (hit_mask && lane == 0) atomicAdd(hit_count, (uint32_t)__popc(hit_mask));
         }
+#if RT_SHADE_SORT && RT_SHADE_OCTSORT
+        {   // compaction of the tile's surviving paths, grouped by the direction octant of the next ray: the traversal kernel
+            // refills its warps with runs of consecutive rays, and rays that start close together (one 128-path tile) and
+            // leave into the same octant walk the same part of the tree in the same order
+            const uint32_t key = r.alive ? (7u - octant_inv(r.next.dir)) : 8u;
+            __syncthreads();                                   // s_hist / s_wsum are free again
+            if (threadIdx.x < 36u) s_hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+            const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            if (rank == 0u) s_hist[key * 4u + warp] = (uint32_t)__popc(peers);
+            __syncthreads();
+            if (warp == 0u) {                                  // exclusive scan of the 32 (octant-major, warp-minor) counts, one atomic per tile
+                const uint32_t v = s_hist[lane];
+                uint32_t incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+                if (lane == 31u) s_wsum[0] = incl ? atomicAdd(out_count, incl) : 0u;
+                s_hist[lane] = incl - v;
+            }
+            __syncthreads();
+            const uint32_t slot = s_wsum[0] + s_hist[(key & 7u) * 4u + warp] + rank;
+            __syncthreads();                                   // the next tile's sort reuses s_hist / s_wsum
+            if (r.alive) store_path(qout, slot, r.next);
+        }
+#else
         const uint32_t alive_mask = __ballot_sync(0xFFFFFFFFu, r.alive);
         if (alive_mask) {
             uint32_t slot0 = 0;
@@ -683,6 +712,7 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
             slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
             if (r.alive) store_path(qout, slot0 + (uint32_t)__popc(alive_mask & ((1u << lane) - 1u)), r.next);
         }
+#endif
         const uint32_t sh_mask = __ballot_sync(0xFFFFFFFFu, r.has_shadow);
         if (sh_mask) {
             uint32_t slot0 = 0;
