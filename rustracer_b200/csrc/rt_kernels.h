@@ -609,8 +609,9 @@ RT_D void rt_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" :
 #define RT_SHADE_SORT 1       // 1: material-sorted shading (CTA-local counting sort of each 128-path tile), 0: queue order
 #endif
 #ifndef RT_SHADE_OCTSORT
-#define RT_SHADE_OCTSORT 1    // next-bounce queue grouped by direction octant inside each 128-path tile
+#define RT_SHADE_OCTSORT 1    // next-bounce queue grouped by direction class inside each 128-path tile (1: octant, 2: octant x major axis, 3: two sign bits; 0: off)
 #endif
+#define RT_OCT_CLASSES (RT_SHADE_OCTSORT == 2 ? 24u : (RT_SHADE_OCTSORT == 3 ? 4u : 8u))
 #define RT_SHADE_CLASSES 32   // class 0 = miss, 1..30 = material id (mod 30), 31 = no path (tail of the last tile)
 
 // Material-sorted closest-hit shading (north_star: "a material-sorted ... closest-hit shading pass").  The reference's
@@ -680,27 +681,42 @@ __global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) shade_kernel(DScene 
             if (hit_mask && lane == 0) atomicAdd(hit_count, (uint32_t)__popc(hit_mask));
         }
 #if RT_SHADE_SORT && RT_SHADE_OCTSORT
-        {   // compaction of the tile's surviving paths, grouped by the direction octant of the next ray: the traversal kernel
+        {   // compaction of the tile's surviving paths, grouped by the direction class of the next ray: the traversal kernel
             // refills its warps with runs of consecutive rays, and rays that start close together (one 128-path tile) and
             // leave into the same octant walk the same part of the tree in the same order
-            const uint32_t key = r.alive ? (7u - octant_inv(r.next.dir)) : 8u;
+            uint32_t key = RT_OCT_CLASSES;
+            if (r.alive) {
+                const uint32_t oct = 7u - octant_inv(r.next.dir);
+#if RT_SHADE_OCTSORT == 1
+                key = oct;                                                     // 8 classes: the octant
+#elif RT_SHADE_OCTSORT == 2
+                const float ax = fabsf(r.next.dir.x), ay = fabsf(r.next.dir.y), az = fabsf(r.next.dir.z);
+                key = oct * 3u + (ax >= ay && ax >= az ? 0u : (ay >= az ? 1u : 2u));   // 24 classes: octant x major axis
+#else
+                key = oct >> 1;                                                // 4 classes: signs of x and y
+#endif
+            }
             __syncthreads();                                   // s_hist / s_wsum are free again
-            if (threadIdx.x < 36u) s_hist[threadIdx.x] = 0u;
+            s_hist[threadIdx.x] = 0u;
             __syncthreads();
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
             const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
             if (rank == 0u) s_hist[key * 4u + warp] = (uint32_t)__popc(peers);
             __syncthreads();
-            if (warp == 0u) {                                  // exclusive scan of the 32 (octant-major, warp-minor) counts, one atomic per tile
-                const uint32_t v = s_hist[lane];
-                uint32_t incl = v;
+            // exclusive scan of the (class-major, warp-minor) counts, one entry per thread; the dead class sorts last
+            const uint32_t v = s_hist[threadIdx.x];
+            uint32_t incl = v;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
-                if (lane == 31u) s_wsum[0] = incl ? atomicAdd(out_count, incl) : 0u;
-                s_hist[lane] = incl - v;
-            }
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += o; }
+            if (lane == 31u) s_wsum[warp] = incl;
             __syncthreads();
-            const uint32_t slot = s_wsum[0] + s_hist[(key & 7u) * 4u + warp] + rank;
+            uint32_t base = 0u;
+            for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
+            s_hist[threadIdx.x] = base + incl - v;
+            __syncthreads();
+            if (threadIdx.x == 0u) { const uint32_t n_alive = s_hist[RT_OCT_CLASSES * 4u]; s_wsum[0] = n_alive ? atomicAdd(out_count, n_alive) : 0u; }   // one atomic per tile
+            __syncthreads();
+            const uint32_t slot = s_wsum[0] + s_hist[key * 4u + warp] + rank;
             __syncthreads();                                   // the next tile's sort reuses s_hist / s_wsum
             if (r.alive) store_path(qout, slot, r.next);
         }
