@@ -316,6 +316,11 @@ def run_ours(args):
     desc = build_scene_desc()
     ctx = core.Context(WIDTH, HEIGHT, device=local)
     t0 = time.perf_counter(); scene = core.Scene(ctx, desc); build_s = time.perf_counter() - t0
+    first_build_ms = float(scene.bvh_info().build_ms)
+    # the first build of a process also pays one-time costs (module loading, the first large allocations of a fresh GPU):
+    # 3 ms to > 100 ms from run to run.  The scene is built a second time and that (warm) build is the reported figure.
+    scene.close()
+    t0 = time.perf_counter(); scene = core.Scene(ctx, desc); build_s = time.perf_counter() - t0
     info = scene.bvh_info()
     cam = host.Camera(WIDTH, HEIGHT).set(position=CAM_POS)
     gui = make_gui()
@@ -584,7 +589,7 @@ def run_ours(args):
                            "exchange": exchange,
                            "frames_in_flight": NF,
                            "bvh": {"nodes": int(info.blas_nodes), "depth": int(info.max_depth_blas), "bytes": int(info.bytes), "build_s": build_s,
-                                   "build_ms_device": float(info.build_ms), "tlas_ms_device": float(info.tlas_ms)}},
+                                   "build_ms_device": float(info.build_ms), "build_ms_device_first": first_build_ms, "tlas_ms_device": float(info.tlas_ms)}},
                 "samples_per_s": samples_all / (ms_max * 1e-3),
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 324 + (16384 if POSE is not None else 0), "d2h_bytes_per_step": WIDTH * HEIGHT * 4},
                 "refit": ((upd | {"skinning_gbs": 256.0 * desc.n_vertices / (upd["skin_ms"] * 1e-3) / 1e9 if upd["skin_ms"] > 0 else None,
