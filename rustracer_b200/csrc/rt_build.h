@@ -501,7 +501,8 @@ inline int build_wide_bvh(const DAabb* prim_boxes, uint32_t n, BuildScratch& sc,
             rt_atomic_min(&bounds[k], float_to_ordered(c)); rt_atomic_max(&bounds[3 + k], float_to_ordered(c));
         }
     });
-    const float max_aspect = getenv("RT_B200_MORTON_ASPECT") ? (float)atof(getenv("RT_B200_MORTON_ASPECT")) : RT_MORTON_MAX_ASPECT;   // (env: A/B knob; 1e30 = per axis)
+    float max_aspect = RT_MORTON_MAX_ASPECT;
+    if (const char* e = getenv("RT_B200_MORTON_ASPECT")) { const float v = (float)atof(e); if (v >= 1.0f) max_aspect = v; }   // (env: A/B knob; 1e30 = per axis)
     rt_launch(n, stream, RT_LAMBDA(size_t i) {
         const DAabb b = prim_boxes[i];
         uint32_t q[3];

@@ -464,7 +464,8 @@ static int build_tlas(rt_scene* s) {
     instance_boxes(s, ne);
     const uint32_t* recd = s->d_entry_rec; DAabb* ib = s->d_inst_boxes;
     WideOut out; out.nodes = s->d_tlas_nodes; out.prim_order = s->d_tlas_prims; out.node_box = s->d_tlas_box; out.node_parent = s->d_tlas_parent; out.max_nodes = ne ? ne : 1u;
-    out.leaf_max = getenv("RT_B200_TLAS_LEAF") ? (uint32_t)atoi(getenv("RT_B200_TLAS_LEAF")) : 1u;   // (env: A/B knob)
+    out.leaf_max = 1u;
+    if (const char* e = getenv("RT_B200_TLAS_LEAF")) { const int v = atoi(e); out.leaf_max = (uint32_t)(v < 1 ? 1 : (v > (int)RT_LEAF_MAX ? (int)RT_LEAF_MAX : v)); }   // (env: A/B knob)
     WideBvhInfo info;
     const int e = build_wide_bvh(ib, ne, s->scratch, out, st, &info);
     if (e) return fail("TLAS build failed (code " + std::to_string(e) + ")");

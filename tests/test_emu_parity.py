@@ -87,3 +87,23 @@ def test_flat_scene_morton_cells_stay_cubic(monkeypatch):
         out[name] = (st.nodes / max(st.rays_extend, 1), ctx.readback()[0].copy())
     assert np.array_equal(out["cubic"][1], out["per_axis"][1])
     assert out["cubic"][0] < 0.9 * out["per_axis"][0], (out["cubic"][0], out["per_axis"][0])
+
+
+def test_tlas_leaves_hold_one_instance():
+    """rt_scene_read_nodes(geo = -2) returns the TLAS; every TLAS leaf slot holds exactly one instance (rt_build.h
+    WideOut::leaf_max = 1: an instance is only entered after its own box test), BLAS leaf slots hold up to three triangles."""
+    import numpy as np
+    from rustracer_b200 import core, scenes
+    d = scenes.instanced_foliage(n_side=12, tris_per_mesh=600, cards=200, tex_size=16)    # 200 cards = 400 triangles: not baked
+    ctx = core.Context(8, 8, api=emu_api()); sc = core.Scene(ctx, d)
+    def leaf_counts(nodes):
+        meta = nodes[:, 6:8].copy().view(np.uint8).reshape(-1, 8)
+        planes = nodes[:, 8:32].reshape(-1, 3, 8)
+        valid = ((planes & 0xFFFF) != 0x7F80).all(1)
+        inner = (meta & 0x18) == 0x18
+        leaf = valid & ~inner
+        return np.array([bin(int(m) >> 5).count("1") for m in meta[leaf]])
+    tl = leaf_counts(sc.read_nodes(-2))
+    assert len(tl) == 288 and (tl == 1).all()                     # 144 bodies + 144 card sets (+ the ground is baked)
+    bl = leaf_counts(sc.read_nodes(0))
+    assert bl.max() == 3 and bl.min() >= 1
