@@ -1,3 +1,6 @@
+"""Developer probe (CPU only): decodes the TLAS of config 3 built by the host emulation (rt_scene_read_nodes(-2)) and prints
+its child-box surface areas / fan-out: how the Morton normalisation was diagnosed (run with RT_B200_MORTON_ASPECT=1e30 for the
+round-1 tree).  Needs the profile build of the emulation library (see emu_profile.py)."""
 import ctypes as C, sys, os
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
