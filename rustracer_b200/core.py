@@ -210,7 +210,7 @@ class Scene:
         return v
 
     def read_nodes(self, geo: int = -1) -> np.ndarray:
-        """128-byte wide nodes of one BLAS as (n, 32) uint32 (geo < 0: the merged world-space BLAS)."""
+        """128-byte wide nodes as (n, 32) uint32: geo >= 0 that geometry's BLAS, -1 the merged world-space BLAS, -2 the TLAS."""
         n = F.c_u32()
         self.api.check(self.api.rt_scene_read_nodes(self._h, geo, None, 0, C.byref(n)))
         out = np.zeros((n.value, 32), np.float32)
